@@ -1,0 +1,152 @@
+"""Synthetic weights and inputs of the reference's default shapes.
+
+There is no network for checkpoints or datasets, so parity tests, smoke() and bench.py
+run on random-init weights keyed exactly like the reference ``SalUNet.state_dict()``
+(215 tensors, /root/reference/models/saliency_decoder/sal_unet.py:146-277) and on
+synthetic clips shaped like cfgs/audio_visual.py (224x384 maps, MViT feature pyramid
+of diff_model.py:106-111, VGGish/AudioAttnNet features [B,512,9,7,12]).
+
+All tensors are drawn from seeded CPU generators so that the CUDA path, the oracle
+and the committed golden fixtures see bit-identical inputs.
+"""
+import math
+
+import torch
+
+STAGE_C = (768, 384, 192, 96)
+STAGE_HW = ((7, 12), (14, 24), (28, 48), (56, 96))
+STAGE_S = (2, 4, 8, 16)
+IMG_HW = (224, 384)
+AUDIO_SHAPE = (512, 9, 7, 12)
+
+
+def state_dict_spec():
+    """[(key, shape)] in the reference's state_dict order."""
+    spec = []
+    dec = "invpt_decoder."
+    for i, c in enumerate(STAGE_C):
+        spec += [(dec + "norm_mts.%d.weight" % i, (c,)), (dec + "norm_mts.%d.bias" % i, (c,))]
+    for i, c in enumerate(STAGE_C):
+        spec.append((dec + "redu_chan_up.%d.proj.0.weight" % i, (768, c, 5, 1, 1)))
+    for i, c in enumerate(STAGE_C):
+        st = dec + "mid_stages.%d." % i
+        if i > 0:
+            cin = STAGE_C[i - 1]
+            pe = st + "patch_embed.0.proj."
+            for conv, bn, ci in (("1", "2", cin), ("4", "5", c)):
+                spec.append((pe + conv + ".weight", (c, ci, 3, 3)))
+                spec += [(pe + bn + ".weight", (c,)), (pe + bn + ".bias", (c,)),
+                         (pe + bn + ".running_mean", (c,)), (pe + bn + ".running_var", (c,)),
+                         (pe + bn + ".num_batches_tracked", ())]
+        b = st + "blocks.0."
+        s = STAGE_S[i]
+        spec += [(b + "mlp.fc1.weight", (2 * c, c)), (b + "mlp.fc1.bias", (2 * c,)),
+                 (b + "mlp.fc2.weight", (c, 2 * c)), (b + "mlp.fc2.bias", (c,)),
+                 (b + "norm.weight", (c,)), (b + "norm.bias", (c,)),
+                 (b + "attn.conv_proj_q.conv.weight", (c, 1, 3, 3, 3)),
+                 (b + "attn.conv_proj_q.bn.weight", (c,)), (b + "attn.conv_proj_q.bn.bias", (c,)),
+                 (b + "attn.conv_proj_k.conv.weight", (c, 1, 1, s, s)),
+                 (b + "attn.conv_proj_k.bn.weight", (c,)), (b + "attn.conv_proj_k.bn.bias", (c,)),
+                 (b + "attn.conv_proj_v.conv.weight", (c, 1, 1, s, s)),
+                 (b + "attn.conv_proj_v.bn.weight", (c,)), (b + "attn.conv_proj_v.bn.bias", (c,))]
+        for n in ("proj_q", "proj_k", "proj_v", "proj"):
+            spec += [(b + "attn.%s.weight" % n, (c, c)), (b + "attn.%s.bias" % n, (c,))]
+        spec += [(b + "norm2.weight", (c,)), (b + "norm2.bias", (c,)),
+                 (b + "align_conv.weight", (c, 512, 1, 1)), (b + "align_conv.bias", (c,))]
+    spec += [(dec + "mt_proj.0.weight", (96, 768, 3, 3)), (dec + "mt_proj.0.bias", (96,)),
+             (dec + "mt_proj.1.weight", (96,)), (dec + "mt_proj.1.bias", (96,)),
+             (dec + "mt_proj.1.running_mean", (96,)), (dec + "mt_proj.1.running_var", (96,)),
+             (dec + "mt_proj.1.num_batches_tracked", ()),
+             ("logits.linear_pred.weight", (1, 96, 1, 1)), ("logits.linear_pred.bias", (1,)),
+             ("temb.dense.0.weight", (384, 96)), ("temb.dense.0.bias", (384,)),
+             ("temb.dense.1.weight", (384, 384)), ("temb.dense.1.bias", (384,)),
+             ("conv_in.weight", (96, 1, 3, 3)), ("conv_in.bias", (96,)),
+             ("down1.conv.weight", (96, 96, 3, 3)), ("down1.conv.bias", (96,))]
+    cin = 96
+    for i, c in enumerate((192, 384, 768)):
+        r = "res_encoder.%d.0." % i
+        spec += [(r + "norm1.weight", (cin,)), (r + "norm1.bias", (cin,)),
+                 (r + "conv1.weight", (c, cin, 3, 3)), (r + "conv1.bias", (c,)),
+                 (r + "temb_proj.weight", (c, 384)), (r + "temb_proj.bias", (c,)),
+                 (r + "norm2.weight", (c,)), (r + "norm2.bias", (c,)),
+                 (r + "conv2.weight", (c, c, 3, 3)), (r + "conv2.bias", (c,)),
+                 (r + "nin_shortcut.weight", (c, cin, 1, 1)), (r + "nin_shortcut.bias", (c,)),
+                 ("res_encoder.%d.1.conv.weight" % i, (c, c, 3, 3)), ("res_encoder.%d.1.conv.bias" % i, (c,))]
+        cin = c
+    return spec
+
+
+def _is_norm_affine(key):
+    return (".norm" in key or "norm_mts" in key or ".bn." in key or key.endswith(".weight") and False)
+
+
+def make_state_dict(kind="wide", seed=0):
+    """Random weights keyed like the reference.
+
+    kind="ref_init": what ``SalUNet.init_weights`` produces (sal_unet.py:263-277): every
+        conv/linear weight ~ N(0, 0.01), biases 0, LayerNorm/BatchNorm weight 1 bias 0, BN
+        running stats (0, 1), GroupNorm default affine (1, 0).  The output map is then nearly
+        flat (span ~0.04), which makes min-max-normalised comparisons very strict.
+    kind="wide": fan-in scaled weights, non-zero biases, randomised norm affines and BN
+        running statistics, so that every term of every formula influences the output
+        (a test on ref_init alone would not notice a dropped bias or a swapped BN stat).
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in state_dict_spec():
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros((), dtype=torch.int64)
+            continue
+        leaf = key.rsplit(".", 1)[1]
+        parent = key.rsplit(".", 1)[0]
+        is_norm = (len(shape) == 1 and leaf in ("weight", "bias") and
+                   (".norm" in key or "norm_mts" in key or parent.endswith(".bn")
+                    or parent.endswith("proj.2") or parent.endswith("proj.5") or parent.endswith("mt_proj.1")))
+        if kind == "ref_init":
+            if leaf == "running_mean":
+                v = torch.zeros(shape)
+            elif leaf == "running_var":
+                v = torch.ones(shape)
+            elif is_norm:
+                v = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+            elif leaf == "bias":
+                v = torch.zeros(shape)
+            else:
+                v = torch.randn(shape, generator=g) * 0.01
+        elif kind == "wide":
+            if leaf == "running_mean":
+                v = torch.randn(shape, generator=g) * 0.1
+            elif leaf == "running_var":
+                v = 0.5 + torch.rand(shape, generator=g)
+            elif is_norm:
+                v = (1.0 + 0.2 * torch.randn(shape, generator=g)) if leaf == "weight" \
+                    else 0.1 * torch.randn(shape, generator=g)
+            elif leaf == "bias":
+                v = 0.05 * torch.randn(shape, generator=g)
+            else:
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                v = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+        else:
+            raise ValueError(kind)
+        sd[key] = v.float().contiguous()
+    return sd
+
+
+def make_inputs(batch, audio=True, seed=1234):
+    """Seeded synthetic clip batch: x_T, the four MViT-shaped feature tensors and the
+    audio feature tensor.  Clip ``i`` uses generator seed ``seed + i`` so that a clip's
+    inputs do not depend on which rank / micro-batch it lands in."""
+    xs, feats, auds = [], [[] for _ in range(4)], []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed + i)
+        xs.append(torch.randn((1, 1) + IMG_HW, generator=g))
+        for j, (c, (h, w)) in enumerate(zip(STAGE_C, STAGE_HW)):
+            feats[j].append(torch.randn((1, c, 8, h, w), generator=g))
+        if audio:
+            auds.append(torch.randn((1,) + AUDIO_SHAPE, generator=g))
+    x = torch.cat(xs, 0)
+    feat_list = [torch.cat(f, 0) for f in feats]
+    aud = torch.cat(auds, 0) if audio else None
+    return x, feat_list, aud

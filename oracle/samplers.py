@@ -1,0 +1,249 @@
+"""ORACLE (test infrastructure, not product code): fp32 restatement of the reference's
+sampling loops around a denoiser callable ``model(x, t) -> prediction``.
+
+Restates
+  get_beta_schedule('cosine') + tables   models/diffusion_decoder/diffusion_utils.py:34-41,
+                                         diffusion_trainer.py:47-76
+  DiffusionTrainer.sample_ddim           diffusion_trainer.py:439-480 (+ :434-437)
+  NoiseScheduleVP (discrete)             models/dpm_solver/sampler.py:6-167
+  interpolate_fn                         sampler.py:1255-1294
+  model_wrapper (uncond; noise/x_start)  sampler.py:170-334
+  DPM_Solver.sample, multistep path      sampler.py:1048-1247, updates :548-593, :797-905,
+                                         data_prediction_fn :434-443
+
+Scalars are kept as 1-element fp32 torch tensors and combined in the reference's
+expression order so that the restatement tracks the reference to fp32 round-off.
+Pinned against the imported reference in tests/test_oracle_vs_reference.py.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+# ----------------------------------------------------------------------------- schedule
+def cosine_betas(n=1000):
+    """diffusion_utils.py:34-41 (float64 numpy)."""
+    step = n + 1
+    s = 0.008
+    x = np.linspace(0, step, step)
+    ac = np.cos(((x / step) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = 1 - (ac[1:] / ac[:-1])
+    return np.clip(betas, a_min=0, a_max=0.999)
+
+
+def betas_fp32(n=1000):
+    return torch.tensor(cosine_betas(n), dtype=torch.float32)
+
+
+class DdimTables:
+    """diffusion_trainer.py:47-76: fp32 cumprod of fp32 (1 - beta)."""
+
+    def __init__(self, betas=None):
+        betas = betas_fp32() if betas is None else betas
+        self.betas = betas
+        self.alphas_hat = (1.0 - betas).cumprod(dim=0)
+        self.sqrt_alphas_hat = torch.sqrt(self.alphas_hat)
+        self.sqrt_recip_alphas_hat = torch.sqrt(1.0 / self.alphas_hat)
+        self.sqrt_recipm1_alphas_hat = torch.sqrt(1.0 / self.alphas_hat - 1)
+        self.num_timesteps = betas.shape[0]
+
+
+def sample_ddim(model, x, timesteps, eta=0.0, training_target="x0", tables=None, noise_fn=None):
+    """diffusion_trainer.py:439-480.  ``model(x, t_int64[B])``.  ``noise_fn(x)`` supplies the
+    eta-noise (default randn_like; with eta == 0 it is multiplied by c1 == 0)."""
+    tb = DdimTables() if tables is None else tables
+    skip = tb.num_timesteps // timesteps
+    seq = list(range(0, tb.num_timesteps, skip))
+    seq_next = [-1] + seq[:-1]
+    n = x.shape[0]
+    for time, time_next in zip(reversed(seq), reversed(seq_next)):
+        t = torch.full((n,), time, dtype=torch.int64)
+        alpha = tb.alphas_hat[time]
+        alpha_next = tb.alphas_hat[time_next]
+        if training_target == "x0":
+            x_start = model(x, t)
+            pred_noise = (tb.sqrt_recip_alphas_hat[time] * x - x_start) / tb.sqrt_recipm1_alphas_hat[time]
+        else:
+            pred_noise = model(x, t)
+            x_start = (x - pred_noise * (1 - alpha).sqrt()) / alpha.sqrt()
+        if time_next < 0:
+            x = x_start
+            continue
+        c1 = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c2 = ((1 - alpha_next) - c1 ** 2).sqrt()
+        z = torch.randn_like(x) if noise_fn is None else noise_fn(x)
+        x = tb.sqrt_alphas_hat[time_next] * x_start + c1 * z + c2 * pred_noise
+    return x
+
+
+# ----------------------------------------------------------------------------- DPM-solver
+def _interp(x, xp, yp):
+    """sampler.py:1255-1294 for a 1-element x and ascending 1-D xp: piecewise linear, the
+    outermost segments extended beyond the ends."""
+    K = xp.shape[0]
+    idx = int(torch.searchsorted(xp, x.reshape(())).item())   # number of keypoints < x
+    if idx == 0:
+        i0 = 0
+    elif idx == K:
+        i0 = K - 2
+    else:
+        i0 = idx - 1
+    x0, x1, y0, y1 = xp[i0], xp[i0 + 1], yp[i0], yp[i0 + 1]
+    return y0 + (x - x0) * (y1 - y0) / (x1 - x0)
+
+
+class NoiseScheduleDiscrete:
+    """sampler.py:71-82,114-167 with schedule='discrete', betas given."""
+
+    def __init__(self, betas):
+        log_alphas = 0.5 * torch.log(1 - betas).cumsum(dim=0)
+        log_sigmas = 0.5 * torch.log(1.0 - torch.exp(2.0 * log_alphas))
+        lambs = log_alphas - log_sigmas
+        idx = int(torch.searchsorted(torch.flip(lambs, [0]), torch.tensor(-5.1)).item())
+        if idx > 0:
+            log_alphas = log_alphas[:-idx]
+        self.T = 1.0
+        self.log_alpha_array = log_alphas.float()
+        self.total_N = log_alphas.shape[0]
+        self.t_array = torch.linspace(0.0, 1.0, self.total_N + 1)[1:].float()
+
+    def log_alpha(self, t):
+        return _interp(t, self.t_array, self.log_alpha_array)
+
+    def alpha(self, t):
+        return torch.exp(self.log_alpha(t))
+
+    def sigma(self, t):
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.log_alpha(t)))
+
+    def lam(self, t):
+        la = self.log_alpha(t)
+        return la - 0.5 * torch.log(1.0 - torch.exp(2.0 * la))
+
+    def inverse_lambda(self, lamb):
+        log_alpha = -0.5 * torch.logaddexp(torch.zeros(()), -2.0 * lamb)
+        return _interp(log_alpha, torch.flip(self.log_alpha_array, [0]), torch.flip(self.t_array, [0]))
+
+
+def dpm_time_steps(ns, steps, skip_type="logSNR"):
+    """sampler.py:454-481."""
+    t_T, t_0 = ns.T, 1.0 / ns.total_N
+    if skip_type == "logSNR":
+        lam_T = ns.lam(torch.tensor(t_T))
+        lam_0 = ns.lam(torch.tensor(t_0))
+        ls = torch.linspace(lam_T.item(), lam_0.item(), steps + 1)
+        return [ns.inverse_lambda(l) for l in ls]
+    if skip_type == "time_uniform":
+        return list(torch.linspace(t_T, t_0, steps + 1))
+    if skip_type == "time_quadratic":
+        return list(torch.linspace(t_T ** 0.5, t_0 ** 0.5, steps + 1).pow(2))
+    raise ValueError(skip_type)
+
+
+def sample_dpm(model, x, betas=None, steps=9, order=2, algorithm_type="dpmsolver",
+               model_type="x_start", skip_type="logSNR", lower_order_final=False,
+               denoise_to_zero=True, solver_type="dpmsolver", return_model_times=False):
+    """DPM_Solver.sample(method='multistep') driven through model_wrapper(uncond).
+    ``model(x, t_float[B])`` is the raw network; model_type says what it predicts."""
+    betas = betas_fp32() if betas is None else betas
+    ns = NoiseScheduleDiscrete(betas)
+    n = x.shape[0]
+    model_times = []
+
+    def noise_pred(x, t):
+        t_in = (t - 1.0 / ns.total_N) * 1000.0
+        model_times.append(float(t_in))
+        out = model(x, t_in.reshape(1).expand(n))
+        if model_type == "noise":
+            return out
+        if model_type == "x_start":
+            return (x - ns.alpha(t) * out) / ns.sigma(t)
+        raise ValueError(model_type)
+
+    def data_pred(x, t):
+        noise = noise_pred(x, t)
+        return (x - ns.sigma(t) * noise) / ns.alpha(t)
+
+    def model_fn(x, t):
+        return data_pred(x, t) if algorithm_type == "dpmsolver++" else noise_pred(x, t)
+
+    def update(x, ms, ts, t, k):
+        lam_t, lam_0 = ns.lam(t), ns.lam(ts[-1])
+        h = lam_t - lam_0
+        la_0, la_t = ns.log_alpha(ts[-1]), ns.log_alpha(t)
+        sig_0, sig_t = ns.sigma(ts[-1]), ns.sigma(t)
+        alpha_t = torch.exp(la_t)
+        pp = algorithm_type == "dpmsolver++"
+        phi_1 = torch.expm1(-h) if pp else torch.expm1(h)
+        if k == 1:
+            if pp:
+                return sig_t / sig_0 * x - alpha_t * phi_1 * ms[-1]
+            return torch.exp(la_t - la_0) * x - (sig_t * phi_1) * ms[-1]
+        if k == 2:
+            h_0 = lam_0 - ns.lam(ts[-2])
+            r0 = h_0 / h
+            D1 = (1.0 / r0) * (ms[-1] - ms[-2])
+            if pp:
+                if solver_type == "dpmsolver":
+                    return (sig_t / sig_0) * x - (alpha_t * phi_1) * ms[-1] - 0.5 * (alpha_t * phi_1) * D1
+                return (sig_t / sig_0) * x - (alpha_t * phi_1) * ms[-1] + (alpha_t * (phi_1 / h + 1.0)) * D1
+            if solver_type == "dpmsolver":
+                return torch.exp(la_t - la_0) * x - (sig_t * phi_1) * ms[-1] - 0.5 * (sig_t * phi_1) * D1
+            return torch.exp(la_t - la_0) * x - (sig_t * phi_1) * ms[-1] - (sig_t * (phi_1 / h - 1.0)) * D1
+        if k == 3:
+            lam_1, lam_2 = ns.lam(ts[-2]), ns.lam(ts[-3])
+            h_1, h_0 = lam_1 - lam_2, lam_0 - lam_1
+            r0, r1 = h_0 / h, h_1 / h
+            D1_0 = (1.0 / r0) * (ms[-1] - ms[-2])
+            D1_1 = (1.0 / r1) * (ms[-2] - ms[-3])
+            D1 = D1_0 + (r0 / (r0 + r1)) * (D1_0 - D1_1)
+            D2 = (1.0 / (r0 + r1)) * (D1_0 - D1_1)
+            if pp:
+                phi_2 = phi_1 / h + 1.0
+                phi_3 = phi_2 / h - 0.5
+                return (sig_t / sig_0) * x - (alpha_t * phi_1) * ms[-1] + (alpha_t * phi_2) * D1 - (alpha_t * phi_3) * D2
+            phi_2 = phi_1 / h - 1.0
+            phi_3 = phi_2 / h - 0.5
+            return torch.exp(la_t - la_0) * x - (sig_t * phi_1) * ms[-1] - (sig_t * phi_2) * D1 - (sig_t * phi_3) * D2
+        raise ValueError(k)
+
+    assert steps >= order
+    ts_all = dpm_time_steps(ns, steps, skip_type)
+    t_prev = [ts_all[0]]
+    m_prev = [model_fn(x, ts_all[0])]
+    for step in range(1, order):
+        t = ts_all[step]
+        x = update(x, m_prev, t_prev, t, step)
+        t_prev.append(t)
+        m_prev.append(model_fn(x, t))
+    for step in range(order, steps + 1):
+        t = ts_all[step]
+        k = min(order, steps + 1 - step) if (lower_order_final and steps < 10) else order
+        x = update(x, m_prev, t_prev, t, k)
+        t_prev = t_prev[1:] + [t]
+        if step < steps:
+            m_prev = m_prev[1:] + [model_fn(x, t)]
+        else:
+            m_prev = m_prev[1:] + [None]
+    if denoise_to_zero:
+        x = data_pred(x, torch.ones(()) * (1.0 / ns.total_N))
+    if return_model_times:
+        return x, model_times
+    return x
+
+
+# ----------------------------------------------------------------------------- post-processing
+def inverse_data_transform(x):
+    """datasets/__init__.py:26-35 with cfgs/diffusion.yml:1-8 (no rescale, no logit)."""
+    return torch.clamp(x, 0.0, 1.0)
+
+
+def minmax_map(x):
+    """Per-clip min-max normalisation to [0,1] (util/utils.py:11-16 before the uint8 cast;
+    metrics/utils.py:11-13) -- the space the 1e-2 max-abs tolerance is stated in."""
+    flat = x.reshape(x.shape[0], -1)
+    lo = flat.min(dim=1, keepdim=True).values
+    hi = flat.max(dim=1, keepdim=True).values
+    return ((flat - lo) / (hi - lo)).reshape(x.shape)

@@ -1,0 +1,71 @@
+"""CPU: the oracle restatement (oracle/) against the committed golden fixtures that were
+generated from the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diff_sal_b200 import synth
+from oracle import salunet, samplers
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 5e-6          # fp32 re-association only (restatement vs reference modules)
+
+
+def gold(name):
+    return torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["y"])
+
+
+@pytest.mark.parametrize("name,kind,audio,t", [
+    ("step_wide_av_t500", "wide", True, [500]),
+    ("step_wide_vis_t500", "wide", False, [500]),
+    ("step_refinit_av_t37", "ref_init", True, [37]),
+    ("step_wide_av_t886p9", "wide", True, [886.9]),
+])
+def test_single_evaluation(name, kind, audio, t):
+    sd = synth.make_state_dict(kind)
+    x, feats, aud = synth.make_inputs(1, audio=audio)
+    y = salunet.forward(sd, x, torch.tensor(t), feats, aud)
+    assert (y - gold(name)).abs().max().item() < TOL
+
+
+def _net(kind, audio):
+    sd = synth.make_state_dict(kind)
+    x, feats, aud = synth.make_inputs(1, audio=audio)
+    return x, (lambda x_, t_: salunet.forward(sd, x_, t_, feats, aud))
+
+
+@pytest.mark.parametrize("S", [1, 5])
+def test_ddim(S):
+    x, net = _net("wide", True)
+    y = samplers.sample_ddim(net, x, S, eta=0.0, training_target="x0")
+    assert (y - gold("ddim%d_wide_av" % S)).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("name,algo,mtype,tol", [
+    ("dpm_wide_av_xstart_o2_s4", "dpmsolver", "x_start", TOL),
+    ("dpmpp_wide_av_xstart_o2_s4", "dpmsolver++", "x_start", TOL),
+    ("dpm_wide_av_noise_o2_s4", "dpmsolver", "noise", 2e-3),   # values reach +-670
+])
+def test_dpm_solver(name, algo, mtype, tol):
+    x, net = _net("wide", True)
+    y = samplers.sample_dpm(net, x, steps=4, order=2, algorithm_type=algo, model_type=mtype)
+    assert (y - gold(name)).abs().max().item() < tol
+
+
+def test_config1_visual_only_dpm():
+    """BASELINE config 1: visual-only, batch 1, reference init, DPM-solver multistep-2, 10 NFE."""
+    x, net = _net("ref_init", False)
+    y = samplers.sample_dpm(net, x, steps=9, order=2, algorithm_type="dpmsolver", model_type="x_start")
+    assert (y - gold("cfg1_dpm_refinit_vis_xstart_o2_s9")).abs().max().item() < TOL
+
+
+def test_visual_only_is_noise_invariant():
+    """in visual-only eval mode the output does not depend on x_t or t (only frames
+    0..4 reach ReduceTemp and the noise slice is frame 8)."""
+    sd = synth.make_state_dict("wide")
+    x, feats, _ = synth.make_inputs(1, audio=False)
+    a = salunet.forward(sd, x, torch.tensor([500]), feats, None)
+    b = salunet.forward(sd, torch.randn_like(x), torch.tensor([3]), feats, None)
+    assert torch.equal(a, b)

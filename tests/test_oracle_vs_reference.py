@@ -1,0 +1,106 @@
+"""CPU, build container only: the oracle restatement against the imported, unmodified
+reference (skipped where /root/reference does not exist, e.g. on the GPU box)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from diff_sal_b200 import synth
+from oracle import metrics, ref_loader, salunet, samplers
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+
+def _toy(x, t):
+    return torch.tanh(0.7 * x + 0.001 * t.float()[:, None, None, None]) * 0.5 + 0.1 * torch.roll(x, 1, -1)
+
+
+def test_state_dict_spec_matches_reference():
+    ref = ref_loader.build_salunet().state_dict()
+    spec = synth.state_dict_spec()
+    assert [k for k, _ in spec] == list(ref.keys())
+    for k, s in spec:
+        assert tuple(ref[k].shape) == tuple(s), k
+
+
+def test_betas_bit_exact():
+    ns = ref_loader.load()
+    rb = ns.to_torch(ns.get_beta_schedule(beta_schedule="cosine", beta_start=1e-4, beta_end=0.02,
+                                          num_diffusion_timesteps=1000))
+    assert torch.equal(rb, samplers.betas_fp32())
+
+
+@pytest.mark.parametrize("kind", ["wide", "ref_init"])
+@pytest.mark.parametrize("audio", [True, False])
+def test_forward_batch2(kind, audio):
+    m = ref_loader.build_salunet()
+    sd = synth.make_state_dict(kind)
+    m.load_state_dict(sd, strict=True)
+    x, feats, aud = synth.make_inputs(2, audio=audio)
+    t = torch.tensor([37, 812])
+    with torch.no_grad():
+        ref = m(x, t, [f.clone() for f in feats], aud)
+    assert (salunet.forward(sd, x, t, feats, aud) - ref).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize("algo", ["dpmsolver", "dpmsolver++"])
+@pytest.mark.parametrize("mtype", ["x_start", "noise"])
+@pytest.mark.parametrize("order,steps,lof", [(2, 9, False), (1, 4, False), (3, 7, False), (2, 5, True),
+                                              (3, 6, True), (1, 1, False), (2, 24, False)])
+def test_dpm_solver_bit_exact_on_toy_net(algo, mtype, order, steps, lof):
+    ns = ref_loader.load()
+    betas = samplers.betas_fp32()
+    # the reference's x_start wrapper only broadcasts for batch 1 (sampler.py:290-292)
+    x = torch.randn(1 if mtype == "x_start" else 2, 1, 8, 8, generator=torch.Generator().manual_seed(1))
+    nsv = ns.NoiseScheduleVP(schedule="discrete", betas=betas)
+    mf = ns.model_wrapper(lambda x_, t_, img, **kw: _toy(x_, t_), nsv, model_type=mtype, model_kwargs={},
+                          guidance_type="uncond")
+    ref = ns.DPM_Solver(mf, nsv, algorithm_type=algo).sample(
+        x, None, steps=steps, order=order, skip_type="logSNR", method="multistep",
+        lower_order_final=lof, denoise_to_zero=True)
+    mine = samplers.sample_dpm(_toy, x, betas, steps=steps, order=order, algorithm_type=algo,
+                               model_type=mtype, lower_order_final=lof)
+    assert torch.equal(ref, mine)
+
+
+@pytest.mark.parametrize("target", ["x0", "noise"])
+@pytest.mark.parametrize("S,eta", [(1, 0.0), (5, 0.0), (10, 0.5), (25, 0.0)])
+def test_ddim_bit_exact_on_toy_net(target, S, eta):
+    ref_loader.load()
+    import diffusion_trainer as dt
+
+    class Dec(torch.nn.Module):
+        def forward(self, x, t, img, audio=None):
+            return _toy(x, t)
+
+    tb = samplers.DdimTables()
+    tr = dt.DiffusionTrainer.__new__(dt.DiffusionTrainer)
+    tr.device = torch.device("cpu")
+    tr.num_timesteps = 1000
+    tr.training_target = target
+    for k in ("alphas_hat", "sqrt_alphas_hat", "sqrt_recip_alphas_hat", "sqrt_recipm1_alphas_hat"):
+        setattr(tr, k, getattr(tb, k))
+    tr.config = types.SimpleNamespace(sampling=types.SimpleNamespace(timesteps=S, eta=eta))
+    tr.model = types.SimpleNamespace(module=types.SimpleNamespace(decoder_net=Dec()))
+    x = torch.randn(2, 1, 8, 8, generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(5)
+    ref = tr.sample_ddim(x, [torch.zeros(1)], None)
+    torch.manual_seed(5)
+    mine = samplers.sample_ddim(_toy, x, S, eta=eta, training_target=target)
+    assert torch.equal(ref, mine)
+
+
+def test_metrics_match_reference():
+    rm = ref_loader.load().metrics
+    rng = np.random.RandomState(0)
+    for i in range(2):
+        dens, fix = metrics.synthetic_ground_truth(i)
+        pred = rng.rand(224, 384) ** 3 + 0.3 * dens
+        np.random.seed(0)
+        a = rm.AUC_Judd(pred.copy(), fix)
+        np.random.seed(0)
+        assert abs(a - metrics.auc_judd(pred, fix)) < 1e-12
+        assert abs(rm.NSS(pred, fix) - metrics.nss(pred, fix)) < 1e-12
+        assert abs(rm.CC(pred, dens) - metrics.cc(pred, dens)) < 1e-12
+        assert abs(rm.SIM(pred, dens) - metrics.sim(pred, dens)) < 1e-12
