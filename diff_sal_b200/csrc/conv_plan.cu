@@ -1,0 +1,124 @@
+#include "conv_plan.cuh"
+
+#include <string.h>
+
+namespace dsb {
+
+static int pick_bn(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    for (int bn = 256; bn >= 16; bn -= 16)
+        if (N % bn == 0) return bn;
+    return 0;
+}
+
+// Choose the 128-pixel tile box (bw x bh x bf, powers of two) that wastes the fewest accumulator rows.
+static void pick_tile(int W, int H, int F, int* bw_log2, int* bh_log2) {
+    long best = -1;
+    int bx = 7, by = 0;
+    for (int lx = 7; lx >= 0; --lx) {
+        for (int ly = 0; lx + ly <= 7; ++ly) {
+            const int bw = 1 << lx, bh = 1 << ly, bf = 128 >> (lx + ly);
+            const long tiles = (long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((F + bf - 1) / bf);
+            if (best < 0 || tiles < best) {
+                best = tiles;
+                bx = lx;
+                by = ly;
+            }
+        }
+    }
+    *bw_log2 = bx;
+    *bh_log2 = by;
+}
+
+int conv_lower(const ConvOp& op, ConvLaunch* out) {
+    memset(out, 0, sizeof(*out));
+    GemmParams& p = out->p;
+    const int C = op.Cin;
+    const int bk = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
+    if (!bk) return -20;
+    const int bn = pick_bn(op.N);
+    if (!bn) return -21;
+    p.W = op.W; p.H = op.H; p.F = op.F;
+    pick_tile(op.W, op.H, op.F, &p.bw_log2, &p.bh_log2);
+    const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2, bf = 128 >> (p.bw_log2 + p.bh_log2);
+    p.tiles_x = (op.W + bw - 1) / bw;
+    p.tiles_y = (op.H + bh - 1) / bh;
+    p.tiles_f = (op.F + bf - 1) / bf;
+    p.cin_blocks = C / bk;
+    p.bk = bk;
+    p.N = op.N;
+    p.bn = bn;
+    p.ydim = 2;
+
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    const uint64_t e = 2;   // bytes per bf16
+    if (op.kind == CONV_3X3) {
+        p.taps = 9;
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                int* o = p.tap_off[dy * 3 + dx];
+                o[0] = 0; o[1] = (dx - 1) * op.dilation; o[2] = (dy - 1) * op.dilation; o[3] = 0;
+            }
+        dims[0] = C; dims[1] = op.W; dims[2] = op.H; dims[3] = 1; dims[4] = op.F;
+        strides[0] = C * e; strides[1] = (uint64_t)op.W * C * e; strides[2] = (uint64_t)op.H * op.W * C * e;
+        strides[3] = (uint64_t)op.H * op.W * C * e;
+        box[0] = bk; box[1] = bw; box[2] = bh; box[3] = 1; box[4] = bf;
+    } else if (op.kind == CONV_1X1) {
+        p.taps = 1;
+        dims[0] = C; dims[1] = op.W; dims[2] = op.H; dims[3] = 1; dims[4] = op.F;
+        strides[0] = C * e; strides[1] = (uint64_t)op.W * C * e; strides[2] = (uint64_t)op.H * op.W * C * e;
+        strides[3] = (uint64_t)op.H * op.W * C * e;
+        box[0] = bk; box[1] = bw; box[2] = bh; box[3] = 1; box[4] = bf;
+    } else if (op.kind == CONV_3X3_S2) {
+        // input [F, 2H, 2W, C] viewed as [F][H][2][W][2C]: x_in = 2x + dx -> (x + dx/2, parity dx%2)
+        p.taps = 9;
+        p.ydim = 3;
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                int* o = p.tap_off[dy * 3 + dx];
+                o[0] = (dx & 1) * C; o[1] = dx >> 1; o[2] = dy & 1; o[3] = dy >> 1;
+            }
+        const uint64_t Win = 2 * (uint64_t)op.W, Hin = 2 * (uint64_t)op.H;
+        dims[0] = 2 * C; dims[1] = op.W; dims[2] = 2; dims[3] = op.H; dims[4] = op.F;
+        strides[0] = 2 * C * e; strides[1] = Win * C * e; strides[2] = 2 * Win * C * e; strides[3] = Hin * Win * C * e;
+        box[0] = bk; box[1] = bw; box[2] = 1; box[3] = bh; box[4] = bf;
+    } else if (op.kind == CONV_TEMPORAL) {
+        if (op.kt < 1 || op.kt > 9 || op.kt > op.T) return -22;
+        p.taps = op.kt;
+        for (int t = 0; t < op.kt; ++t) {
+            int* o = p.tap_off[t];
+            o[0] = 0; o[1] = 0; o[2] = 0; o[3] = t;
+        }
+        dims[0] = C; dims[1] = op.W; dims[2] = op.H; dims[3] = op.T; dims[4] = op.F;
+        strides[0] = C * e; strides[1] = (uint64_t)op.W * C * e; strides[2] = (uint64_t)op.H * op.W * C * e;
+        strides[3] = (uint64_t)op.T * op.H * op.W * C * e;
+        box[0] = bk; box[1] = bw; box[2] = bh; box[3] = 1; box[4] = bf;
+    } else {
+        return -23;
+    }
+    int r = make_tensor_map(&out->tmA, op.A, 5, dims, strides, box);
+    if (r) return r;
+    const uint64_t K = (uint64_t)p.taps * C;
+    uint64_t wd[2] = {K, (uint64_t)op.N};
+    uint64_t ws[1] = {K * e};
+    uint32_t wb[2] = {(uint32_t)bk, (uint32_t)bn};
+    r = make_tensor_map(&out->tmB, op.Wt, 2, wd, ws, wb);
+    if (r) return r;
+
+    p.scale = op.scale; p.shift = op.shift; p.rowbias = op.rowbias; p.residual = op.residual;
+    p.act = op.act;
+    p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
+    p.ldo = op.ldo ? op.ldo : op.N;
+    p.out_fmul = op.out_fmul ? op.out_fmul : 1;
+    p.out_fadd = op.out_fadd;
+    p.head_w = op.head_w; p.head_b = op.head_b; p.out_head = op.out_head;
+    return 0;
+}
+
+int conv_run(const ConvLaunch& l, int num_sms, cudaStream_t stream) {
+    return gemm_launch(l.p, l.tmA, l.tmB, num_sms, stream);
+}
+
+}  // namespace dsb

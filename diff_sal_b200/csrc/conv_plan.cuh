@@ -1,0 +1,47 @@
+// Host-side description of one dense contraction (conv / linear) and its lowering to GemmParams + TMA maps.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace dsb {
+
+enum ConvKind {
+    CONV_3X3 = 0,        // 3x3, stride 1, dilation d, padding d           (A: [F,H,W,Cin])
+    CONV_3X3_S2 = 1,     // zero-pad right/bottom by 1, 3x3, stride 2      (A: [F,2H,2W,Cin], space-to-depth view)
+    CONV_1X1 = 2,        // 1x1 conv / token linear                        (A: [F,H,W,Cin])
+    CONV_TEMPORAL = 3    // (kt,1,1) conv over the first kt of T frames    (A: [F,T,H,W,Cin], F = clips)
+};
+
+struct ConvOp {
+    int kind;
+    int F, H, W;         // OUTPUT extent
+    int Cin, N;
+    int dilation;        // CONV_3X3 only
+    int T, kt;           // CONV_TEMPORAL only
+    const bf16* A;       // activations, channels-last bf16
+    const bf16* Wt;      // weights [N][taps*Cin], k = tap*Cin + c, tap = dy*3+dx (or t)
+    // epilogue (see GemmParams)
+    const float* scale;
+    const float* shift;
+    const float* rowbias;
+    const float* residual;
+    int act;
+    float* out_f32;
+    bf16* out_bf16;
+    int ldo;             // 0 -> N
+    int out_fmul;        // 0 -> 1
+    int out_fadd;
+    const float* head_w;
+    float head_b;
+    float* out_head;
+};
+
+struct ConvLaunch {
+    GemmParams p;
+    CUtensorMap tmA, tmB;
+};
+
+// Lowers `op`; returns 0 or a negative error.
+int conv_lower(const ConvOp& op, ConvLaunch* out);
+int conv_run(const ConvLaunch& l, int num_sms, cudaStream_t stream);
+
+}  // namespace dsb

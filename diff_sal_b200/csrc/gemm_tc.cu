@@ -1,0 +1,290 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel (see gemm_tc.cuh).  Warp-specialised, persistent:
+//   warp 0      : TMA producer (one lane)           smem ring  full[] / empty[]
+//   warp 1      : tcgen05.mma issuer (one lane)      TMEM double buffer  tmem_full[] / tmem_empty[]
+//   warps 2..5  : epilogue, one TMEM lane quadrant each (tcgen05.ld -> registers -> fused epilogue -> global)
+#include "gemm_tc.cuh"
+
+#include <stdio.h>
+
+namespace dsb {
+
+static constexpr int kGemmThreads = 192;
+static constexpr int kMaxStages = 8;
+static constexpr uint32_t kAccStride = 256;   // TMEM columns between the two accumulator buffers
+static constexpr uint32_t kTmemCols = 512;
+
+struct __align__(8) GemmBarriers {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const int num_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = 128u * p.bk * 2u;
+    const uint32_t b_bytes = (uint32_t)p.bn * p.bk * 2u;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + (size_t)num_stages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < num_stages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars->tmem_full[a], 1);
+            mbar_init(&bars->tmem_empty[a], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const int n_tiles = p.N / p.bn;
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
+    const int total_tiles = m_tiles * n_tiles;
+    const int nk = p.taps * p.cin_blocks;
+    const int bh_log2 = p.bh_log2, bw_log2 = p.bw_log2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % n_tiles;
+                const int mt = tile / n_tiles;
+                const int tx = mt % p.tiles_x;
+                const int ty = (mt / p.tiles_x) % p.tiles_y;
+                const int tf = mt / (p.tiles_x * p.tiles_y);
+                const int x0 = tx << bw_log2;
+                const int y0 = ty << bh_log2;
+                const int f0 = tf << (7 - bw_log2 - bh_log2);
+                const int y2 = (p.ydim == 2) ? y0 : 0;
+                const int y3 = (p.ydim == 3) ? y0 : 0;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int c1 = p.tap_off[tap][1] + x0;
+                    const int c2 = p.tap_off[tap][2] + y2;
+                    const int c3 = p.tap_off[tap][3] + y3;
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        mbar_wait(&bars->empty[s], phase ^ 1u);
+                        mbar_expect_tx(&bars->full[s], stage_bytes);
+                        uint8_t* sa = smem + (size_t)s * stage_bytes;
+                        tma_load_5d(sa, &tmA, &bars->full[s], p.tap_off[tap][0] + cb * p.bk, c1, c2, c3, f0);
+                        tma_load_2d(sa + a_bytes, &tmB, &bars->full[s], (tap * p.cin_blocks + cb) * p.bk, nt * p.bn);
+                        if (++s == num_stages) { s = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16((uint32_t)p.bn);
+            const uint32_t row_bytes = (uint32_t)p.bk * 2u;
+            const int ksteps = p.bk / 16;
+            int s = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&bars->full[s], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t b_addr = a_addr + a_bytes;
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t da = umma_smem_desc(a_addr + k * 32, row_bytes);
+                        const uint64_t db = umma_smem_desc(b_addr + k * 32, row_bytes);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bars->empty[s]);     // frees the smem slot once these MMAs have read it
+                    if (++s == num_stages) { s = 0; phase ^= 1u; }
+                }
+                umma_commit(&bars->tmem_full[acc]);   // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int r = q * 32 + lane;                  // accumulator row == pixel within the tile
+        const int rx = r & ((1 << bw_log2) - 1);
+        const int ry = (r >> bw_log2) & ((1 << bh_log2) - 1);
+        const int rf = r >> (bw_log2 + bh_log2);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles;
+            const int mt = tile / n_tiles;
+            const int tx = mt % p.tiles_x;
+            const int ty = (mt / p.tiles_x) % p.tiles_y;
+            const int tf = mt / (p.tiles_x * p.tiles_y);
+            const int x = (tx << bw_log2) + rx;
+            const int y = (ty << bh_log2) + ry;
+            const int f = (tf << (7 - bw_log2 - bh_log2)) + rf;
+            const bool valid = (x < p.W) && (y < p.H) && (f < p.F);
+            const size_t pix_in = ((size_t)f * p.H + y) * p.W + x;
+            const size_t pix_out = ((size_t)(f * p.out_fmul + p.out_fadd) * p.H + y) * p.W + x;
+            const int n0 = nt * p.bn;
+
+            mbar_wait(&bars->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
+            float head = 0.0f;
+            for (int c = 0; c < p.bn; c += 16) {
+                uint32_t raw[16];
+                tmem_ld16(t_addr + c, raw);
+                tmem_ld_wait();
+                if (valid) {
+                    const int n = n0 + c;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    if (p.scale) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] *= __ldg(p.scale + n + j);
+                    }
+                    if (p.shift) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.shift + n + j);
+                    }
+                    if (p.rowbias) {
+                        const float* rb = p.rowbias + (size_t)f * p.N + n;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldg(rb + j);
+                    }
+                    if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    } else if (p.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (p.residual) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.residual + pix_in * p.N + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = rp[j];
+                            v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        }
+                    }
+                    if (p.head_w) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) head = fmaf(v[j], __ldg(p.head_w + n + j), head);
+                    }
+                    if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix_out * p.ldo + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (p.out_bf16) {
+                        uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
+                        op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                           pack_bf16x2(v[6], v[7]));
+                        op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                    }
+                }
+            }
+            if (p.head_w && valid) p.out_head[pix_out] = 1.0f / (1.0f + __expf(-(head + p.head_b)));
+            tc_fence_before();
+            mbar_arrive(&bars->tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    const uint32_t inner_bytes = box[0] * 2u;
+    CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return -2;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(100 + (int)r);
+}
+
+int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                cudaStream_t stream) {
+    if (p.bn % 16 || p.bn > 256 || p.bn < 16 || p.N % p.bn) return -10;
+    if (p.bk != 64 && p.bk != 32) return -11;
+    if (p.taps < 1 || p.taps > 9 || p.cin_blocks < 1) return -12;
+    if (p.bw_log2 + p.bh_log2 > 7) return -13;
+    if (p.head_w && p.N != p.bn) return -14;
+    const uint32_t stage_bytes = 128u * p.bk * 2u + (uint32_t)p.bn * p.bk * 2u;
+    const uint32_t budget = 200u * 1024u;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -15;
+    const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int total = p.tiles_x * p.tiles_y * p.tiles_f * (p.N / p.bn);
+    int grid = total < num_sms ? total : num_sms;
+    if (grid < 1) return -16;
+    gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(p, tmA, tmB, stages);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dsb

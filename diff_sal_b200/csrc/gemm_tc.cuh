@@ -1,0 +1,54 @@
+// tcgen05 implicit-GEMM for every dense contraction of the SalUNet denoiser.
+//
+//   D[m, n] = epilogue( sum_{tap, c} A[pixel(m) + offset(tap), c] * W[n, tap*Cin + c] )
+//
+// A is a channels-last bf16 activation tensor addressed through a 5-D TMA tensor map, W a K-major bf16 weight
+// matrix [N][K] through a 2-D map.  One M tile is a 128-pixel box (bw x bh x bf pixels/frames) so that one TMA box
+// load per (tap, 64-channel block) lands exactly one 128-row K-major SWIZZLE_128B operand tile in shared memory;
+// out-of-image taps are zero-filled by TMA, which is the convolution's zero padding.  Covers: 3x3 (pad 1),
+// 3x3 dilation 2, 3x3 stride 2 with right/bottom pad (via a space-to-depth view of the input), 1x1, the (5,1,1)
+// temporal reduction, and plain token linears (bw = 128).
+#pragma once
+#include "common.cuh"
+
+namespace dsb {
+
+enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct GemmParams {
+    // M tiling (output pixels).  bw * bh * bf == 128, all powers of two.
+    int W, H, F;                    // output extent: x in [0,W), y in [0,H), frame in [0,F)
+    int bw_log2, bh_log2;           // tile box
+    int tiles_x, tiles_y, tiles_f;  // tile grid
+    // K loop
+    int taps;                       // 1..9
+    int cin_blocks;                 // Cin / BK
+    int bk;                         // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int ydim;                       // which tensor-map dimension carries y (2 normally, 3 for the s2d view)
+    int tap_off[9][4];              // per tap: coordinate offsets for tensor-map dims 0..3
+    // N tiling
+    int N, bn;                      // N % bn == 0, bn % 16 == 0, bn <= 256
+    // epilogue: v = act(acc * scale[n] + shift[n] + rowbias[frame][n]) + residual[pix][n]
+    const float* scale;             // [N] or null (== 1)
+    const float* shift;             // [N] or null (== 0)
+    const float* rowbias;           // [F][N] or null
+    const float* residual;          // fp32 [pix][N] or null
+    int act;
+    float* out_f32;                 // [pix][ldo] or null
+    bf16* out_bf16;                 // [pix][ldo] or null
+    int ldo;                        // output row pitch in elements
+    int out_fmul, out_fadd;         // output frame = f * out_fmul + out_fadd
+    // fused 96->1 head (mt_proj + logits): out_head[pix] = sigmoid(sum_n v[n] * head_w[n] + head_b)
+    const float* head_w;            // [N] or null
+    float head_b;
+    float* out_head;
+};
+
+// Builds tensor maps and launches; returns a cudaError_t-compatible code (0 = ok).
+int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms, cudaStream_t stream);
+
+// Host helper: encode a tensor map (bf16, SWIZZLE_128B when box[0]*2 == 128, SWIZZLE_64B when == 64).
+int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+}  // namespace dsb

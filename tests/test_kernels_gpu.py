@@ -1,0 +1,126 @@
+"""GPU: every hand-written kernel through its C-ABI test entry against plain fp32 torch ops on the same
+inputs (TF32 disabled).  Inputs of tensor-core kernels are pre-rounded to bf16 so that only the accumulation
+order differs."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CONV_3X3, CONV_3X3_S2, CONV_1X1, CONV_TEMPORAL = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def L():
+    from diff_sal_b200 import _lib
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _lib
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def run_conv(L, kind, A_nhwc, Wt, N, F_, H, W, Cin, dilation=1, T=1, kt=1, scale=None, shift=None, rowbias=None,
+             residual=None, act=0, want="f32", out_frames=None, out_fmul=1, out_fadd=0, head_w=None, head_b=0.0):
+    lib = L.lib()
+    out_frames = out_frames or F_
+    o32 = torch.zeros(out_frames, H, W, N, device="cuda") if want == "f32" else None
+    o16 = torch.zeros(out_frames, H, W, N, device="cuda", dtype=torch.bfloat16) if want == "bf16" else None
+    oh = torch.zeros(out_frames, H, W, device="cuda") if head_w is not None else None
+    r = lib.dsb_test_conv(kind, F_, H, W, Cin, N, dilation, T, kt, L.ptr(A_nhwc), L.ptr(Wt), L.ptr(scale),
+                          L.ptr(shift), L.ptr(rowbias), L.ptr(residual), act, L.ptr(o32), L.ptr(o16), out_fmul,
+                          out_fadd, L.ptr(head_w), ctypes.c_float(head_b), L.ptr(oh), L.stream_ptr())
+    assert r == 0, "dsb_test_conv returned %d" % r
+    torch.cuda.synchronize()
+    return o32 if want == "f32" else (o16 if want == "bf16" else oh)
+
+
+def pack_w(w):
+    """[N, C, kh, kw] -> [N, (kh kw C)] bf16 (k = tap*Cin + c)."""
+    n = w.shape[0]
+    return w.permute(0, 2, 3, 1).reshape(n, -1).to(torch.bfloat16).contiguous()
+
+
+def close(a, b, tol):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * max(ref, 1e-6), "max err %g vs ref max %g" % (err, ref)
+
+
+@pytest.mark.parametrize("M,Cin,N,act,resid", [(1000, 192, 384, ACT_GELU, False), (777, 96, 96, ACT_NONE, True),
+                                               (130, 768, 1536, ACT_GELU, False), (64 * 1024, 96, 192, ACT_NONE, False)])
+def test_linear(L, M, Cin, N, act, resid):
+    a = _rand(M, Cin, seed=1).to(torch.bfloat16)
+    w = _rand(N, Cin, seed=2, scale=Cin ** -0.5).to(torch.bfloat16)
+    b = _rand(N, seed=3)
+    res = _rand(M, N, seed=4) if resid else None
+    out = run_conv(L, CONV_1X1, a, w, N, 1, 1, M, Cin, shift=b, residual=res, act=act, want="f32")
+    ref = F.linear(a.float(), w.float(), b)
+    if act == ACT_GELU:
+        ref = F.gelu(ref)
+    if resid:
+        ref = ref + res
+    close(out.reshape(M, N), ref, 2e-3)
+
+
+@pytest.mark.parametrize("Fr,H,W,Cin,N,dil", [(2, 28, 48, 192, 384, 1), (3, 14, 24, 768, 384, 2), (1, 56, 96, 96, 192, 1),
+                                              (9, 56, 96, 96, 96, 2), (4, 7, 12, 768, 768, 1)])
+def test_conv3x3(L, Fr, H, W, Cin, N, dil):
+    x = _rand(Fr, Cin, H, W, seed=5).to(torch.bfloat16)
+    w = _rand(N, Cin, 3, 3, seed=6, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    scale = 1.0 + 0.1 * _rand(N, seed=7)
+    shift = _rand(N, seed=8)
+    rowbias = _rand(Fr, N, seed=9)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, Cin, dilation=dil, scale=scale, shift=shift,
+                   rowbias=rowbias, act=ACT_RELU, want="bf16")
+    ref = F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None] + rowbias[:, :, None, None])
+    close(out.permute(0, 3, 1, 2), ref, 1e-2)
+
+
+@pytest.mark.parametrize("Fr,H,W,C", [(2, 14, 24, 384), (3, 28, 48, 192), (2, 7, 12, 768)])
+def test_conv3x3_stride2_into_frame_slot(L, Fr, H, W, C):
+    x = _rand(Fr, C, 2 * H, 2 * W, seed=10).to(torch.bfloat16)
+    w = _rand(C, C, 3, 3, seed=11, scale=(9 * C) ** -0.5).to(torch.bfloat16)
+    b = _rand(C, seed=12)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3_S2, a, pack_w(w), C, Fr, H, W, C, shift=b, want="f32", out_frames=Fr * 9,
+                   out_fmul=9, out_fadd=8)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), b, stride=2)
+    out = out.reshape(Fr, 9, H, W, C)
+    close(out[:, 8].permute(0, 3, 1, 2), ref, 2e-3)
+    assert out[:, :8].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 7, 12, 768), (3, 28, 48, 192), (1, 56, 96, 96)])
+def test_temporal_reduce(L, B, H, W, C):
+    x = _rand(B, C, 9, H, W, seed=13).to(torch.bfloat16)
+    w = _rand(768, C, 5, 1, 1, seed=14, scale=(5 * C) ** -0.5).to(torch.bfloat16)
+    a = x.permute(0, 2, 3, 4, 1).contiguous()                       # [B,T,H,W,C]
+    wt = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(768, 5 * C).contiguous()
+    out = run_conv(L, CONV_TEMPORAL, a, wt, 768, B, H, W, C, T=9, kt=5, act=ACT_RELU, want="f32")
+    ref = F.relu(F.conv3d(x.float(), w.float(), None, stride=(5, 1, 1))).squeeze(2)
+    close(out.permute(0, 3, 1, 2), ref, 2e-3)
+
+
+def test_head_epilogue(L):
+    Fr, H, W, Cin, N = 2, 16, 64, 768, 96
+    x = _rand(Fr, Cin, H, W, seed=15).to(torch.bfloat16)
+    w = _rand(N, Cin, 3, 3, seed=16, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    scale = 1.0 + 0.1 * _rand(N, seed=17)
+    shift = _rand(N, seed=18)
+    hw = _rand(N, seed=19, scale=0.3)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, Cin, scale=scale, shift=shift, act=ACT_RELU,
+                   want="head", head_w=hw, head_b=0.25)
+    ref = F.relu(F.conv2d(x.float(), w.float(), None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    ref = torch.sigmoid((ref * hw[None, :, None, None]).sum(1) + 0.25)
+    close(out, ref, 2e-3)
