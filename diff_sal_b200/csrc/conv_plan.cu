@@ -13,11 +13,12 @@ static int pick_bn(int N) {
 }
 
 // Choose the 128-pixel tile box (bw x bh x bf, powers of two) that wastes the fewest accumulator rows.
-static void pick_tile(int W, int H, int F, int* bw_log2, int* bh_log2) {
+static void pick_tile(int W, int H, int F, bool single_frame, int* bw_log2, int* bh_log2) {
     long best = -1;
     int bx = 7, by = 0;
     for (int lx = 7; lx >= 0; --lx) {
         for (int ly = 0; lx + ly <= 7; ++ly) {
+            if (single_frame && lx + ly != 7) continue;
             const int bw = 1 << lx, bh = 1 << ly, bf = 128 >> (lx + ly);
             const long tiles = (long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((F + bf - 1) / bf);
             if (best < 0 || tiles < best) {
@@ -40,7 +41,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     const int bn = pick_bn(op.N);
     if (!bn) return -21;
     p.W = op.W; p.H = op.H; p.F = op.F;
-    pick_tile(op.W, op.H, op.F, &p.bw_log2, &p.bh_log2);
+    pick_tile(op.W, op.H, op.F, op.b_rows_per_frame != 0, &p.bw_log2, &p.bh_log2);
     const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2, bf = 128 >> (p.bw_log2 + p.bh_log2);
     p.tiles_x = (op.W + bw - 1) / bw;
     p.tiles_y = (op.H + bh - 1) / bh;
@@ -101,7 +102,8 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     int r = make_tensor_map(&out->tmA, op.A, 5, dims, strides, box);
     if (r) return r;
     const uint64_t K = (uint64_t)p.taps * C;
-    uint64_t wd[2] = {K, (uint64_t)op.N};
+    const uint64_t wrows = op.b_rows_per_frame ? (uint64_t)op.F * op.b_rows_per_frame : (uint64_t)op.N;
+    uint64_t wd[2] = {K, wrows};
     uint64_t ws[1] = {K * e};
     uint32_t wb[2] = {(uint32_t)bk, (uint32_t)bn};
     r = make_tensor_map(&out->tmB, op.Wt, 2, wd, ws, wb);
@@ -114,6 +116,8 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.out_fmul = op.out_fmul ? op.out_fmul : 1;
     p.out_fadd = op.out_fadd;
     p.head_w = op.head_w; p.head_b = op.head_b; p.out_head = op.out_head;
+    p.b_rows_per_frame = op.b_rows_per_frame;
+    p.out_softmax = op.out_softmax;
     return 0;
 }
 

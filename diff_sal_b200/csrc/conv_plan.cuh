@@ -33,6 +33,8 @@ struct ConvOp {
     const float* head_w;
     float head_b;
     float* out_head;
+    int b_rows_per_frame;   // per-frame B operand (attention): Wt is [F * b_rows_per_frame][K]
+    bf16* out_softmax;      // attention-score epilogue (N == 48)
 };
 
 struct ConvLaunch {

@@ -86,7 +86,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         mbar_expect_tx(&bars->full[s], stage_bytes);
                         uint8_t* sa = smem + (size_t)s * stage_bytes;
                         tma_load_5d(sa, &tmA, &bars->full[s], p.tap_off[tap][0] + cb * p.bk, c1, c2, c3, f0);
-                        tma_load_2d(sa + a_bytes, &tmB, &bars->full[s], (tap * p.cin_blocks + cb) * p.bk, nt * p.bn);
+                        tma_load_2d(sa + a_bytes, &tmB, &bars->full[s], (tap * p.cin_blocks + cb) * p.bk,
+                                    nt * p.bn + f0 * p.b_rows_per_frame);
                         if (++s == num_stages) { s = 0; phase ^= 1u; }
                     }
                 }
@@ -150,6 +151,43 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
             float head = 0.0f;
+            if (p.out_softmax) {
+                // 2 heads x 18 keys: the whole score row lives in this thread
+                uint32_t raw[48];
+                tmem_ld16(t_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(raw + 0));
+                tmem_ld16(t_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(raw + 16));
+                tmem_ld16(t_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(raw + 32));
+                tmem_ld_wait();
+                if (valid) {
+                    float pr[36];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) {
+                            float sc = __uint_as_float(raw[h * 18 + j]);
+                            if (p.rowbias) sc += __ldg(p.rowbias + (size_t)f * p.N + h * 18 + j);
+                            pr[h * 18 + j] = sc;
+                            mx = fmaxf(mx, sc);
+                        }
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) { pr[h * 18 + j] = expf(pr[h * 18 + j] - mx); sum += pr[h * 18 + j]; }
+                        const float inv = 1.0f / sum;
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) pr[h * 18 + j] *= inv;
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.out_softmax + pix_out * 64);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        op[k] = make_uint4(pack_bf16x2(pr[8 * k], pr[8 * k + 1]), pack_bf16x2(pr[8 * k + 2], pr[8 * k + 3]),
+                                           pack_bf16x2(pr[8 * k + 4], pr[8 * k + 5]), pack_bf16x2(pr[8 * k + 6], pr[8 * k + 7]));
+                    op[4] = make_uint4(pack_bf16x2(pr[32], pr[33]), pack_bf16x2(pr[34], pr[35]), 0u, 0u);
+                    op[5] = make_uint4(0u, 0u, 0u, 0u);
+                    op[6] = make_uint4(0u, 0u, 0u, 0u);
+                    op[7] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else
             for (int c = 0; c < p.bn; c += 16) {
                 uint32_t raw[16];
                 tmem_ld16(t_addr + c, raw);
@@ -261,6 +299,16 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
     return r == CUDA_SUCCESS ? 0 : -(100 + (int)r);
 }
 
+int gemm_init() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    return 0;
+}
+
 int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                 cudaStream_t stream) {
     if (p.bn % 16 || p.bn > 256 || p.bn < 16 || p.N % p.bn) return -10;
@@ -268,18 +316,15 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.taps < 1 || p.taps > 9 || p.cin_blocks < 1) return -12;
     if (p.bw_log2 + p.bh_log2 > 7) return -13;
     if (p.head_w && p.N != p.bn) return -14;
+    if (p.out_softmax && (p.N != 48 || p.bn != 48)) return -17;
+    if (p.b_rows_per_frame && (p.bw_log2 + p.bh_log2 != 7)) return -18;
     const uint32_t stage_bytes = 128u * p.bk * 2u + (uint32_t)p.bn * p.bk * 2u;
     const uint32_t budget = 200u * 1024u;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -15;
     const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    if (int e = gemm_init()) return e;
     const int total = p.tiles_x * p.tiles_y * p.tiles_f * (p.N / p.bn);
     int grid = total < num_sms ? total : num_sms;
     if (grid < 1) return -16;

@@ -28,6 +28,8 @@ struct GemmParams {
     int tap_off[9][4];              // per tap: coordinate offsets for tensor-map dims 0..3
     // N tiling
     int N, bn;                      // N % bn == 0, bn % 16 == 0, bn <= 256
+    int b_rows_per_frame;           // 0: shared weights; else B rows of frame f start at f * b_rows_per_frame
+                                    //    (per-frame attention operands; requires single-frame tiles)
     // epilogue: v = act(acc * scale[n] + shift[n] + rowbias[frame][n]) + residual[pix][n]
     const float* scale;             // [N] or null (== 1)
     const float* shift;             // [N] or null (== 0)
@@ -42,8 +44,13 @@ struct GemmParams {
     const float* head_w;            // [N] or null
     float head_b;
     float* out_head;
+    // attention scores: N == bn == 48 = 2 heads x 18 keys (+12 zero rows); per-head softmax over the 18 keys,
+    // written as bf16 probabilities [pix][64] (columns 36..63 zero) -- the A operand of the P.V GEMM
+    bf16* out_softmax;
 };
 
+// One-time per-process kernel attribute setup (safe to call repeatedly; called outside stream capture).
+int gemm_init();
 // Builds tensor maps and launches; returns a cudaError_t-compatible code (0 = ok).
 int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms, cudaStream_t stream);
 

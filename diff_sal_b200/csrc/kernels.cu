@@ -1,0 +1,735 @@
+// Memory-bound kernels of the SalUNet denoiser (see kernels.cuh).  Vectorised, coalesced over the channel axis,
+// warp-shuffle reductions for the LayerNorm / softmax statistics.
+#include "kernels.cuh"
+
+namespace dsb {
+
+#define DSB_LAUNCH_CHECK() return (int)cudaGetLastError()
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float t = (lane < nw) ? red[lane] : 0.0f;
+    return warp_sum(t);
+}
+
+// ------------------------------------------------------------------------------------------ timestep embedding
+__global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, TembWeights w, float* tp0, float* tp1,
+                                                  float* tp2) {
+    __shared__ float emb[96];
+    __shared__ float h1[384];
+    __shared__ float h2[384];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float tv = t[b];
+    if (tid < 48) {
+        const float fr = expf((float)tid * -0.19596468876545072f);   // exp(-k * ln(1e4) / 47)
+        const float a = tv * fr;
+        emb[tid] = sinf(a);
+        emb[48 + tid] = cosf(a);
+    }
+    __syncthreads();
+    for (int r = wid; r < 384; r += 12) {
+        const float* row = w.w0 + r * 96;
+        float acc = row[lane] * emb[lane] + row[lane + 32] * emb[lane + 32] + row[lane + 64] * emb[lane + 64];
+        acc = warp_sum(acc);
+        if (lane == 0) h1[r] = swishf(acc + w.b0[r]);
+    }
+    __syncthreads();
+    for (int r = wid; r < 384; r += 12) {
+        const float* row = w.w1 + r * 384;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc = fmaf(row[lane + 32 * k], h1[lane + 32 * k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) h2[r] = swishf(acc + w.b1[r]);      // only swish(temb) is consumed (sal_unet.py:129)
+    }
+    __syncthreads();
+    float* outs[3] = {tp0, tp1, tp2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int co = w.cout[i];
+        for (int r = wid; r < co; r += 12) {
+            const float* row = w.wp[i] + r * 384;
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc = fmaf(row[lane + 32 * k], h2[lane + 32 * k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) outs[i][(size_t)b * co + r] = acc + w.bp[i][r];
+        }
+    }
+}
+
+int temb_launch(const float* t, int B, const TembWeights& w, float* const tp[3], cudaStream_t s) {
+    temb_kernel<<<B, 384, 0, s>>>(t, w, tp[0], tp[1], tp[2]);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ stem 5x5 stride 4
+__global__ void __launch_bounds__(96) stem_kernel(const float* __restrict__ x, const float* __restrict__ w5,
+                                                 const float* __restrict__ b5, float* __restrict__ h0) {
+    __shared__ float patch[5][132];
+    const int xo0 = blockIdx.x * 32, y = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
+    const float* xb = x + (size_t)b * 224 * 384;
+    for (int i = threadIdx.x; i < 5 * 129; i += 96) {
+        const int r = i / 129, col = i % 129;
+        const int yy = 4 * y - 1 + r, xx = 4 * xo0 - 1 + col;
+        patch[r][col] = (yy >= 0 && yy < 224 && xx >= 0 && xx < 384) ? xb[yy * 384 + xx] : 0.0f;
+    }
+    float w[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) w[k] = w5[k * 96 + c];
+    const float bias = b5[c];
+    __syncthreads();
+    float* out = h0 + (((size_t)b * 56 + y) * 96 + xo0) * 96 + c;
+    for (int px = 0; px < 32; ++px) {
+        float acc = bias;
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc = fmaf(w[r * 5 + q], patch[r][4 * px + q], acc);
+        out[(size_t)px * 96] = acc;
+    }
+}
+
+int stem_launch(const float* x, int B, const float* w5, const float* b5, float* h0, cudaStream_t s) {
+    stem_kernel<<<dim3(3, 56, B), 96, 0, s>>>(x, w5, b5, h0);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+// Deterministic two-level reduction (no atomics): block (split, frame) writes the (sum, sum of squares) of its
+// pixel range for each of the 32 groups to part[frame][split][group]; gn_apply adds the splits in a fixed order.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, double* part) {
+    __shared__ float ssum[960];
+    __shared__ float ssq[960];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int cv_n = C >> 2;
+    const int P = 256 / cv_n;                       // pixel lanes (10, 5, 2, 1 for C = 96..768)
+    const int cv = tid % cv_n, pl = tid / cv_n;
+    const int per = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per;
+    const int p1 = min(HW, p0 + per);
+    if (pl < P) {
+        float4 s4 = make_float4(0, 0, 0, 0), q4 = make_float4(0, 0, 0, 0);
+        const float4* base = reinterpret_cast<const float4*>(x + (size_t)f * HW * C) + cv;
+        for (int px = p0 + pl; px < p1; px += P) {
+            const float4 v = base[(size_t)px * cv_n];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
+        }
+        float* ps = ssum + pl * C + 4 * cv;
+        float* pq = ssq + pl * C + 4 * cv;
+        ps[0] = s4.x; ps[1] = s4.y; ps[2] = s4.z; ps[3] = s4.w;
+        pq[0] = q4.x; pq[1] = q4.y; pq[2] = q4.z; pq[3] = q4.w;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int cg = C >> 5;
+        double s = 0.0, q = 0.0;
+        for (int l = 0; l < P; ++l)
+            for (int k = 0; k < cg; ++k) { s += (double)ssum[l * C + tid * cg + k]; q += (double)ssq[l * C + tid * cg + k]; }
+        double* o = part + (((size_t)f * gridDim.x + blockIdx.x) * 32 + tid) * 2;
+        o[0] = s;
+        o[1] = q;
+    }
+}
+
+static int gn_splits(int HW) { int S = HW / 8; return S > 64 ? 64 : (S < 1 ? 1 : S); }
+
+int gn_stats_launch(const float* x, int F, int HW, int C, double* part, cudaStream_t s) {
+    if (C % 32 || C > 768 || C < 96) return -30;
+    gn_stats_kernel<<<dim3(gn_splits(HW), F), 256, 0, s>>>(x, HW, C, part);
+    DSB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int HW, int C, int S,
+                                                      const double* __restrict__ part, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, bf16* __restrict__ out_act,
+                                                      bf16* __restrict__ out_raw) {
+    __shared__ float mean[32];
+    __shared__ float rstd[32];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int cg = C >> 5;
+    if (tid < 32) {
+        double sm = 0.0, sq = 0.0;
+        for (int k = 0; k < S; ++k) {
+            const double* o = part + (((size_t)f * S + k) * 32 + tid) * 2;
+            sm += o[0];
+            sq += o[1];
+        }
+        const double n = (double)HW * cg;
+        const double m = sm / n;
+        double v = sq / n - m * m;
+        if (v < 0.0) v = 0.0;
+        mean[tid] = (float)m;
+        rstd[tid] = (float)(1.0 / sqrt(v + 1e-6));
+    }
+    __syncthreads();
+    const int cv_n = C >> 2;
+    const long total = (long)HW * cv_n;
+    const size_t fb = (size_t)f * HW * C;
+    for (long i = (long)blockIdx.x * 256 + tid; i < total; i += (long)gridDim.x * 256) {
+        const int cv = (int)(i % cv_n);
+        const float4 v = reinterpret_cast<const float4*>(x + fb)[i];
+        const float4 g = reinterpret_cast<const float4*>(gamma)[cv];
+        const float4 bt = reinterpret_cast<const float4*>(beta)[cv];
+        const int c = 4 * cv;
+        const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
+        const float a0 = swishf((v.x - mean[g0]) * rstd[g0] * g.x + bt.x);
+        const float a1 = swishf((v.y - mean[g1]) * rstd[g1] * g.y + bt.y);
+        const float a2 = swishf((v.z - mean[g2]) * rstd[g2] * g.z + bt.z);
+        const float a3 = swishf((v.w - mean[g3]) * rstd[g3] * g.w + bt.w);
+        reinterpret_cast<uint2*>(out_act + fb)[i] = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+        if (out_raw) reinterpret_cast<uint2*>(out_raw + fb)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, const float* gamma, const float* beta,
+                    bf16* out_act, bf16* out_raw, cudaStream_t s) {
+    long total = (long)HW * (C / 4);
+    int gx = (int)((total + 255) / 256);
+    if (gx > 296) gx = 296;
+    gn_apply_kernel<<<dim3(gx, F), 256, 0, s>>>(x, HW, C, gn_splits(HW), acc, gamma, beta, out_act, out_raw);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ bilinear helpers
+// PyTorch area_pixel_compute_source_index (align_corners=False): src = scale*(dst+0.5)-0.5 clamped at 0.
+__device__ __forceinline__ void bil_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.0f) src = 0.0f;
+    i0 = (int)src;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int F, int H, int W, int C,
+                                                        bf16* __restrict__ out) {
+    const int cv_n = C >> 2;
+    const long total = (long)F * 4 * H * W * cv_n;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const int cv = (int)(i % cv_n);
+        long p = i / cv_n;
+        const int xo = (int)(p % (2 * W)); p /= (2 * W);
+        const int yo = (int)(p % (2 * H));
+        const int f = (int)(p / (2 * H));
+        int y0, y1, x0, x1; float ly, lx;
+        bil_src(yo, 0.5f, H, y0, y1, ly);
+        bil_src(xo, 0.5f, W, x0, x1, lx);
+        const float4* src = reinterpret_cast<const float4*>(x + (size_t)f * H * W * C);
+        const float4 v00 = src[((size_t)y0 * W + x0) * cv_n + cv], v01 = src[((size_t)y0 * W + x1) * cv_n + cv];
+        const float4 v10 = src[((size_t)y1 * W + x0) * cv_n + cv], v11 = src[((size_t)y1 * W + x1) * cv_n + cv];
+        const float hy0 = 1.0f - ly, hx0 = 1.0f - lx;
+        const float r0 = hy0 * (hx0 * v00.x + lx * v01.x) + ly * (hx0 * v10.x + lx * v11.x);
+        const float r1 = hy0 * (hx0 * v00.y + lx * v01.y) + ly * (hx0 * v10.y + lx * v11.y);
+        const float r2 = hy0 * (hx0 * v00.z + lx * v01.z) + ly * (hx0 * v10.z + lx * v11.z);
+        const float r3 = hy0 * (hx0 * v00.w + lx * v01.w) + ly * (hx0 * v10.w + lx * v11.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+    }
+}
+
+int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s) {
+    const long total = (long)F * 4 * H * W * (C / 4);
+    long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    upsample2x_kernel<<<(int)g, 256, 0, s>>>(x, F, H, W, C, out);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm (warp / token)
+template <int NV>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, long tokens, float2* stats) {
+    constexpr int C = NV * 32;
+    const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tok >= tokens) return;
+    const float* row = x + tok * C;
+    float v[NV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = row[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float var = warp_sum(q) * (1.0f / C);
+    if (lane == 0) stats[tok] = make_float2(mean, rsqrtf(var + 1e-5f));
+}
+
+int ln_stats_launch(const float* x, long tokens, int C, float2* stats, cudaStream_t s) {
+    const int g = (int)((tokens + 7) / 8);
+    switch (C) {
+        case 96: ln_stats_kernel<3><<<g, 256, 0, s>>>(x, tokens, stats); break;
+        case 192: ln_stats_kernel<6><<<g, 256, 0, s>>>(x, tokens, stats); break;
+        case 384: ln_stats_kernel<12><<<g, 256, 0, s>>>(x, tokens, stats); break;
+        case 768: ln_stats_kernel<24><<<g, 256, 0, s>>>(x, tokens, stats); break;
+        default: return -31;
+    }
+    DSB_LAUNCH_CHECK();
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_apply_kernel(const float* __restrict__ x, long tokens,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      bf16* __restrict__ out, int hw, int T, int tmax) {
+    constexpr int C = NV * 32;
+    const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tok >= tokens) return;
+    if ((int)((tok / hw) % T) >= tmax) return;
+    const float* row = x + tok * C;
+    float v[NV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = row[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    bf16* o = out + tok * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        o[c] = __float2bfloat16((v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
+                    int T, int tmax, cudaStream_t s) {
+    const int g = (int)((tokens + 7) / 8);
+    switch (C) {
+        case 96: ln_apply_kernel<3><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
+        case 192: ln_apply_kernel<6><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
+        case 384: ln_apply_kernel<12><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
+        case 768: ln_apply_kernel<24><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
+        default: return -31;
+    }
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ q = LN(dw3x3(LN(x)))
+template <int NV>
+__global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                                    long tokens, int H, int W, const float* __restrict__ ng,
+                                                    const float* __restrict__ nb, const float* __restrict__ wq,
+                                                    const float* __restrict__ qg, const float* __restrict__ qb,
+                                                    bf16* __restrict__ out) {
+    constexpr int C = NV * 32;
+    const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tok >= tokens) return;
+    const int hw = H * W;
+    const long f = tok / hw;
+    const int pix = (int)(tok % hw);
+    const int y = pix / W, xx = pix % W;
+    float g[NV], b[NV], q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { g[i] = ng[lane + 32 * i]; b[i] = nb[lane + 32 * i]; q[i] = 0.0f; }
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xn = xx + dx;
+            if (xn < 0 || xn >= W) continue;
+            const long nt = f * hw + (long)yy * W + xn;
+            const float2 st = stats[nt];
+            const float* row = x + nt * C;
+            const float* wr = wq + ((dy + 1) * 3 + (dx + 1)) * C;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                const float xv = (row[c] - st.x) * st.y * g[i] + b[i];
+                q[i] = fmaf(wr[c], xv, q[i]);
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += q[i];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float v2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const float d = q[i] - mean; v2 = fmaf(d, d, v2); }
+    const float rstd = rsqrtf(warp_sum(v2) * (1.0f / C) + 1e-5f);
+    bf16* o = out + tok * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        o[c] = __float2bfloat16((q[i] - mean) * rstd * qg[c] + qb[c]);
+    }
+}
+
+int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
+                  const float* wq, const float* qg, const float* qb, bf16* out, cudaStream_t s) {
+    const long tokens = (long)F * H * W;
+    const int g = (int)((tokens + 7) / 8);
+    switch (C) {
+        case 96: q_dwln_kernel<3><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
+        case 192: q_dwln_kernel<6><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
+        case 384: q_dwln_kernel<12><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
+        case 768: q_dwln_kernel<24><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
+        default: return -31;
+    }
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ pooled K / V tokens
+// Tail shared by both pooling kernels: pre[C] (smem) -> LayerNorm -> bf16 row.
+__device__ __forceinline__ void pooled_ln_store(const float* pre, int C, const float* __restrict__ g,
+                                                const float* __restrict__ b, bf16* __restrict__ o, float* red) {
+    float s = 0.0f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s += pre[c];
+    const float mean = block_sum(s, red) / (float)C;
+    float q = 0.0f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { const float d = pre[c] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(block_sum(q, red) / (float)C + 1e-5f);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2bfloat16((pre[c] - mean) * rstd * g[c] + b[c]);
+}
+
+// Accumulates pre[c] = sum_p src(p, c) over the s*s window into sm[0..C).  Threads are laid out as
+// channels x pixel-groups when C <= blockDim (partials combined through smem), else channels are looped.
+template <class Src>
+__device__ __forceinline__ void pool_accumulate(const Src& src, int C, int npx, float* sm) {
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    if (C <= nthr) {
+        const int G = nthr / C;
+        const int c = tid % C, gq = tid / C;
+        float acc = 0.0f;
+        if (gq < G) {
+            for (int p = gq; p < npx; p += G) acc += src(p, c);
+            sm[gq * C + c] = acc;
+        }
+        __syncthreads();
+        float a = 0.0f;
+        if (tid < C)
+            for (int k = 0; k < G; ++k) a += sm[k * C + tid];
+        __syncthreads();
+        if (tid < C) sm[tid] = a;
+        __syncthreads();
+    } else {
+        for (int c = tid; c < C; c += nthr) {
+            float acc = 0.0f;
+            for (int p = 0; p < npx; ++p) acc += src(p, c);
+            sm[c] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// one block per pooled token (f, Y, X)
+__global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __restrict__ stats, int H, int W, int C,
+                               int s_, const float* __restrict__ ng, const float* __restrict__ nb,
+                               const float* __restrict__ wv, const float* __restrict__ vg,
+                               const float* __restrict__ vb, bf16* __restrict__ out) {
+    extern __shared__ float sm[];          // part[G][C]; pre[C] aliases part[0]
+    __shared__ float red[32];
+    const int tokv = blockIdx.x;           // f*18 + Y*6 + X
+    const int f = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
+    const size_t fbase = (size_t)f * H * W;
+    auto src = [&](int p, int c) -> float {
+        const int dy = p / s_, dx = p % s_;
+        const size_t t = fbase + (size_t)(Y * s_ + dy) * W + (X * s_ + dx);
+        const float2 st = stats[t];
+        return wv[p * C + c] * ((x[t * C + c] - st.x) * st.y * ng[c] + nb[c]);
+    };
+    pool_accumulate(src, C, s_ * s_, sm);
+    pooled_ln_store(sm, C, vg, vb, out + (size_t)tokv * C, red);
+}
+
+static int pool_threads(int C) { return C <= 192 ? 192 : 384; }
+
+int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
+                   const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, cudaStream_t s) {
+    const int nthr = pool_threads(C);
+    const int G = (C <= nthr) ? nthr / C : 1;
+    const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
+    pool_ln_kernel<<<F * 18, nthr, smem, s>>>(x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ audio gate
+// one block per (y, b): m[x][c] = mean_t a*x ; softmax over x ; g written as [b][c][y][x]
+__global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ x, const float* __restrict__ a_low,
+                                                     int T, int H, int W, int C, float* __restrict__ g) {
+    extern __shared__ float m[];           // [W][C+1]
+    const int y = blockIdx.x, b = blockIdx.y;
+    const int r = H / 7;
+    const int CP = C + 1;
+    const float invT = 1.0f / (float)T;
+    for (int e = threadIdx.x; e < W * C; e += 256) {
+        const int c = e % C, xx = e / C;
+        float acc = 0.0f;
+        for (int t = 0; t < T; ++t) {
+            const size_t fr = (size_t)b * T + t;
+            const float xv = x[((fr * H + y) * W + xx) * C + c];
+            const float av = a_low[((fr * 7 + y / r) * 12 + xx / r) * C + c];
+            acc = fmaf(av, xv, acc);
+        }
+        m[xx * CP + c] = acc * invT;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float mx = -INFINITY;
+        for (int xx = 0; xx < W; ++xx) mx = fmaxf(mx, m[xx * CP + c]);
+        float sum = 0.0f;
+        for (int xx = 0; xx < W; ++xx) { const float e = expf(m[xx * CP + c] - mx); m[xx * CP + c] = e; sum += e; }
+        const float inv = 1.0f / sum;
+        for (int xx = 0; xx < W; ++xx) m[xx * CP + c] *= inv;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < W * C; e += 256) {
+        const int xx = e % W, c = e / W;
+        g[(((size_t)b * C + c) * H + y) * W + xx] = m[xx * CP + c];
+    }
+}
+
+int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s) {
+    const size_t smem = (size_t)W * (C + 1) * sizeof(float);
+    av_gate_kernel<<<dim3(H, B), 256, smem, s>>>(x, a_low, T, H, W, C, g);
+    DSB_LAUNCH_CHECK();
+}
+
+// K source = raw reinterpretation of the contiguous [B][C][T][H][W] buffer (a*g) as [(B T)][H W][C]
+// (transformer.py:146) followed by 'b (h w) c -> b c h w' (attention.py:89): element (bt, pix', c') is the flat
+// element j = (bt % T)*HW*C + pix'*C + c' of clip b = bt / T, and flat j decodes to (c, t, pix) = [C][T][HW].
+__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int T, int H, int W,
+                                int C, int s_, const float* __restrict__ wk, const float* __restrict__ kg,
+                                const float* __restrict__ kb, bf16* __restrict__ out) {
+    extern __shared__ float sm[];
+    __shared__ float red[32];
+    const int tokv = blockIdx.x;                 // bt*18 + Y*6 + X
+    const int bt = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
+    const int b = bt / T, tt = bt % T;
+    const int HW = H * W;
+    const int r = H / 7;
+    const long clip_base = (long)tt * HW * C;
+    const int THW = T * HW;
+    auto src = [&](int p, int c) -> float {
+        const int dy = p / s_, dx = p % s_;
+        const int pixp = (Y * s_ + dy) * W + (X * s_ + dx);
+        const long j = clip_base + (long)pixp * C + c;
+        const int cs = (int)(j / THW);
+        const int rem = (int)(j % THW);
+        const int ts = rem / HW;
+        const int pix = rem % HW;
+        const int ys = pix / W, xs = pix % W;
+        const float av = a_low[((((size_t)b * T + ts) * 7 + ys / r) * 12 + xs / r) * C + cs];
+        const float gv = g[((size_t)b * C + cs) * HW + pix];
+        return wk[p * C + c] * (av * gv);
+    };
+    pool_accumulate(src, C, s_ * s_, sm);
+    pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
+}
+
+int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_, const float* wk,
+                    const float* kg, const float* kb, bf16* out, cudaStream_t s) {
+    const int nthr = pool_threads(C);
+    const int G = (C <= nthr) ? nthr / C : 1;
+    const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
+    kpool_av_kernel<<<B * T * 18, nthr, smem, s>>>(g, a_low, T, H, W, C, s_, wk, kg, kb, out);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ attention operands
+__global__ void __launch_bounds__(256) attn_operands_kernel(const float* __restrict__ kp, const float* __restrict__ vp,
+                                                           int F, int C, float scale, bf16* __restrict__ KB,
+                                                           bf16* __restrict__ VB) {
+    const long nK = (long)F * 48 * C, nV = (long)F * C * 64;
+    const int d = C >> 1;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nK + nV; i += (long)gridDim.x * 256) {
+        if (i < nK) {
+            const int c = (int)(i % C);
+            const int row = (int)((i / C) % 48);
+            const long f = i / ((long)C * 48);
+            float v = 0.0f;
+            if (row < 36 && (c / d) == (row / 18)) v = kp[(f * 18 + row % 18) * C + c] * scale;
+            KB[i] = __float2bfloat16(v);
+        } else {
+            const long k = i - nK;
+            const int col = (int)(k % 64);
+            const int c = (int)((k / 64) % C);
+            const long f = k / ((long)C * 64);
+            float v = 0.0f;
+            if (col < 36 && (c / d) == (col / 18)) v = vp[(f * 18 + col % 18) * C + c];
+            VB[k] = __float2bfloat16(v);
+        }
+    }
+}
+
+int attn_operands_launch(const float* kp, const float* vp, int F, int C, float scale, bf16* KB, bf16* VB,
+                         cudaStream_t s) {
+    const long n = (long)F * 48 * C + (long)F * C * 64;
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    attn_operands_kernel<<<(int)g, 256, 0, s>>>(kp, vp, F, C, scale, KB, VB);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ multi-scale sum
+struct MsSrc { const float* r[4]; };
+
+__global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, int B, bf16* __restrict__ S) {
+    constexpr int C = 768, CV = C / 4, OH = 112, OW = 192;
+    const long total = (long)B * OH * OW * CV;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const int cv = (int)(i % CV);
+        long p = i / CV;
+        const int xo = (int)(p % OW); p /= OW;
+        const int yo = (int)(p % OH);
+        const int b = (int)(p / OH);
+        float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int H = 7 << k, W = 12 << k;
+            const float scale = (float)H / (float)OH;
+            int y0, y1, x0, x1; float ly, lx;
+            bil_src(yo, scale, H, y0, y1, ly);
+            bil_src(xo, scale, W, x0, x1, lx);
+            const float4* s4 = reinterpret_cast<const float4*>(src.r[k] + (size_t)b * H * W * C);
+            const float4 v00 = s4[((size_t)y0 * W + x0) * CV + cv], v01 = s4[((size_t)y0 * W + x1) * CV + cv];
+            const float4 v10 = s4[((size_t)y1 * W + x0) * CV + cv], v11 = s4[((size_t)y1 * W + x1) * CV + cv];
+            const float hy0 = 1.0f - ly, hx0 = 1.0f - lx;
+            acc.x += hy0 * (hx0 * v00.x + lx * v01.x) + ly * (hx0 * v10.x + lx * v11.x);
+            acc.y += hy0 * (hx0 * v00.y + lx * v01.y) + ly * (hx0 * v10.y + lx * v11.y);
+            acc.z += hy0 * (hx0 * v00.z + lx * v01.z) + ly * (hx0 * v10.z + lx * v11.z);
+            acc.w += hy0 * (hx0 * v00.w + lx * v01.w) + ly * (hx0 * v10.w + lx * v11.w);
+        }
+        reinterpret_cast<uint2*>(S)[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
+}
+
+int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {
+    MsSrc src;
+    for (int k = 0; k < 4; ++k) src.r[k] = r[k];
+    const long total = (long)B * 112 * 192 * 192;
+    long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    ms_sum_kernel<<<(int)g, 256, 0, s>>>(src, B, S);
+    DSB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) final_up_kernel(const float* __restrict__ p, int B, float* __restrict__ out) {
+    const long total = (long)B * 224 * 384;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const int xo = (int)(i % 384);
+        const int yo = (int)((i / 384) % 224);
+        const int b = (int)(i / (384 * 224));
+        int y0, y1, x0, x1; float ly, lx;
+        bil_src(yo, 0.5f, 112, y0, y1, ly);
+        bil_src(xo, 0.5f, 192, x0, x1, lx);
+        const float* s = p + (size_t)b * 112 * 192;
+        const float v00 = s[y0 * 192 + x0], v01 = s[y0 * 192 + x1], v10 = s[y1 * 192 + x0], v11 = s[y1 * 192 + x1];
+        out[i] = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    }
+}
+
+int final_up_launch(const float* p, int B, float* out, cudaStream_t s) {
+    const long total = (long)B * 224 * 384;
+    long g = (total + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    final_up_kernel<<<(int)g, 256, 0, s>>>(p, B, out);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ sampler update
+struct AxpyArgs { const float* in[4]; float c[4]; };
+
+__global__ void __launch_bounds__(256) axpy_kernel(int nin, AxpyArgs a, const float* __restrict__ noise, float cn,
+                                                  float* __restrict__ out, long n4) {
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+        float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 4
+        for (int k = 0; k < nin; ++k) {
+            const float4 v = reinterpret_cast<const float4*>(a.in[k])[i];
+            const float c = a.c[k];
+            acc.x = fmaf(c, v.x, acc.x); acc.y = fmaf(c, v.y, acc.y); acc.z = fmaf(c, v.z, acc.z); acc.w = fmaf(c, v.w, acc.w);
+        }
+        if (noise) {
+            const float4 z = reinterpret_cast<const float4*>(noise)[i];
+            acc.x = fmaf(cn, z.x, acc.x); acc.y = fmaf(cn, z.y, acc.y); acc.z = fmaf(cn, z.z, acc.z); acc.w = fmaf(cn, z.w, acc.w);
+        }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    }
+}
+
+int axpy_launch(int nin, const float* const in[4], const float c[4], const float* noise, float cn, float* out, long n,
+                cudaStream_t s) {
+    if (nin < 1 || nin > 4 || (n & 3)) return -32;
+    AxpyArgs a;
+    for (int k = 0; k < 4; ++k) { a.in[k] = k < nin ? in[k] : nullptr; a.c[k] = k < nin ? c[k] : 0.0f; }
+    const long n4 = n >> 2;
+    long g = (n4 + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    axpy_kernel<<<(int)g, 256, 0, s>>>(nin, a, noise, cn, out, n4);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ layout conversion
+// [B][C][Tv][HW] -> [(b*T+t)][HW][C] through a 32x32 smem transpose (coalesced on both sides)
+__global__ void __launch_bounds__(256) nct_to_frames_kernel(const float* __restrict__ vis, int C, int Tv, int HW, int T,
+                                                           float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int bt = blockIdx.z;                // b*Tv + t
+    const int b = bt / Tv, t = bt % Tv;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, p = p0 + tx;
+        tile[k][tx] = (c < C && p < HW) ? vis[(((size_t)b * C + c) * Tv + t) * HW + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int p = p0 + k, c = c0 + tx;
+        if (c < C && p < HW) dst[(((size_t)b * T + t) * HW + p) * C + c] = tile[tx][k];
+    }
+}
+
+int nct_to_frames_launch(const float* vis, int B, int C, int Tv, int HW, int T, float* dst, cudaStream_t s) {
+    nct_to_frames_kernel<<<dim3((HW + 31) / 32, (C + 31) / 32, B * Tv), 256, 0, s>>>(vis, C, Tv, HW, T, dst);
+    DSB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) audio_tokens_kernel(const float* __restrict__ audio, int T,
+                                                          bf16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int bt = blockIdx.z;
+    const int b = bt / T, t = bt % T;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, p = p0 + tx;
+        tile[k][tx] = (p < 84) ? audio[(((size_t)b * 512 + c) * T + t) * 84 + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int p = p0 + k, c = c0 + tx;
+        if (p < 84) out[(((size_t)b * T + t) * 84 + p) * 512 + c] = __float2bfloat16(tile[tx][k]);
+    }
+}
+
+int audio_tokens_launch(const float* audio, int B, int T, bf16* out, cudaStream_t s) {
+    audio_tokens_kernel<<<dim3(3, 16, B * T), 256, 0, s>>>(audio, T, out);
+    DSB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ x, long n, bf16* __restrict__ out) {
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256)
+        out[i] = __float2bfloat16(x[i]);
+}
+
+int to_bf16_launch(const float* x, long n, bf16* out, cudaStream_t s) {
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g < 1) g = 1;
+    to_bf16_kernel<<<(int)g, 256, 0, s>>>(x, n, out);
+    DSB_LAUNCH_CHECK();
+}
+
+}  // namespace dsb

@@ -1,0 +1,75 @@
+// Memory-bound kernels of the SalUNet denoiser (everything that is not a dense contraction).
+// All activations are channels-last: frames [F][H][W][C]; a clip's frames are contiguous (f = b*T + t).
+#pragma once
+#include "common.cuh"
+
+namespace dsb {
+
+struct TembWeights {
+    const float* w0; const float* b0;      // temb.dense.0  [384,96]
+    const float* w1; const float* b1;      // temb.dense.1  [384,384]
+    const float* wp[3]; const float* bp[3];  // res_encoder.i.0.temb_proj [Cout_i,384]
+    int cout[3];
+};
+
+// t[B] -> per-block temb projections tp_i[B][Cout_i]   (sal_unet.py:15-38,304-307,129)
+int temb_launch(const float* t, int B, const TembWeights& w, float* const tp[3], cudaStream_t s);
+
+// conv_in (3x3, pad 1) composed with down1 (pad right/bottom, 3x3, stride 4) = one 5x5 stride-4 conv 1->96
+// x[B][224][384] -> h0[B][56][96][96]   (sal_unet.py:292-293)
+int stem_launch(const float* x, int B, const float* w5, const float* b5, float* h0, cudaStream_t s);
+
+// GroupNorm(32, eps 1e-6): acc[F][<=64 splits][32][2] (double) receives per-split sums / sums of squares (no atomics,
+// bitwise reproducible); gn_apply adds the splits in a fixed order
+int gn_stats_launch(const float* x, int F, int HW, int C, double* acc, cudaStream_t s);
+// out_act = bf16(swish(GN(x))) ; out_raw = bf16(x) (optional)
+int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, const float* gamma, const float* beta,
+                    bf16* out_act, bf16* out_raw, cudaStream_t s);
+
+// bilinear x2, align_corners=False: fp32 [F][H][W][C] -> bf16 [F][2H][2W][C]
+int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s);
+
+// LayerNorm(eps 1e-5) statistics per token: stats[token] = (mean, rstd)
+int ln_stats_launch(const float* x, long tokens, int C, float2* stats, cudaStream_t s);
+// out = bf16(LN(x) * gamma + beta); tokens of frames with (frame % T) >= tmax are skipped (hw = tokens per frame)
+int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
+                    int T, int tmax, cudaStream_t s);
+
+// q = LN_q( depthwise3x3( LN_norm(x) ) )  -> bf16 [tokens][C]      (attention.py:36-48,92 ; transformer.py:151)
+int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
+                  const float* wq /*[9][C]*/, const float* qg, const float* qb, bf16* out, cudaStream_t s);
+
+// v (or visual-only k) = LN( depthwise sxs stride s ( LN_norm(x) ) ) -> bf16 [F*18][C]   (attention.py:53-76,93)
+int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
+                   const float* nb, const float* wv /*[s*s][C]*/, const float* vg, const float* vb, bf16* out,
+                   cudaStream_t s);
+
+// audio gate: g[b][c][y][x] = softmax_x( mean_t( a[b,t,y/r,x/r,c] * x[b,t,y,x,c] ) )   (transformer.py:140-144)
+int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s);
+// k = LN( depthwise sxs stride s ( scrambled (a*g) ) ) -> bf16 [B*T*18][C]   (transformer.py:145-146, attention.py:89-91)
+int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_,
+                    const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, cudaStream_t s);
+
+// per-frame tensor-core operands of the 18-key, 2-head attention:
+//   KB[f][h*18+j][c] = scale * K[f,j,c] if c in head h else 0        ([F][48][C], rows 36..47 zero)
+//   VB[f][c][h*18+j] = V[f,j,c]         if c in head h else 0        ([F][C][64], cols 36..63 zero)
+int attn_operands_launch(const float* kp, const float* vp, int F, int C, float scale, bf16* KB, bf16* VB,
+                         cudaStream_t s);
+
+// S[b][y][x][c] = sum_i bilinear(r_i -> 112x192)[b,y,x,c]  (bf16)   (sal_unet.py:482-487)
+int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s);
+// bilinear x2 on a single-channel map: p[B][112][192] -> out[B][224][384]   (sal_unet.py:325-327)
+int final_up_launch(const float* p, int B, float* out, cudaStream_t s);
+
+// out = c[0]*in[0] + c[1]*in[1] + ... (nin <= 4) + cn*noise       (sampler updates, n elements)
+int axpy_launch(int nin, const float* const in[4], const float c[4], const float* noise, float cn, float* out, long n,
+                cudaStream_t s);
+
+// vis[B][C][Tv][HW] fp32 -> frames[(b*T + t)][HW][C] for t < Tv  (T = frames per clip in dst)
+int nct_to_frames_launch(const float* vis, int B, int C, int Tv, int HW, int T, float* dst, cudaStream_t s);
+// audio[B][512][T][84] fp32 -> tokens[(b*T+t)*84 + p][512] bf16
+int audio_tokens_launch(const float* audio, int B, int T, bf16* out, cudaStream_t s);
+// fp32 -> bf16 elementwise
+int to_bf16_launch(const float* x, long n, bf16* out, cudaStream_t s);
+
+}  // namespace dsb

@@ -1,0 +1,799 @@
+// Handle, weight store, workspace plan and the C ABI of libdiffsal_b200 (include/diffsal_b200.h).
+//
+// One denoiser evaluation (reference: SalUNet.forward, sal_unet.py:302-328) is lowered at dsb_set_condition time
+// into a flat list of kernel launches over a static workspace; dsb_denoise replays the list on the caller's stream
+// and dsb_sample replays it inside the sampler program (optionally captured into a CUDA graph).
+#include <diffsal_b200.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "conv_plan.cuh"
+#include "kernels.cuh"
+#include "weights.cuh"
+
+using namespace dsb;
+
+namespace {
+
+constexpr int kStageC[4] = {768, 384, 192, 96};
+constexpr int kStageH[4] = {7, 14, 28, 56};
+constexpr int kStageW[4] = {12, 24, 48, 96};
+constexpr int kStageS[4] = {2, 4, 8, 16};
+constexpr int kT = 9;            // frames per clip inside the decoder (8 MViT slices + the noise slice)
+constexpr int kTv = 8;
+constexpr int kReduce = 5;       // ReduceTemp kernel == stride (cfgs/audio_visual.py:62)
+constexpr size_t frame_elems(int i) { return (size_t)64512 << i; }   // C_i * h_i * w_i of decoder stage i
+constexpr size_t kMaxFrame = (size_t)64512 << 3;
+constexpr long kMapElems = 224L * 384L;
+
+struct Weight {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    long numel = 0;
+};
+
+typedef std::function<int(cudaStream_t)> Launch;
+
+struct SamplerGraph {
+    cudaGraphExec_t exec = nullptr;
+};
+
+}  // namespace
+
+struct dsb_handle {
+    dsb_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    std::map<std::string, Weight> w;
+    bool finalized = false;
+    std::vector<void*> allocs;
+    size_t alloc_bytes = 0;
+    size_t weight_bytes = 0;
+
+    // ---- derived weights
+    std::map<std::string, bf16*> wpack;          // K-major bf16 GEMM weights by reference key
+    std::map<std::string, float*> wf;            // derived fp32 tables (bn scale/shift, depthwise taps, stem)
+
+    // ---- workspace (sized for cfg.max_batch)
+    bool ws_ready = false;
+    float* tp[3] = {nullptr, nullptr, nullptr};  // temb projections
+    float* h0 = nullptr;
+    double* gn_acc = nullptr;                    // [6][B][64 splits][32][2]
+    bf16 *enc_act = nullptr, *enc_raw = nullptr, *enc_res = nullptr;
+    float *enc_c1 = nullptr, *enc_sc = nullptr;
+    float* enc_d[3] = {nullptr, nullptr, nullptr};
+    float* back[3] = {nullptr, nullptr, nullptr};
+    float* a_low[4] = {nullptr, nullptr, nullptr, nullptr};
+    bf16* audio_tok = nullptr;
+    float *X[4] = {}, *X1[4] = {}, *X2[4] = {};
+    float* r[4] = {};
+    bf16 *up = nullptr, *mid = nullptr, *q_ln = nullptr, *Qp = nullptr, *k_ln = nullptr, *v_ln = nullptr;
+    float *Kp = nullptr, *Vp = nullptr, *gate = nullptr;
+    bf16 *KB = nullptr, *VB = nullptr, *P = nullptr, *o = nullptr, *ln2 = nullptr, *hid = nullptr, *lnm = nullptr;
+    float2* lnstats = nullptr;
+    bf16* S = nullptr;
+    float* p = nullptr;
+    float* sbuf[8] = {};                          // sampler buffers
+    float* t_all = nullptr;                       // [max evals][B]
+    int t_all_cap = 0;
+
+    // ---- per-condition state
+    int B = 0;
+    bool has_audio = false;
+    std::vector<Launch> prog;                     // one denoiser evaluation
+    const float* cur_x = nullptr;
+    const float* cur_t = nullptr;
+    float* cur_out = nullptr;
+    int64_t last_launches = 0;
+    std::map<std::string, SamplerGraph> graphs;
+    uint64_t cond_epoch = 0;
+};
+
+namespace {
+
+int fail(dsb_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(h, DSB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));       \
+    } while (0)
+
+template <class T>
+int dev_alloc(dsb_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = ((count * sizeof(T) + 255) / 256) * 256;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(h, DSB_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cudaMemset(p, 0, bytes);
+    h->allocs.push_back(p);
+    h->alloc_bytes += bytes;
+    *out = reinterpret_cast<T*>(p);
+    return 0;
+}
+
+const Weight* find_w(dsb_handle* h, const std::string& key) {
+    auto it = h->w.find(key);
+    return it == h->w.end() ? nullptr : &it->second;
+}
+
+int need_w(dsb_handle* h, const std::string& key, std::initializer_list<int64_t> shape, const float** out) {
+    const Weight* w = find_w(h, key);
+    if (!w) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", key.c_str());
+    if (w->shape != std::vector<int64_t>(shape)) return fail(h, DSB_ERR_WEIGHT, "weight '%s' has the wrong shape", key.c_str());
+    *out = w->p;
+    return 0;
+}
+
+const float* W(dsb_handle* h, const std::string& key) {
+    const Weight* w = find_w(h, key);
+    return w ? w->p : nullptr;
+}
+
+// ------------------------------------------------------------------------------------------ finalize helpers
+int pack_gemm_weight(dsb_handle* h, const std::string& key, int N, int Cin, int taps) {
+    const Weight* w = find_w(h, key);
+    if (!w) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", key.c_str());
+    if (w->numel != (long)N * Cin * taps) return fail(h, DSB_ERR_WEIGHT, "weight '%s' has the wrong size", key.c_str());
+    bf16* dst = nullptr;
+    if (int r = dev_alloc(h, &dst, (size_t)N * Cin * taps)) return r;
+    if (int r = pack_weight_launch(w->p, N, Cin, taps, dst, 0)) return fail(h, DSB_ERR_CUDA, "pack_weight launch %d", r);
+    h->wpack[key] = dst;
+    return 0;
+}
+
+int fold_bn(dsb_handle* h, const std::string& bn, const char* conv_bias_key, int C) {
+    const float *w = W(h, bn + ".weight"), *b = W(h, bn + ".bias"), *m = W(h, bn + ".running_mean"),
+                *v = W(h, bn + ".running_var");
+    if (!w || !b || !m || !v) return fail(h, DSB_ERR_WEIGHT, "missing BatchNorm tensors of '%s'", bn.c_str());
+    const float* cb = conv_bias_key ? W(h, conv_bias_key) : nullptr;
+    if (conv_bias_key && !cb) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", conv_bias_key);
+    float *sc = nullptr, *sh = nullptr;
+    if (int r = dev_alloc(h, &sc, C)) return r;
+    if (int r = dev_alloc(h, &sh, C)) return r;
+    if (int r = bn_fold_launch(w, b, m, v, cb, C, 1e-5f, sc, sh, 0)) return fail(h, DSB_ERR_CUDA, "bn_fold launch %d", r);
+    h->wf[bn + ".scale"] = sc;
+    h->wf[bn + ".shift"] = sh;
+    return 0;
+}
+
+int pack_dw(dsb_handle* h, const std::string& key, int C, int taps, int src_stride, int src_off) {
+    const Weight* w = find_w(h, key);
+    if (!w) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", key.c_str());
+    if (w->numel != (long)C * src_stride) return fail(h, DSB_ERR_WEIGHT, "weight '%s' has the wrong size", key.c_str());
+    float* dst = nullptr;
+    if (int r = dev_alloc(h, &dst, (size_t)C * taps)) return r;
+    if (int r = pack_dw_launch(w->p, C, taps, src_stride, src_off, dst, 0)) return fail(h, DSB_ERR_CUDA, "pack_dw launch %d", r);
+    h->wf[key] = dst;
+    return 0;
+}
+
+std::string stage_key(int i) { return "invpt_decoder.mid_stages." + std::to_string(i) + "."; }
+
+// ------------------------------------------------------------------------------------------ workspace
+int alloc_workspace(dsb_handle* h) {
+    const size_t B = (size_t)h->cfg.max_batch;
+    const size_t F = B * kT;
+    const int enc_cout[3] = {192, 384, 768};
+    for (int i = 0; i < 3; ++i)
+        if (int r = dev_alloc(h, &h->tp[i], B * enc_cout[i])) return r;
+    if (int r = dev_alloc(h, &h->h0, B * 5376 * 96)) return r;
+    if (int r = dev_alloc(h, &h->gn_acc, 6 * B * 64 * 64)) return r;
+    // encoder scratch: largest tensors are [B][5376][192]
+    const size_t enc_max = B * 5376 * 192;
+    if (int r = dev_alloc(h, &h->enc_act, enc_max)) return r;
+    if (int r = dev_alloc(h, &h->enc_raw, enc_max)) return r;
+    if (int r = dev_alloc(h, &h->enc_res, enc_max)) return r;
+    if (int r = dev_alloc(h, &h->enc_c1, enc_max)) return r;
+    if (int r = dev_alloc(h, &h->enc_sc, enc_max)) return r;
+    for (int i = 0; i < 3; ++i)
+        if (int r = dev_alloc(h, &h->enc_d[i], B * frame_elems(2 - i))) return r;
+    for (int i = 0; i < 3; ++i)
+        if (int r = dev_alloc(h, &h->back[i], F * frame_elems(i))) return r;
+    if (h->cfg.audio_visual) {
+        for (int i = 0; i < 4; ++i)
+            if (int r = dev_alloc(h, &h->a_low[i], F * 84 * kStageC[i])) return r;
+        if (int r = dev_alloc(h, &h->audio_tok, F * 84 * 512)) return r;
+        if (int r = dev_alloc(h, &h->gate, B * kMaxFrame)) return r;
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (i > 0)
+            if (int r = dev_alloc(h, &h->X[i], F * frame_elems(i))) return r;
+        if (int r = dev_alloc(h, &h->X1[i], F * frame_elems(i))) return r;
+        if (int r = dev_alloc(h, &h->X2[i], F * frame_elems(i))) return r;
+        if (int r = dev_alloc(h, &h->r[i], B * kStageH[i] * kStageW[i] * 768)) return r;
+    }
+    if (int r = dev_alloc(h, &h->up, F * kMaxFrame * 2)) return r;
+    if (int r = dev_alloc(h, &h->mid, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->q_ln, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->Qp, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->k_ln, F * 18 * 768)) return r;
+    if (int r = dev_alloc(h, &h->v_ln, F * 18 * 768)) return r;
+    if (int r = dev_alloc(h, &h->Kp, F * 18 * 768)) return r;
+    if (int r = dev_alloc(h, &h->Vp, F * 18 * 768)) return r;
+    if (int r = dev_alloc(h, &h->KB, F * 48 * 768)) return r;
+    if (int r = dev_alloc(h, &h->VB, F * 768 * 64)) return r;
+    if (int r = dev_alloc(h, &h->P, F * 5376 * 64)) return r;
+    if (int r = dev_alloc(h, &h->o, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->ln2, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->hid, F * kMaxFrame * 2)) return r;
+    if (int r = dev_alloc(h, &h->lnm, F * kMaxFrame)) return r;
+    if (int r = dev_alloc(h, &h->lnstats, F * 5376)) return r;
+    if (int r = dev_alloc(h, &h->S, B * 112 * 192 * 768)) return r;
+    if (int r = dev_alloc(h, &h->p, B * 112 * 192)) return r;
+    for (int i = 0; i < 8; ++i)
+        if (int r = dev_alloc(h, &h->sbuf[i], B * kMapElems)) return r;
+    h->t_all_cap = 1024;
+    if (int r = dev_alloc(h, &h->t_all, (size_t)h->t_all_cap * B)) return r;
+    h->ws_ready = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ program building
+struct Builder {
+    dsb_handle* h;
+    std::vector<Launch>* out;
+    int err = 0;
+
+    void add(Launch l) { out->push_back(std::move(l)); }
+
+    void conv(ConvOp op) {
+        if (err) return;
+        ConvLaunch cl;
+        int r = conv_lower(op, &cl);
+        if (r) { err = fail(h, DSB_ERR_CUDA, "conv_lower failed (%d) for a %dx%d conv %d->%d", r, op.H, op.W, op.Cin, op.N); return; }
+        const int sms = h->num_sms;
+        add([cl, sms](cudaStream_t s) { return conv_run(cl, sms, s); });
+    }
+};
+
+ConvOp make_op(int kind, int F, int H, int W, int Cin, int N, const bf16* A, const bf16* Wt) {
+    ConvOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = kind; op.F = F; op.H = H; op.W = W; op.Cin = Cin; op.N = N; op.A = A; op.Wt = Wt;
+    op.dilation = 1; op.T = 1; op.kt = 1;
+    return op;
+}
+
+int build_program(dsb_handle* h) {
+    h->prog.clear();
+    Builder b{h, &h->prog};
+    const int B = h->B, F = B * kT;
+    auto WP = [&](const std::string& k) -> const bf16* {
+        auto it = h->wpack.find(k);
+        return it == h->wpack.end() ? nullptr : it->second;
+    };
+    auto WF = [&](const std::string& k) -> const float* {
+        auto it = h->wf.find(k);
+        return it == h->wf.end() ? nullptr : it->second;
+    };
+
+    // ------------------------------------------------------------ noise encoder (sal_unet.py:279-300)
+    {
+        TembWeights tw;
+        tw.w0 = W(h, "temb.dense.0.weight"); tw.b0 = W(h, "temb.dense.0.bias");
+        tw.w1 = W(h, "temb.dense.1.weight"); tw.b1 = W(h, "temb.dense.1.bias");
+        const int cout[3] = {192, 384, 768};
+        for (int i = 0; i < 3; ++i) {
+            const std::string r = "res_encoder." + std::to_string(i) + ".0.temb_proj.";
+            tw.wp[i] = W(h, r + "weight"); tw.bp[i] = W(h, r + "bias"); tw.cout[i] = cout[i];
+        }
+        float* tp[3] = {h->tp[0], h->tp[1], h->tp[2]};
+        b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); });
+        const float *w5 = WF("stem.w5"), *b5 = WF("stem.b5");
+        float* h0 = h->h0;
+        b.add([h, w5, b5, h0, B](cudaStream_t s) { return stem_launch(h->cur_x, B, w5, b5, h0, s); });
+
+        const float* cur = h->h0;
+        int Cin = 96, H = 56, Wd = 96;
+        for (int i = 0; i < 3; ++i) {
+            const int Cout = cout[i], HW = H * Wd;
+            const std::string rk = "res_encoder." + std::to_string(i) + ".0.";
+            double* acc1 = h->gn_acc + (size_t)(2 * i) * h->cfg.max_batch * 64 * 64;
+            double* acc2 = h->gn_acc + (size_t)(2 * i + 1) * h->cfg.max_batch * 64 * 64;
+            const float *g1 = W(h, rk + "norm1.weight"), *b1 = W(h, rk + "norm1.bias");
+            const float *g2 = W(h, rk + "norm2.weight"), *b2 = W(h, rk + "norm2.bias");
+            bf16 *act = h->enc_act, *raw = h->enc_raw, *res = h->enc_res;
+            float *c1 = h->enc_c1, *sc = h->enc_sc;
+            b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); });
+            b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); });
+            {   // conv1 + bias + temb projection
+                ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
+                op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
+                b.conv(op);
+            }
+            {   // 1x1 shortcut on the raw block input
+                ConvOp op = make_op(CONV_1X1, B, H, Wd, Cin, Cout, raw, WP(rk + "nin_shortcut.weight"));
+                op.shift = W(h, rk + "nin_shortcut.bias"); op.out_f32 = sc;
+                b.conv(op);
+            }
+            b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); });
+            b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); });
+            {   // conv2 + bias + shortcut -> block output (only ever a GEMM operand: bf16)
+                ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
+                op.shift = W(h, rk + "conv2.bias"); op.residual = sc; op.out_bf16 = res;
+                b.conv(op);
+            }
+            const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
+            float* d = h->enc_d[i];
+            {   // Downsample: pad (0,1,0,1) + 3x3 stride 2
+                ConvOp op = make_op(CONV_3X3_S2, B, H / 2, Wd / 2, Cout, Cout, res, WP(dk + "weight"));
+                op.shift = W(h, dk + "bias"); op.out_f32 = d;
+                b.conv(op);
+            }
+            // noise slice = frame 8 of the stage input / skip tensor (sal_unet.py:311-317)
+            const size_t fe = frame_elems(2 - i);
+            float* dst = h->back[2 - i] + (size_t)kTv * fe;
+            b.add([=](cudaStream_t s) {
+                return (int)cudaMemcpy2DAsync(dst, (size_t)kT * fe * sizeof(float), d, fe * sizeof(float),
+                                              fe * sizeof(float), B, cudaMemcpyDeviceToDevice, s);
+            });
+            cur = d;
+            Cin = Cout; H /= 2; Wd /= 2;
+        }
+    }
+
+    // ------------------------------------------------------------ decoder stages (sal_unet.py:457-491)
+    for (int i = 0; i < 4; ++i) {
+        const int C = kStageC[i], H = kStageH[i], Wd = kStageW[i], HW = H * Wd, sk = kStageS[i];
+        const std::string st = stage_key(i), bk = st + "blocks.0.";
+        const float* Xi;
+        if (i == 0) {
+            Xi = h->back[0];
+        } else {
+            const int Cp = kStageC[i - 1];
+            const float* prev = h->X2[i - 1];
+            bf16* up = h->up;
+            b.add([=](cudaStream_t s) { return upsample2x_launch(prev, F, H / 2, Wd / 2, Cp, up, s); });
+            const std::string pe = st + "patch_embed.0.proj.";
+            {
+                ConvOp op = make_op(CONV_3X3, F, H, Wd, Cp, C, up, WP(pe + "1.weight"));
+                op.dilation = 2; op.scale = WF(pe + "2.scale"); op.shift = WF(pe + "2.shift"); op.act = ACT_RELU;
+                op.out_bf16 = h->mid;
+                b.conv(op);
+            }
+            {
+                ConvOp op = make_op(CONV_3X3, F, H, Wd, C, C, h->mid, WP(pe + "4.weight"));
+                op.dilation = 2; op.scale = WF(pe + "5.scale"); op.shift = WF(pe + "5.shift"); op.act = ACT_RELU;
+                op.residual = (i == 1 || i == 2) ? h->back[i] : nullptr;   // stage 3 has no skip (transformer.py:265-270)
+                op.out_f32 = h->X[i];
+                b.conv(op);
+            }
+            Xi = h->X[i];
+        }
+        const long tokens = (long)F * HW;
+        float2* stats = h->lnstats;
+        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, s); });
+        const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
+        bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
+        const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
+                    *wv = WF(bk + "attn.conv_proj_v.conv.weight");
+        const float *qg = W(h, bk + "attn.conv_proj_q.bn.weight"), *qb = W(h, bk + "attn.conv_proj_q.bn.bias");
+        const float *kg = W(h, bk + "attn.conv_proj_k.bn.weight"), *kb = W(h, bk + "attn.conv_proj_k.bn.bias");
+        const float *vg = W(h, bk + "attn.conv_proj_v.bn.weight"), *vb = W(h, bk + "attn.conv_proj_v.bn.bias");
+        if (h->has_audio) {
+            const float* al = h->a_low[i];
+            float* gate = h->gate;
+            b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); });
+            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, s); });
+        } else {
+            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, s); });
+        }
+        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, s); });
+        b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, s); });
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, q_ln, WP(bk + "attn.proj_q.weight"));
+            op.shift = W(h, bk + "attn.proj_q.bias"); op.out_bf16 = h->Qp;
+            b.conv(op);
+        }
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
+            op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
+            b.conv(op);
+        }
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
+            op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
+            b.conv(op);
+        }
+        {
+            const float *Kp = h->Kp, *Vp = h->Vp;
+            bf16 *KB = h->KB, *VB = h->VB;
+            const float scale = 1.0f / sqrtf((float)C);          // dim_out ** -0.5 (attention.py:33)
+            b.add([=](cudaStream_t s) { return attn_operands_launch(Kp, Vp, F, C, scale, KB, VB, s); });
+        }
+        {   // scores + per-head softmax over the 18 keys
+            ConvOp op = make_op(CONV_1X1, F, 1, HW, C, 48, h->Qp, h->KB);
+            op.b_rows_per_frame = 48; op.out_softmax = h->P;
+            b.conv(op);
+        }
+        {   // P . V
+            ConvOp op = make_op(CONV_1X1, F, 1, HW, 64, C, h->P, h->VB);
+            op.b_rows_per_frame = C; op.out_bf16 = h->o;
+            b.conv(op);
+        }
+        {   // output projection + residual
+            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, h->o, WP(bk + "attn.proj.weight"));
+            op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
+            b.conv(op);
+        }
+        {
+            const float *g2 = W(h, bk + "norm2.weight"), *b2 = W(h, bk + "norm2.bias");
+            const float* x1 = h->X1[i];
+            bf16* ln2 = h->ln2;
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, 1, 1, s); });
+        }
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
+            op.shift = W(h, bk + "mlp.fc1.bias"); op.act = ACT_GELU; op.out_bf16 = h->hid;
+            b.conv(op);
+        }
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, 2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
+            op.shift = W(h, bk + "mlp.fc2.bias"); op.residual = h->X1[i]; op.out_f32 = h->X2[i];
+            b.conv(op);
+        }
+        {   // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU
+            const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";
+            const float *gm = W(h, nk + "weight"), *bm = W(h, nk + "bias");
+            const float* x2 = h->X2[i];
+            bf16* lnm = h->lnm;
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s); });
+            ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
+                                WP("invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight"));
+            op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i];
+            b.conv(op);
+        }
+    }
+
+    // ------------------------------------------------------------ multi-scale head (sal_unet.py:482-489,320-327)
+    {
+        const float* rr[4] = {h->r[0], h->r[1], h->r[2], h->r[3]};
+        bf16* S = h->S;
+        b.add([=](cudaStream_t s) {
+            const float* r4[4] = {rr[0], rr[1], rr[2], rr[3]};
+            return ms_sum_launch(r4, B, S, s);
+        });
+        ConvOp op = make_op(CONV_3X3, B, 112, 192, 768, 96, h->S, WP("invpt_decoder.mt_proj.0.weight"));
+        op.scale = WF("invpt_decoder.mt_proj.1.scale"); op.shift = WF("invpt_decoder.mt_proj.1.shift");
+        op.act = ACT_RELU; op.head_w = W(h, "logits.linear_pred.weight");
+        float hb = 0.0f;
+        cudaMemcpy(&hb, W(h, "logits.linear_pred.bias"), sizeof(float), cudaMemcpyDeviceToHost);
+        op.head_b = hb; op.out_head = h->p;
+        b.conv(op);
+        const float* p = h->p;
+        b.add([h, p, B](cudaStream_t s) { return final_up_launch(p, B, h->cur_out, s); });
+    }
+    return b.err;
+}
+
+int run_program(dsb_handle* h, cudaStream_t s) {
+    for (size_t i = 0; i < h->prog.size(); ++i) {
+        int r = h->prog[i](s);
+        if (r) return fail(h, DSB_ERR_CUDA, "denoiser launch %zu failed: %s (%d)", i,
+                           r > 0 ? cudaGetErrorString((cudaError_t)r) : "launcher error", r);
+    }
+    h->last_launches += (int64_t)h->prog.size();
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" int dsb_create(const dsb_config* cfg, dsb_handle** out) {
+    if (!cfg || !out) return DSB_ERR_ARG;
+    if (cfg->max_batch < 1 || cfg->max_batch > 4096) return DSB_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DSB_ERR_CUDA;   // no CPU fallback
+    dsb_handle* h = new dsb_handle();
+    h->cfg = *cfg;
+    cudaGetDevice(&h->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
+    if (prop.major != 10) {
+        delete h;
+        return DSB_ERR_UNSUPPORTED;      // sm_100a only: tcgen05 / TMEM kernels
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if (gemm_init()) { delete h; return DSB_ERR_CUDA; }
+    *out = h;
+    return DSB_OK;
+}
+
+extern "C" void dsb_destroy(dsb_handle* h) {
+    if (!h) return;
+    for (auto& g : h->graphs)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+extern "C" const char* dsb_last_error(const dsb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" size_t dsb_workspace_bytes(const dsb_handle* h, int B) {
+    if (!h) return 0;
+    if (h->ws_ready && B == h->cfg.max_batch) return h->alloc_bytes;
+    // same formula as alloc_workspace, in bytes per clip (dominant terms) + weights
+    const size_t F = (size_t)B * kT;
+    size_t per = 0;
+    per += F * (size_t)64512 * 4 * (7 + 14 + 15 + 15);     // back, X, X1, X2 over the stages
+    per += F * kMaxFrame * 2 * (2 + 1 + 1 + 1 + 1 + 1 + 2 + 1);   // up, mid, q_ln, Qp, o, ln2, hid, lnm
+    per += F * 5376 * 64 * 2 + F * 5376 * 8;
+    per += (size_t)B * 112 * 192 * 768 * 2 + (size_t)B * 7140 * 768 * 4;
+    per += (size_t)B * 5376 * 192 * (2 * 3 + 4 * 2) + (size_t)B * kMapElems * 4 * 8;
+    return per + h->weight_bytes;
+}
+
+extern "C" int dsb_load_weight(dsb_handle* h, const char* ref_key, const void* data, const int64_t* shape, int ndim) {
+    if (!h || !ref_key || !data || ndim < 0 || ndim > 8) return fail(h, DSB_ERR_ARG, "dsb_load_weight: bad argument");
+    if (h->finalized) return fail(h, DSB_ERR_ARG, "dsb_load_weight after dsb_finalize_weights");
+    Weight w;
+    w.numel = 1;
+    for (int i = 0; i < ndim; ++i) { w.shape.push_back(shape[i]); w.numel *= shape[i]; }
+    if (w.numel < 1) return fail(h, DSB_ERR_ARG, "weight '%s' is empty", ref_key);
+    if (int r = dev_alloc(h, &w.p, (size_t)w.numel)) return r;
+    CUDA_TRY(h, cudaMemcpy(w.p, data, (size_t)w.numel * sizeof(float), cudaMemcpyDefault));
+    h->w[ref_key] = w;
+    return DSB_OK;
+}
+
+extern "C" int dsb_finalize_weights(dsb_handle* h) {
+    if (!h) return DSB_ERR_ARG;
+    if (h->finalized) return fail(h, DSB_ERR_ARG, "weights already finalized");
+    const float* dummy;
+    // ---- noise encoder
+    if (int r = need_w(h, "conv_in.weight", {96, 1, 3, 3}, &dummy)) return r;
+    if (int r = need_w(h, "down1.conv.weight", {96, 96, 3, 3}, &dummy)) return r;
+    for (const char* k : {"conv_in.bias", "down1.conv.bias", "temb.dense.0.weight", "temb.dense.0.bias",
+                          "temb.dense.1.weight", "temb.dense.1.bias", "logits.linear_pred.weight",
+                          "logits.linear_pred.bias"})
+        if (!W(h, k)) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", k);
+    {
+        float *w5 = nullptr, *b5 = nullptr;
+        if (int r = dev_alloc(h, &w5, 25 * 96)) return r;
+        if (int r = dev_alloc(h, &b5, 96)) return r;
+        if (int r = stem_compose_launch(W(h, "conv_in.weight"), W(h, "conv_in.bias"), W(h, "down1.conv.weight"),
+                                        W(h, "down1.conv.bias"), w5, b5, 0))
+            return fail(h, DSB_ERR_CUDA, "stem_compose launch %d", r);
+        h->wf["stem.w5"] = w5;
+        h->wf["stem.b5"] = b5;
+    }
+    int cin = 96;
+    const int cout[3] = {192, 384, 768};
+    for (int i = 0; i < 3; ++i) {
+        const std::string rk = "res_encoder." + std::to_string(i) + ".0.";
+        for (const char* k : {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "conv1.bias", "conv2.bias",
+                              "nin_shortcut.bias", "temb_proj.weight", "temb_proj.bias"})
+            if (!W(h, rk + k)) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s%s'", rk.c_str(), k);
+        if (int r = pack_gemm_weight(h, rk + "conv1.weight", cout[i], cin, 9)) return r;
+        if (int r = pack_gemm_weight(h, rk + "conv2.weight", cout[i], cout[i], 9)) return r;
+        if (int r = pack_gemm_weight(h, rk + "nin_shortcut.weight", cout[i], cin, 1)) return r;
+        const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
+        if (!W(h, dk + "bias")) return fail(h, DSB_ERR_WEIGHT, "missing weight '%sbias'", dk.c_str());
+        if (int r = pack_gemm_weight(h, dk + "weight", cout[i], cout[i], 9)) return r;
+        cin = cout[i];
+    }
+    // ---- decoder stages
+    for (int i = 0; i < 4; ++i) {
+        const int C = kStageC[i], sk = kStageS[i];
+        const std::string st = stage_key(i), bk = st + "blocks.0.";
+        if (i > 0) {
+            const std::string pe = st + "patch_embed.0.proj.";
+            if (int r = pack_gemm_weight(h, pe + "1.weight", C, kStageC[i - 1], 9)) return r;
+            if (int r = pack_gemm_weight(h, pe + "4.weight", C, C, 9)) return r;
+            if (int r = fold_bn(h, pe + "2", nullptr, C)) return r;
+            if (int r = fold_bn(h, pe + "5", nullptr, C)) return r;
+        }
+        for (const char* k : {"norm.weight", "norm.bias", "norm2.weight", "norm2.bias", "attn.conv_proj_q.bn.weight",
+                              "attn.conv_proj_q.bn.bias", "attn.conv_proj_k.bn.weight", "attn.conv_proj_k.bn.bias",
+                              "attn.conv_proj_v.bn.weight", "attn.conv_proj_v.bn.bias", "attn.proj_q.bias",
+                              "attn.proj_k.bias", "attn.proj_v.bias", "attn.proj.bias", "mlp.fc1.bias", "mlp.fc2.bias"})
+            if (!W(h, bk + k)) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s%s'", bk.c_str(), k);
+        for (const char* k : {"attn.proj_q.weight", "attn.proj_k.weight", "attn.proj_v.weight", "attn.proj.weight"})
+            if (int r = pack_gemm_weight(h, bk + k, C, C, 1)) return r;
+        if (int r = pack_gemm_weight(h, bk + "mlp.fc1.weight", 2 * C, C, 1)) return r;
+        if (int r = pack_gemm_weight(h, bk + "mlp.fc2.weight", C, 2 * C, 1)) return r;
+        // depthwise Conv3d(3,3,3) on a depth-1 volume: only the middle temporal tap touches data (attention.py:36-44)
+        if (int r = pack_dw(h, bk + "attn.conv_proj_q.conv.weight", C, 9, 27, 9)) return r;
+        if (int r = pack_dw(h, bk + "attn.conv_proj_k.conv.weight", C, sk * sk, sk * sk, 0)) return r;
+        if (int r = pack_dw(h, bk + "attn.conv_proj_v.conv.weight", C, sk * sk, sk * sk, 0)) return r;
+        if (h->cfg.audio_visual) {
+            if (!W(h, bk + "align_conv.bias")) return fail(h, DSB_ERR_WEIGHT, "missing weight '%salign_conv.bias'", bk.c_str());
+            if (int r = pack_gemm_weight(h, bk + "align_conv.weight", C, 512, 1)) return r;
+        }
+        const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";
+        if (!W(h, nk + "weight") || !W(h, nk + "bias")) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s*'", nk.c_str());
+        if (int r = pack_gemm_weight(h, "invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight", 768, C, kReduce)) return r;
+    }
+    if (int r = pack_gemm_weight(h, "invpt_decoder.mt_proj.0.weight", 96, 768, 9)) return r;
+    if (int r = fold_bn(h, "invpt_decoder.mt_proj.1", "invpt_decoder.mt_proj.0.bias", 96)) return r;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->weight_bytes = h->alloc_bytes;
+    if (int r = alloc_workspace(h)) return r;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->finalized = true;
+    return DSB_OK;
+}
+
+extern "C" int dsb_set_condition(dsb_handle* h, const void* const feat[4], const void* audio, int B, void* stream) {
+    if (!h || !feat) return DSB_ERR_ARG;
+    if (!h->finalized) return fail(h, DSB_ERR_ARG, "dsb_set_condition before dsb_finalize_weights");
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, DSB_ERR_ARG, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+    if (audio && !h->cfg.audio_visual) return fail(h, DSB_ERR_UNSUPPORTED, "audio features given to a visual-only handle");
+    for (int i = 0; i < 3; ++i)
+        if (!feat[i]) return fail(h, DSB_ERR_ARG, "feat[%d] is null", i);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool rebuild = (B != h->B) || ((audio != nullptr) != h->has_audio) || h->prog.empty();
+    h->B = B;
+    h->has_audio = audio != nullptr;
+    // frames 0..7 of the stage-0 input and of the two skip tensors (feat[3] is never read: sal_unet.py:311-317)
+    for (int i = 0; i < 3; ++i) {
+        int r = nct_to_frames_launch((const float*)feat[i], B, kStageC[i], kTv, kStageH[i] * kStageW[i], kT, h->back[i], s);
+        if (r) return fail(h, DSB_ERR_CUDA, "nct_to_frames launch failed (%d)", r);
+    }
+    if (audio) {
+        // loop-invariant align_conv of every stage (transformer.py:128-131), at 7x12
+        int r = audio_tokens_launch((const float*)audio, B, kT, h->audio_tok, s);
+        if (r) return fail(h, DSB_ERR_CUDA, "audio_tokens launch failed (%d)", r);
+        for (int i = 0; i < 4; ++i) {
+            const std::string bk = stage_key(i) + "blocks.0.";
+            ConvOp op = make_op(CONV_1X1, 1, 1, B * kT * 84, 512, kStageC[i], h->audio_tok, h->wpack[bk + "align_conv.weight"]);
+            op.shift = W(h, bk + "align_conv.bias"); op.out_f32 = h->a_low[i];
+            ConvLaunch cl;
+            if ((r = conv_lower(op, &cl))) return fail(h, DSB_ERR_CUDA, "conv_lower(align_conv) failed (%d)", r);
+            if ((r = conv_run(cl, h->num_sms, s))) return fail(h, DSB_ERR_CUDA, "align_conv launch failed (%d)", r);
+        }
+    }
+    if (rebuild) {
+        for (auto& g : h->graphs)
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        h->graphs.clear();
+        if (int r = build_program(h)) return r;
+    }
+    h->cond_epoch++;
+    return DSB_OK;
+}
+
+extern "C" int dsb_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream) {
+    if (!h || !x || !t || !out) return DSB_ERR_ARG;
+    if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_denoise before dsb_set_condition");
+    if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
+    h->cur_x = x; h->cur_t = t; h->cur_out = out;
+    h->last_launches = 0;
+    return run_program(h, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_sampler_update(dsb_handle* h, const float* coef, const float* const* in, int nin,
+                                  const float* noise, float noise_coef, float* out, int64_t n, void* stream) {
+    if (!coef || !in || !out) return DSB_ERR_ARG;     // h may be NULL: the update needs no handle state
+    if (nin < 1 || nin > 4 || n < 4 || (n & 3)) return fail(h, DSB_ERR_ARG, "dsb_sampler_update: nin in [1,4], n %% 4 == 0");
+    const float* ins[4] = {nullptr, nullptr, nullptr, nullptr};
+    float cs[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nin; ++k) { ins[k] = in[k]; cs[k] = coef[k]; }
+    int r = axpy_launch(nin, ins, cs, noise, noise_coef, out, (long)n, (cudaStream_t)stream);
+    if (r) return fail(h, DSB_ERR_CUDA, "axpy launch failed (%d)", r);
+    return DSB_OK;
+}
+
+static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cudaStream_t s) {
+    const long n = (long)B * kMapElems;
+    int eval_idx = 0;
+    for (int i = 0; i < d->n_ops; ++i) {
+        const dsb_sampler_op& op = d->ops[i];
+        if (op.kind == DSB_OP_EVAL) {
+            h->cur_x = h->sbuf[0];
+            h->cur_t = h->t_all + (size_t)eval_idx * B;
+            h->cur_out = h->sbuf[1];
+            ++eval_idx;
+            if (int r = run_program(h, s)) return r;
+        } else if (op.kind == DSB_OP_AXPY) {
+            if (op.nin < 1 || op.nin > 4 || op.dst < 0 || op.dst > 7) return fail(h, DSB_ERR_ARG, "sampler op %d malformed", i);
+            const float* ins[4] = {nullptr, nullptr, nullptr, nullptr};
+            float cs[4] = {0, 0, 0, 0};
+            for (int k = 0; k < op.nin; ++k) {
+                if (op.src[k] < 0 || op.src[k] > 7) return fail(h, DSB_ERR_ARG, "sampler op %d: bad source buffer", i);
+                ins[k] = h->sbuf[op.src[k]];
+                cs[k] = op.coef[k];
+            }
+            const float* nz = (op.noise_index >= 0 && d->noise) ? d->noise + (size_t)op.noise_index * n : nullptr;
+            int r = axpy_launch(op.nin, ins, cs, nz, op.noise_coef, h->sbuf[op.dst], n, s);
+            if (r) return fail(h, DSB_ERR_CUDA, "axpy launch failed (%d)", r);
+            h->last_launches += 1;
+        } else {
+            return fail(h, DSB_ERR_ARG, "sampler op %d: unknown kind %d", i, op.kind);
+        }
+    }
+    return DSB_OK;
+}
+
+extern "C" int dsb_sample(dsb_handle* h, const dsb_sampler_desc* d, float* x_inout, int B, void* stream) {
+    if (!h || !d || !x_inout || !d->ops || d->n_ops < 1) return DSB_ERR_ARG;
+    if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_sample before dsb_set_condition");
+    if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)B * kMapElems * sizeof(float);
+    // model times of all EVAL ops, replicated per clip
+    std::vector<float> ts;
+    for (int i = 0; i < d->n_ops; ++i)
+        if (d->ops[i].kind == DSB_OP_EVAL)
+            for (int b = 0; b < B; ++b) ts.push_back(d->ops[i].t);
+    if ((int)(ts.size() / B) > h->t_all_cap) return fail(h, DSB_ERR_UNSUPPORTED, "more than %d evaluations", h->t_all_cap);
+    h->last_launches = 0;
+    if (!ts.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->t_all, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));     // ts is a stack/heap temporary
+    CUDA_TRY(h, cudaMemcpyAsync(h->sbuf[0], x_inout, bytes, cudaMemcpyDeviceToDevice, s));
+    int rc = DSB_OK;
+    if (d->use_graph) {
+        std::string key((const char*)d->ops, sizeof(dsb_sampler_op) * (size_t)d->n_ops);
+        key.append((const char*)&d->noise, sizeof(d->noise));
+        key.append((const char*)&B, sizeof(B));
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            cudaStream_t cs = nullptr;
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) { cudaStreamDestroy(cs); return fail(h, DSB_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+            rc = enqueue_sampler(h, d, B, cs);
+            e = cudaStreamEndCapture(cs, &graph);
+            cudaStreamDestroy(cs);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(h, DSB_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+            SamplerGraph sg;
+            e = cudaGraphInstantiate(&sg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(h, DSB_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+            it = h->graphs.emplace(key, sg).first;
+        } else {
+            // launches counted as if enqueued individually
+            int evals = 0, axpys = 0;
+            for (int i = 0; i < d->n_ops; ++i) (d->ops[i].kind == DSB_OP_EVAL ? evals : axpys)++;
+            h->last_launches = (int64_t)evals * (int64_t)h->prog.size() + axpys;
+        }
+        CUDA_TRY(h, cudaGraphLaunch(it->second.exec, s));
+    } else {
+        rc = enqueue_sampler(h, d, B, s);
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(x_inout, h->sbuf[0], bytes, cudaMemcpyDeviceToDevice, s));
+    return DSB_OK;
+}
+
+extern "C" int64_t dsb_last_launch_count(const dsb_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" int64_t dsb_debug_read(dsb_handle* h, const char* name, float* dst, int64_t max_elems, void* stream) {
+    if (!h || !name || !dst || h->B == 0) return DSB_ERR_ARG;
+    const std::string n(name);
+    const float* src = nullptr;
+    int64_t count = 0;
+    const int B = h->B;
+    if (n.size() == 2 && n[0] == 'x' && n[1] >= '0' && n[1] <= '3') { src = h->X2[n[1] - '0']; count = (int64_t)B * kT * (int64_t)frame_elems(n[1] - '0'); }
+    else if (n.size() == 2 && n[0] == 'r' && n[1] >= '0' && n[1] <= '3') { const int i = n[1] - '0'; src = h->r[i]; count = (int64_t)B * kStageH[i] * kStageW[i] * 768; }
+    else if (n.size() == 6 && n.compare(0, 5, "noise") == 0 && n[5] >= '0' && n[5] <= '2') { src = h->enc_d[2 - (n[5] - '0')]; count = (int64_t)B * (int64_t)frame_elems(n[5] - '0'); }
+    else if (n == "p") { src = h->p; count = (int64_t)B * 112 * 192; }
+    else if (n == "h0") { src = h->h0; count = (int64_t)B * 5376 * 96; }
+    else if (n.size() == 3 && n.compare(0, 2, "tp") == 0 && n[2] >= '0' && n[2] <= '2') { const int c[3] = {192, 384, 768}; src = h->tp[n[2] - '0']; count = (int64_t)B * c[n[2] - '0']; }
+    else if (n.size() == 2 && n[0] == 'a' && n[1] >= '0' && n[1] <= '3' && h->has_audio) { const int i = n[1] - '0'; src = h->a_low[i]; count = (int64_t)B * kT * 84 * kStageC[i]; }
+    else return fail(h, DSB_ERR_ARG, "unknown debug buffer '%s'", name);
+    if (count > max_elems) return fail(h, DSB_ERR_ARG, "debug buffer '%s' needs %lld elements", name, (long long)count);
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)count * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(h, DSB_ERR_CUDA, "debug copy failed: %s", cudaGetErrorString(e));
+    return count;
+}

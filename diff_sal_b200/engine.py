@@ -1,0 +1,204 @@
+"""Thin ctypes binding of libdiffsal_b200's C ABI (include/diffsal_b200.h).
+
+PyTorch is used only for device memory and streams; every FLOP of the denoiser runs in the
+hand-written sm_100a kernels behind the handle.  No fallback: a missing library, a missing GPU or
+an unsupported configuration raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+OP_EVAL, OP_AXPY = 0, 1
+
+
+class DsbConfig(ctypes.Structure):
+    _fields_ = [("max_batch", ctypes.c_int), ("audio_visual", ctypes.c_int), ("reserved", ctypes.c_int * 6)]
+
+
+class DsbSamplerOp(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("t", ctypes.c_float), ("dst", ctypes.c_int), ("nin", ctypes.c_int),
+                ("src", ctypes.c_int * 4), ("coef", ctypes.c_float * 4), ("noise_coef", ctypes.c_float),
+                ("noise_index", ctypes.c_int)]
+
+
+class DsbSamplerDesc(ctypes.Structure):
+    _fields_ = [("ops", ctypes.POINTER(DsbSamplerOp)), ("n_ops", ctypes.c_int), ("noise", ctypes.c_void_p),
+                ("use_graph", ctypes.c_int)]
+
+
+class DsbError(RuntimeError):
+    pass
+
+
+def _bind(lib):
+    if getattr(lib, "_dsb_bound", False):
+        return lib
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.dsb_create.argtypes = [ctypes.POINTER(DsbConfig), ctypes.POINTER(vp)]
+    lib.dsb_create.restype = ci
+    lib.dsb_destroy.argtypes = [vp]
+    lib.dsb_destroy.restype = None
+    lib.dsb_last_error.argtypes = [vp]
+    lib.dsb_last_error.restype = ctypes.c_char_p
+    lib.dsb_workspace_bytes.argtypes = [vp, ci]
+    lib.dsb_workspace_bytes.restype = ctypes.c_size_t
+    lib.dsb_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.dsb_load_weight.restype = ci
+    lib.dsb_finalize_weights.argtypes = [vp]
+    lib.dsb_finalize_weights.restype = ci
+    lib.dsb_set_condition.argtypes = [vp, ctypes.POINTER(vp), vp, ci, vp]
+    lib.dsb_set_condition.restype = ci
+    lib.dsb_denoise.argtypes = [vp, vp, vp, vp, ci, vp]
+    lib.dsb_denoise.restype = ci
+    lib.dsb_sampler_update.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(vp), ci, vp, cf, vp, ctypes.c_int64, vp]
+    lib.dsb_sampler_update.restype = ci
+    lib.dsb_sample.argtypes = [vp, ctypes.POINTER(DsbSamplerDesc), vp, ci, vp]
+    lib.dsb_sample.restype = ci
+    lib.dsb_last_launch_count.argtypes = [vp]
+    lib.dsb_last_launch_count.restype = ctypes.c_int64
+    lib.dsb_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]
+    lib.dsb_debug_read.restype = ctypes.c_int64
+    lib._dsb_bound = True
+    return lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One handle = one device, one weight set, one workspace sized for ``max_batch`` clips."""
+
+    def __init__(self, max_batch=8, audio_visual=True, device=None):
+        if not torch.cuda.is_available():
+            raise DsbError("diff_sal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _bind(_lib.lib())
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_batch = int(max_batch)
+        self.audio_visual = bool(audio_visual)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            cfg = DsbConfig(self.max_batch, int(self.audio_visual))
+            rc = self.lib.dsb_create(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            raise DsbError("dsb_create failed with %d (needs an sm_100 GPU)" % rc)
+        self._cond = None
+        self.batch = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dsb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0 or (rc != 0 and what != "debug"):
+            msg = self.lib.dsb_last_error(self._h)
+            raise DsbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+        return rc
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, prefix=""):
+        """Loads a reference-keyed SalUNet state_dict (sal_unet.py:146; optional DDP/container
+        prefix such as 'module.decoder_net.').  num_batches_tracked entries are ignored."""
+        with torch.cuda.device(self.device):
+            for key, val in state_dict.items():
+                if prefix:
+                    if not key.startswith(prefix):
+                        continue
+                    key = key[len(prefix):]
+                if key.endswith("num_batches_tracked"):
+                    continue
+                t = val.detach().to(dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                self._check(self.lib.dsb_load_weight(self._h, key.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()),
+                            "dsb_load_weight(%s)" % key)
+            self._check(self.lib.dsb_finalize_weights(self._h), "dsb_finalize_weights")
+
+    # ------------------------------------------------------------------ condition
+    def set_condition(self, feat_list, audio=None):
+        feats = [f.to(device=self.device, dtype=torch.float32).contiguous() for f in feat_list[:3]]
+        B = feats[0].shape[0]
+        exp = [(768, 8, 7, 12), (384, 8, 14, 24), (192, 8, 28, 48)]
+        for f, e in zip(feats, exp):
+            if tuple(f.shape[1:]) != e or f.shape[0] != B:
+                raise DsbError("feature tensor of shape %s, expected [B,%d,%d,%d,%d]" % ((tuple(f.shape),) + e))
+        aud = None
+        if audio is not None:
+            aud = audio.to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(aud.shape) != (B, 512, 9, 7, 12):
+                raise DsbError("audio features of shape %s, expected [%d,512,9,7,12]" % (tuple(aud.shape), B))
+        ptrs = (ctypes.c_void_p * 4)(feats[0].data_ptr(), feats[1].data_ptr(), feats[2].data_ptr(), 0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_set_condition(self._h, ptrs, _lib.ptr(aud), B, _stream()), "dsb_set_condition")
+        self._cond = (feats, aud)      # keep alive until the enqueued conversion kernels have run
+        self.batch = B
+
+    # ------------------------------------------------------------------ one evaluation
+    def denoise(self, x, t, out=None):
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        if tuple(x.shape) != (B, 1, 224, 384):
+            raise DsbError("x of shape %s, expected [B,1,224,384]" % (tuple(x.shape),))
+        t = torch.as_tensor(t).to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        if t.numel() == 1 and B > 1:
+            t = t.expand(B).contiguous()
+        if t.numel() != B:
+            raise DsbError("t has %d entries for a batch of %d" % (t.numel(), B))
+        if out is None:
+            out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_denoise(self._h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), B, _stream()), "dsb_denoise")
+        return out
+
+    def sampler_update(self, coefs, tensors, noise=None, noise_coef=0.0, out=None):
+        n = tensors[0].numel()
+        if out is None:
+            out = torch.empty_like(tensors[0])
+        cs = (ctypes.c_float * len(coefs))(*[float(c) for c in coefs])
+        ps = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_sampler_update(self._h, cs, ps, len(tensors), _lib.ptr(noise), float(noise_coef),
+                                                    _lib.ptr(out), n, _stream()), "dsb_sampler_update")
+        return out
+
+    # ------------------------------------------------------------------ whole loop
+    def sample(self, ops, x, noise=None, use_graph=True):
+        """Runs a sampler program (list of ('eval', t) / ('axpy', dst, [(src, coef), ...], noise_coef,
+        noise_index)) in place on x [B,1,224,384]."""
+        arr = (DsbSamplerOp * len(ops))()
+        for i, op in enumerate(ops):
+            o = arr[i]
+            if op[0] == "eval":
+                o.kind, o.t, o.noise_index = OP_EVAL, float(op[1]), -1
+            else:
+                _, dst, terms, ncoef, nidx = op
+                o.kind, o.dst, o.nin = OP_AXPY, int(dst), len(terms)
+                for k, (s, c) in enumerate(terms):
+                    o.src[k] = int(s)
+                    o.coef[k] = float(c)
+                o.noise_coef = float(ncoef)
+                o.noise_index = int(nidx)
+        desc = DsbSamplerDesc(arr, len(ops), _lib.ptr(noise).value, int(bool(use_graph)))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_sample(self._h, ctypes.byref(desc), _lib.ptr(x), x.shape[0], _stream()), "dsb_sample")
+        return x
+
+    def last_launch_count(self):
+        return int(self.lib.dsb_last_launch_count(self._h))
+
+    def workspace_bytes(self, B=None):
+        return int(self.lib.dsb_workspace_bytes(self._h, self.max_batch if B is None else B))
+
+    def debug_read(self, name, numel):
+        buf = torch.empty(numel, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            n = self._check(self.lib.dsb_debug_read(self._h, name.encode(), _lib.ptr(buf), numel, _stream()), "debug")
+        return buf[:n]

@@ -1,0 +1,533 @@
+"""Host side of the sampling loop: schedules, step coefficients and the reference-compatible sampler API.
+
+All per-step scalar math (the reference does ~30 tiny device ops per step for it, sampler.py:114-167,1255-1294) runs
+here on the host in float64 from the reference's fp32 tables; every tensor update is one launch of the fused axpy
+kernel (dsb_sampler_update), or the whole loop is compiled to a program of EVAL / AXPY ops and run by dsb_sample
+(optionally as one CUDA graph).
+
+API mirrored from /root/reference (same names, argument meaning, error behaviour):
+  get_beta_schedule                         models/diffusion_decoder/diffusion_utils.py:5-45
+  NoiseScheduleVP / model_wrapper / DPM_Solver.sample(method="multistep")
+                                            models/dpm_solver/sampler.py:6-167,170-334,336-1247
+  DiffusionSampler.sample_ddim / sample_image   diffusion_trainer.py:439-480,545-640
+  compute_alpha / generalized_steps         util/denoising.py:3-36
+"""
+import math
+
+import numpy as np
+import torch
+
+# ============================================================================================ schedules
+
+
+def get_beta_schedule(beta_schedule, *, beta_start, beta_end, num_diffusion_timesteps):
+    """float64 numpy betas, diffusion_utils.py:5-45."""
+    n = num_diffusion_timesteps
+    if beta_schedule == "quad":
+        betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=np.float64) ** 2
+    elif beta_schedule == "linear":
+        betas = np.linspace(beta_start, beta_end, n, dtype=np.float64)
+    elif beta_schedule == "const":
+        betas = beta_end * np.ones(n, dtype=np.float64)
+    elif beta_schedule == "jsd":
+        betas = 1.0 / np.linspace(n, 1, n, dtype=np.float64)
+    elif beta_schedule == "sigmoid":
+        betas = np.linspace(-6, 6, n)
+        betas = 1 / (np.exp(-betas) + 1) * (beta_end - beta_start) + beta_start
+    elif beta_schedule == "cosine":
+        step = n + 1
+        s = 0.008
+        x = np.linspace(0, step, step)
+        ac = np.cos(((x / step) + s) / (1 + s) * np.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        betas = np.clip(1 - (ac[1:] / ac[:-1]), a_min=0, a_max=0.999)
+    else:
+        raise NotImplementedError(beta_schedule)
+    assert betas.shape == (n,)
+    return betas
+
+
+def to_torch(a):
+    return torch.tensor(a, dtype=torch.float32)
+
+
+def _as_fp32_cpu(betas):
+    if isinstance(betas, torch.Tensor):
+        return betas.detach().to(device="cpu", dtype=torch.float32)
+    return torch.tensor(np.asarray(betas), dtype=torch.float32)
+
+
+class DdimTables:
+    """diffusion_trainer.py:47-76: fp32 cumprod of fp32 (1 - beta), kept as host float64 scalars."""
+
+    def __init__(self, betas):
+        b = _as_fp32_cpu(betas)
+        ah = (1.0 - b).cumprod(dim=0)
+        self.num_timesteps = b.shape[0]
+        self.alphas_hat = ah.double().numpy()
+        self.sqrt_alphas_hat = torch.sqrt(ah).double().numpy()
+        self.sqrt_recip_alphas_hat = torch.sqrt(1.0 / ah).double().numpy()
+        self.sqrt_recipm1_alphas_hat = torch.sqrt(1.0 / ah - 1).double().numpy()
+
+
+def _scalar(t):
+    if isinstance(t, torch.Tensor):
+        return float(t.reshape(-1)[0].item())
+    if isinstance(t, np.ndarray):
+        return float(t.reshape(-1)[0])
+    return float(t)
+
+
+class NoiseScheduleVP:
+    """Forward-SDE wrapper with the reference's discrete-time semantics (sampler.py:6-167).
+
+    The log-alpha table is built exactly like the reference (fp32 cumsum, clip where lambda < -5.1, which
+    truncates the cosine schedule to total_N = 996); evaluation is piecewise-linear interpolation with the
+    outermost segments extended (interpolate_fn, sampler.py:1255-1294), done on the host in float64.
+    Methods accept python floats or 1-element tensors and return python floats.
+    """
+
+    def __init__(self, schedule="discrete", betas=None, alphas_cumprod=None, continuous_beta_0=0.1,
+                 continuous_beta_1=20.0, dtype=torch.float32):
+        if schedule not in ["discrete", "linear"]:
+            raise ValueError("Unsupported noise schedule {}. The schedule needs to be 'discrete' or 'linear'".format(schedule))
+        self.schedule = schedule
+        self.T = 1.0
+        if schedule == "discrete":
+            if betas is not None:
+                log_alphas = 0.5 * torch.log(1 - _as_fp32_cpu(betas)).cumsum(dim=0)
+            else:
+                assert alphas_cumprod is not None
+                log_alphas = 0.5 * torch.log(_as_fp32_cpu(alphas_cumprod))
+            log_alphas = self.numerical_clip_alpha(log_alphas)
+            self.total_N = int(log_alphas.shape[0])
+            self.log_alpha_array = log_alphas.to(dtype).double().numpy()
+            self.t_array = torch.linspace(0.0, 1.0, self.total_N + 1)[1:].to(dtype).double().numpy()
+        else:
+            self.total_N = 1000
+            self.beta_0 = continuous_beta_0
+            self.beta_1 = continuous_beta_1
+
+    @staticmethod
+    def numerical_clip_alpha(log_alphas, clipped_lambda=-5.1):
+        log_sigmas = 0.5 * torch.log(1.0 - torch.exp(2.0 * log_alphas))
+        lambs = log_alphas - log_sigmas
+        idx = int(torch.searchsorted(torch.flip(lambs, [0]), torch.tensor(clipped_lambda)).item())
+        if idx > 0:
+            log_alphas = log_alphas[:-idx]
+        return log_alphas
+
+    @staticmethod
+    def _interp(x, xp, yp):
+        k = len(xp)
+        idx = int(np.searchsorted(xp, x, side="left"))
+        i0 = 0 if idx == 0 else (k - 2 if idx == k else idx - 1)
+        return yp[i0] + (x - xp[i0]) * (yp[i0 + 1] - yp[i0]) / (xp[i0 + 1] - xp[i0])
+
+    def marginal_log_mean_coeff(self, t):
+        t = _scalar(t)
+        if self.schedule == "discrete":
+            return float(self._interp(t, self.t_array, self.log_alpha_array))
+        return -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+
+    def marginal_alpha(self, t):
+        return math.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return math.sqrt(1.0 - math.exp(2.0 * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        la = self.marginal_log_mean_coeff(t)
+        return la - 0.5 * math.log(1.0 - math.exp(2.0 * la))
+
+    def inverse_lambda(self, lamb):
+        lamb = _scalar(lamb)
+        if self.schedule == "linear":
+            tmp = 2.0 * (self.beta_1 - self.beta_0) * np.logaddexp(-2.0 * lamb, 0.0)
+            delta = self.beta_0 ** 2 + tmp
+            return float(tmp / (math.sqrt(delta) + self.beta_0) / (self.beta_1 - self.beta_0))
+        log_alpha = -0.5 * float(np.logaddexp(0.0, -2.0 * lamb))
+        return float(self._interp(log_alpha, self.log_alpha_array[::-1], self.t_array[::-1]))
+
+    def model_time(self, t_continuous):
+        """model_wrapper.get_model_input_time (sampler.py:271-280): note the literal 1000."""
+        if self.schedule == "discrete":
+            return (_scalar(t_continuous) - 1.0 / self.total_N) * 1000.0
+        return _scalar(t_continuous)
+
+
+# ============================================================================================ elementwise updates
+
+
+def _axpy(coefs, tensors, noise=None, noise_coef=0.0, out=None):
+    """out = sum_k coefs[k] * tensors[k] + noise_coef * noise through the fused CUDA kernel (no CPU path)."""
+    import ctypes
+    from . import _lib
+    from .engine import _bind, _stream
+    t0 = tensors[0]
+    if not t0.is_cuda:
+        raise RuntimeError("diff_sal_b200 sampler updates run on the GPU only (got a %s tensor)" % t0.device)
+    lib = _bind(_lib.lib())
+    ts = [t.to(dtype=torch.float32).contiguous() for t in tensors]
+    if out is None:
+        out = torch.empty_like(ts[0])
+    n = ts[0].numel()
+    if n % 4:
+        raise RuntimeError("sampler update needs a multiple of 4 elements")
+    while len(ts) > 4:          # fold long sums pairwise (not reached by the reference's solvers)
+        raise RuntimeError("at most 4 terms per update")
+    cs = (ctypes.c_float * len(ts))(*[float(c) for c in coefs])
+    ps = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    with torch.cuda.device(t0.device):
+        rc = lib.dsb_sampler_update(None, cs, ps, len(ts), _lib.ptr(noise), float(noise_coef), _lib.ptr(out), n, _stream())
+    if rc != 0:
+        raise RuntimeError("dsb_sampler_update failed (%d)" % rc)
+    return out
+
+
+# ============================================================================================ model_wrapper
+
+
+class _WrappedModel:
+    """Callable returned by model_wrapper; carries what DPM_Solver needs to compile the loop."""
+
+    def __init__(self, model, noise_schedule, model_type, model_kwargs):
+        self.model = model
+        self.noise_schedule = noise_schedule
+        self.model_type = model_type
+        self.model_kwargs = model_kwargs
+
+    def raw(self, x, t_continuous, img=None):
+        ns = self.noise_schedule
+        t_in = torch.full((x.shape[0],), ns.model_time(t_continuous), dtype=torch.float32, device=x.device)
+        return self.model(x, t_in, img, **self.model_kwargs)
+
+    def mix(self, t_continuous):
+        """noise prediction = cx * x + cr * raw_output  (sampler.py:287-298)."""
+        ns = self.noise_schedule
+        if self.model_type == "noise":
+            return 0.0, 1.0
+        a, s = ns.marginal_alpha(t_continuous), ns.marginal_std(t_continuous)
+        if self.model_type == "x_start":
+            return 1.0 / s, -a / s
+        if self.model_type == "v":
+            return s, a
+        if self.model_type == "score":
+            return 0.0, -s
+        raise ValueError(self.model_type)
+
+    def __call__(self, x, t_continuous, img=None):
+        out = self.raw(x, t_continuous, img)
+        cx, cr = self.mix(t_continuous)
+        if cx == 0.0 and cr == 1.0:
+            return out
+        return _axpy([cx, cr], [x, out])
+
+
+def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, guidance_type="uncond", condition=None,
+                  unconditional_condition=None, guidance_scale=1.0, classifier_fn=None, classifier_kwargs={}):
+    """sampler.py:170-334.  ``model(x, t_input, img, **model_kwargs)`` is the denoiser; only the unconditional
+    guidance path is reachable from DiffSal (diffusion_trainer.py:598-608); the classifier variants fail loudly."""
+    assert model_type in ["noise", "x_start", "v", "score"]
+    assert guidance_type in ["uncond", "classifier", "classifier-free"]
+    if guidance_type != "uncond":
+        raise NotImplementedError("guidance_type=%r is outside the DiffSal hot path (uncond only)" % guidance_type)
+    return _WrappedModel(model, noise_schedule, model_type, dict(model_kwargs))
+
+
+# ============================================================================================ step coefficients
+
+
+def dpm_time_steps(ns, skip_type, t_T, t_0, N):
+    """DPM_Solver.get_time_steps (sampler.py:454-481)."""
+    if skip_type == "logSNR":
+        lam_T, lam_0 = ns.marginal_lambda(t_T), ns.marginal_lambda(t_0)
+        # the reference round-trips both ends through fp32 (.cpu().item() of fp32 tensors) and linspaces in fp32
+        ls = torch.linspace(float(np.float32(lam_T)), float(np.float32(lam_0)), N + 1).double().numpy()
+        return [ns.inverse_lambda(l) for l in ls]
+    if skip_type == "time_uniform":
+        return [float(v) for v in torch.linspace(t_T, t_0, N + 1).double().numpy()]
+    if skip_type == "time_quadratic":
+        return [float(v) for v in torch.linspace(t_T ** 0.5, t_0 ** 0.5, N + 1).pow(2).double().numpy()]
+    raise ValueError("Unsupported skip_type {}, need to be 'logSNR' or 'time_uniform' or 'time_quadratic'".format(skip_type))
+
+
+def multistep_update_coefs(ns, algorithm_type, t_prev, t, order, solver_type="dpmsolver"):
+    """x_t = c_x * x + sum_k c_m[k] * m_k, with m_0 the newest model value (t_prev[-1]).
+    Expands dpm_solver_first_update / multistep second / third update (sampler.py:548-593,797-905)."""
+    pp = algorithm_type == "dpmsolver++"
+    lam_t, lam_0 = ns.marginal_lambda(t), ns.marginal_lambda(t_prev[-1])
+    h = lam_t - lam_0
+    la_0, la_t = ns.marginal_log_mean_coeff(t_prev[-1]), ns.marginal_log_mean_coeff(t)
+    sig_0, sig_t = ns.marginal_std(t_prev[-1]), ns.marginal_std(t)
+    alpha_t = math.exp(la_t)
+    phi_1 = math.expm1(-h) if pp else math.expm1(h)
+    c_x = (sig_t / sig_0) if pp else math.exp(la_t - la_0)
+    b1 = (alpha_t * phi_1) if pp else (sig_t * phi_1)          # x_t = c_x x - b1 m0 ...
+    if order == 1:
+        return c_x, [-b1]
+    if order == 2:
+        r0 = (lam_0 - ns.marginal_lambda(t_prev[-2])) / h
+        if solver_type == "dpmsolver":
+            d = -0.5 * b1                                      # ... - 0.5 b1 D1
+        elif solver_type == "taylor":
+            d = alpha_t * (phi_1 / h + 1.0) if pp else -sig_t * (phi_1 / h - 1.0)
+        else:
+            raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+        # D1 = (m0 - m1) / r0
+        return c_x, [-b1 + d / r0, -d / r0]
+    if order == 3:
+        lam_1, lam_2 = ns.marginal_lambda(t_prev[-2]), ns.marginal_lambda(t_prev[-3])
+        r0, r1 = (lam_0 - lam_1) / h, (lam_1 - lam_2) / h
+        if pp:
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            e1, e2 = alpha_t * phi_2, -alpha_t * phi_3
+        else:
+            phi_2 = phi_1 / h - 1.0
+            phi_3 = phi_2 / h - 0.5
+            e1, e2 = -sig_t * phi_2, -sig_t * phi_3
+        # D1_0 = (m0-m1)/r0, D1_1 = (m1-m2)/r1, D1 = D1_0 + r0/(r0+r1) (D1_0-D1_1), D2 = (D1_0-D1_1)/(r0+r1)
+        g = r0 / (r0 + r1)
+        a0 = e1 * (1.0 + g) + e2 / (r0 + r1)                   # coefficient of D1_0
+        a1 = -e1 * g - e2 / (r0 + r1)                          # coefficient of D1_1
+        return c_x, [-b1 + a0 / r0, -a0 / r0 + a1 / r1, -a1 / r1]
+    raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
+
+
+# program buffer ids (include/diffsal_b200.h): 0 = x, 1 = raw network output, 2.. = model-value history
+_X, _RAW, _HIST = 0, 1, 2
+
+
+def build_dpm_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type="x_start", skip_type="logSNR",
+                      lower_order_final=False, denoise_to_zero=True, solver_type="dpmsolver", t_start=None, t_end=None):
+    """DPM_Solver.sample(method='multistep') (sampler.py:1171-1247) as EVAL/AXPY ops; returns (ops, model_times)."""
+    assert steps >= order
+    t_0 = 1.0 / ns.total_N if t_end is None else t_end
+    t_T = ns.T if t_start is None else t_start
+    assert t_0 > 0 and t_T > 0
+    pp = algorithm_type == "dpmsolver++"
+    wm = _WrappedModel(None, ns, model_type, {})
+    ts = dpm_time_steps(ns, skip_type, t_T, t_0, steps)
+    ops, times = [], []
+
+    def model_value(t, slot):
+        """m = model_fn(x, t) into history slot; m = cx*x + cr*raw."""
+        times.append(ns.model_time(t))
+        ops.append(("eval", ns.model_time(t)))
+        cx, cr = wm.mix(t)                                   # noise prediction
+        if pp:                                               # data prediction x0 = (x - sigma*noise)/alpha
+            a, s = ns.marginal_alpha(t), ns.marginal_std(t)
+            cx, cr = (1.0 - s * cx) / a, -s * cr / a
+            if model_type == "x_start":
+                cx, cr = 0.0, 1.0                            # the two conversions cancel exactly
+        terms = [(_RAW, cr)] if cx == 0.0 else [(_X, cx), (_RAW, cr)]
+        ops.append(("axpy", slot, terms, 0.0, -1))
+
+    hist = []                                                # [(t, slot)], oldest first
+    free = [_HIST + k for k in range(order)]
+
+    def push(t):
+        slot = free.pop(0) if free else hist.pop(0)[1]
+        if len(hist) >= order:
+            hist.pop(0)
+        model_value(t, slot)
+        hist.append((t, slot))
+
+    def update(t, k):
+        tp = [h_[0] for h_ in hist]
+        c_x, c_m = multistep_update_coefs(ns, algorithm_type, tp, t, k, solver_type)
+        terms = [(_X, c_x)] + [(hist[-1 - j][1], c_m[j]) for j in range(k)]
+        ops.append(("axpy", _X, terms, 0.0, -1))
+
+    push(ts[0])
+    for step in range(1, order):
+        update(ts[step], step)
+        push(ts[step])
+    for step in range(order, steps + 1):
+        k = min(order, steps + 1 - step) if (lower_order_final and steps < 10) else order
+        update(ts[step], k)
+        if step < steps:
+            if len(hist) == order:
+                free.append(hist.pop(0)[1])
+            push(ts[step])
+    if denoise_to_zero:
+        times.append(ns.model_time(t_0))
+        ops.append(("eval", ns.model_time(t_0)))
+        cx, cr = wm.mix(t_0)
+        a, s = ns.marginal_alpha(t_0), ns.marginal_std(t_0)
+        cx, cr = (1.0 - s * cx) / a, -s * cr / a
+        if model_type == "x_start":
+            cx, cr = 0.0, 1.0
+        terms = [(_RAW, cr)] if cx == 0.0 else [(_X, cx), (_RAW, cr)]
+        ops.append(("axpy", _X, terms, 0.0, -1))
+    return ops, times
+
+
+def build_ddim_program(tables, timesteps, eta=0.0, training_target="x0"):
+    """DiffusionTrainer.sample_ddim (diffusion_trainer.py:439-480) as EVAL/AXPY ops.
+    Returns (ops, n_noise_slabs); noise slab k belongs to the k-th non-final step."""
+    skip = tables.num_timesteps // timesteps
+    seq = list(range(0, tables.num_timesteps, skip))
+    seq_next = [-1] + seq[:-1]
+    ops, n_noise = [], 0
+    for time, time_next in zip(reversed(seq), reversed(seq_next)):
+        ops.append(("eval", float(time)))
+        alpha = tables.alphas_hat[time]
+        if training_target == "x0":
+            a, b = tables.sqrt_recip_alphas_hat[time], tables.sqrt_recipm1_alphas_hat[time]
+            xs_x, xs_r = 0.0, 1.0                           # x_start = raw
+            pn_x, pn_r = a / b, -1.0 / b                    # pred_noise = (a x - raw) / b
+        else:
+            pn_x, pn_r = 0.0, 1.0
+            xs_x, xs_r = 1.0 / math.sqrt(alpha), -math.sqrt(1 - alpha) / math.sqrt(alpha)
+        if time_next < 0:
+            terms = [(_RAW, xs_r)] if xs_x == 0.0 else [(_X, xs_x), (_RAW, xs_r)]
+            ops.append(("axpy", _X, terms, 0.0, -1))
+            continue
+        alpha_next = tables.alphas_hat[time_next]
+        c1 = eta * math.sqrt((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha))
+        c2 = math.sqrt((1 - alpha_next) - c1 ** 2)
+        sa = tables.sqrt_alphas_hat[time_next]
+        terms = [(_X, sa * xs_x + c2 * pn_x), (_RAW, sa * xs_r + c2 * pn_r)]
+        if c1 != 0.0:
+            ops.append(("axpy", _X, terms, c1, n_noise))
+            n_noise += 1
+        else:
+            ops.append(("axpy", _X, terms, 0.0, -1))
+    return ops, n_noise
+
+
+def run_program_generic(ops, x, model, noise=None):
+    """Executes a sampler program with an arbitrary denoiser callable ``model(x, t[B]) -> tensor`` (one fused
+    update launch per AXPY).  The SalUNetB200 fast path runs the same ops inside dsb_sample instead."""
+    bufs = {_X: x}
+    for op in ops:
+        if op[0] == "eval":
+            t = torch.full((x.shape[0],), op[1], dtype=torch.float32, device=x.device)
+            bufs[_RAW] = model(bufs[_X], t)
+        else:
+            _, dst, terms, ncoef, nidx = op
+            nz = noise[nidx] if (nidx >= 0 and noise is not None) else None
+            bufs[dst] = _axpy([c for _, c in terms], [bufs[s] for s, _ in terms], nz, ncoef)
+    return bufs[_X]
+
+
+# ============================================================================================ DPM_Solver
+
+
+class DPM_Solver:
+    """sampler.py:336-1247, multistep path.  ``model_fn`` is what model_wrapper returned."""
+
+    def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
+                 correcting_xt_fn=None, thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
+        assert algorithm_type in ["dpmsolver", "dpmsolver++"]
+        if correcting_x0_fn is not None or correcting_xt_fn is not None:
+            raise NotImplementedError("correcting_x0_fn / correcting_xt_fn (dynamic thresholding) are not on the hot path "
+                                      "(cfgs/diffusion.yml: thresholding false)")
+        if not isinstance(model_fn, _WrappedModel):
+            raise TypeError("model_fn must come from diff_sal_b200.sampler.model_wrapper")
+        self.wrapped = model_fn
+        self.noise_schedule = noise_schedule
+        self.algorithm_type = algorithm_type
+
+    def sample(self, x, img=None, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform",
+               method="multistep", lower_order_final=True, denoise_to_zero=False, solver_type="dpmsolver",
+               atol=0.0078, rtol=0.05, return_intermediate=False, use_graph=True):
+        if method != "multistep":
+            # the reference's singlestep / adaptive branches drop the conditioning argument (sampler.py:573-635)
+            raise NotImplementedError("method=%r: only 'multistep' forwards the conditioning in the reference" % method)
+        if return_intermediate:
+            raise NotImplementedError("return_intermediate is not supported by the fused loop")
+        ns = self.noise_schedule
+        ops, _ = build_dpm_program(ns, steps, order, self.algorithm_type, self.wrapped.model_type, skip_type,
+                                   lower_order_final, denoise_to_zero, solver_type, t_start, t_end)
+        model = self.wrapped.model
+        kwargs = self.wrapped.model_kwargs
+        fused = getattr(model, "_dsb_fused_sample", None)
+        if fused is not None:
+            return fused(ops, x, img, kwargs, use_graph=use_graph)
+        return run_program_generic(ops, x.clone(), lambda x_, t_: model(x_, t_, img, **kwargs))
+
+
+# ============================================================================================ DDIM driver
+
+
+class DiffusionSampler:
+    """The sampling half of the reference's DiffusionTrainer (diffusion_trainer.py:29-76,434-640) around a
+    SalUNetB200 decoder: same config keys (config.sampling.*, config.training.training_target), same
+    ``sample_ddim(x, img, audio_cond)`` / ``sample_image(x, img, audio)`` call shapes.  ``img`` is the MViT feature
+    list and ``audio`` the [B,512,9,7,12] audio feature tensor (the encoders are outside the hot path)."""
+
+    def __init__(self, decoder_net, config, betas=None):
+        self.decoder_net = decoder_net
+        self.config = config
+        self.training_target = config.training.training_target
+        assert self.training_target in ["x0", "noise"]
+        if betas is None:
+            betas = get_beta_schedule(beta_schedule=config.diffusion.beta_schedule, beta_start=config.diffusion.beta_start,
+                                      beta_end=config.diffusion.beta_end,
+                                      num_diffusion_timesteps=config.diffusion.num_diffusion_timesteps)
+        self.betas = to_torch(betas)
+        self.tables = DdimTables(self.betas)
+        self.num_timesteps = self.tables.num_timesteps
+
+    @torch.no_grad()
+    def sample_ddim(self, x, img=None, audio_cond=None, use_graph=True):
+        eta = self.config.sampling.eta
+        ops, n_noise = build_ddim_program(self.tables, self.config.sampling.timesteps, eta, self.training_target)
+        noise = torch.randn((n_noise,) + tuple(x.shape), device=x.device) if n_noise else None
+        return self.decoder_net._dsb_fused_sample(ops, x, img, {"audio_feat_list": audio_cond}, noise=noise,
+                                                  use_graph=use_graph)
+
+    @torch.no_grad()
+    def sample_image(self, x, img=None, audio=None, base_samples=None, use_graph=True):
+        st = self.config.sampling.sample_type
+        if st == "ddim":
+            return self.sample_ddim(x, img, audio, use_graph=use_graph)
+        if st in ["dpmsolver", "dpmsolver++"]:
+            ns = NoiseScheduleVP(schedule="discrete", betas=self.betas)
+            mtype = "x_start" if self.training_target == "x0" else "noise"
+            mf = model_wrapper(self.decoder_net, ns, model_type=mtype, model_kwargs={"audio_feat_list": audio},
+                               guidance_type="uncond")
+            solver = DPM_Solver(mf, ns, algorithm_type=st)
+            s = self.config.sampling
+            return solver.sample(x, img, steps=(s.timesteps - 1 if s.denoise else s.timesteps), order=s.dpm_solver_order,
+                                 skip_type=s.skip_type, method=s.dpm_solver_method, lower_order_final=s.lower_order_final,
+                                 denoise_to_zero=s.denoise, solver_type=s.dpm_solver_type, atol=s.dpm_solver_atol,
+                                 rtol=s.dpm_solver_rtol, use_graph=use_graph)
+        raise NotImplementedError(st)
+
+
+# ============================================================================================ util/denoising.py
+
+
+def compute_alpha(beta, t):
+    """util/denoising.py:3-6."""
+    beta = torch.cat([torch.zeros(1).to(beta.device), beta], dim=0)
+    return (1 - beta).cumprod(dim=0).index_select(0, t + 1).view(-1, 1, 1, 1)
+
+
+def generalized_steps(x, seq, model, b, img=None, **kwargs):
+    """util/denoising.py:9-36 (DDIM repo loop, eps-parameterised ``model(data, t)``).  The per-step .to('cuda') /
+    .to('cpu') round trips of the reference are not reproduced; xs / x0_preds stay on x's device."""
+    with torch.no_grad():
+        n = x.size(0)
+        seq = list(seq)
+        seq_next = [-1] + seq[:-1]
+        bcpu = _as_fp32_cpu(b)
+        ah = torch.cat([torch.ones(1), (1 - bcpu).cumprod(dim=0)]).double().numpy()   # index t+1
+        eta = kwargs.get("eta", 0)
+        xs, x0_preds = [x], []
+        for i, j in zip(reversed(seq), reversed(seq_next)):
+            t = (torch.ones(n) * i).to(x.device)
+            at, at_next = float(ah[i + 1]), float(ah[j + 1])
+            xt = xs[-1]
+            et = model({"img": img, "input": xt}, t)
+            x0_t = _axpy([1.0 / math.sqrt(at), -math.sqrt(1 - at) / math.sqrt(at)], [xt, et])
+            x0_preds.append(x0_t)
+            c1 = eta * math.sqrt((1 - at / at_next) * (1 - at_next) / (1 - at))
+            c2 = math.sqrt((1 - at_next) - c1 ** 2)
+            nz = torch.randn_like(x) if c1 != 0.0 else None
+            xs.append(_axpy([math.sqrt(at_next), c2], [x0_t, et], nz, c1))
+    return xs, x0_preds

@@ -1,0 +1,118 @@
+/* libdiffsal_b200 -- C ABI of the B200-native DiffSal sampling hot path.
+ *
+ * Drop-in boundary for the reference's denoiser + sampler update.  Plain pointers and sizes only;
+ * every call returns 0 on success or a negative error class (message via dsb_last_error); nothing throws, nothing
+ * falls back to the CPU.  A handle is bound to the CUDA device that is current at dsb_create, is not thread-safe,
+ * and all work is enqueued asynchronously on the caller's stream.  Device tensors passed in are never modified
+ * (the reference's in-place feature-list mutation, sal_unet.py:317, is not reproduced) and never freed.
+ *
+ * What each entry point replaces in /root/reference:
+ *   dsb_create / dsb_load_weight / dsb_finalize_weights
+ *        SalUNet.__init__ + load_state_dict with the reference key names
+ *        (models/saliency_decoder/sal_unet.py:146-277, model.py:17-22)
+ *   dsb_set_condition
+ *        the per-clip, loop-invariant part of SalUNet.forward: feature list / audio features handed to the
+ *        decoder (models/diff_model.py:106-113, diffusion_trainer.py:556-565) incl. TransformerBlock.align_conv
+ *        on the audio features (models/saliency_decoder/transformer.py:128-131)
+ *   dsb_denoise
+ *        SalUNet.forward(x, t, feat_list, audio_feat_list)  (sal_unet.py:302-328) = one denoiser evaluation
+ *   dsb_sampler_update
+ *        the elementwise state updates of DiffusionTrainer.sample_ddim (diffusion_trainer.py:434-437,470-478)
+ *        and DPM_Solver.{dpm_solver_first_update, multistep_dpm_solver_second/third_update, data_prediction_fn}
+ *        (models/dpm_solver/sampler.py:548-593,797-905,434-443), with host-computed scalar coefficients
+ *   dsb_sample
+ *        the whole loop: DiffusionTrainer.sample_ddim (diffusion_trainer.py:439-480) /
+ *        DPM_Solver.sample(method="multistep") (sampler.py:1048-1247) as a program of EVAL / AXPY ops
+ */
+#ifndef DIFFSAL_B200_H
+#define DIFFSAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsb_handle dsb_handle;
+
+typedef struct dsb_config {
+    int max_batch;      /* clips per denoiser evaluation the workspace is sized for            */
+    int audio_visual;   /* 1: cfgs/audio_visual.py (audio-gated K), 0: cfgs/visual.py           */
+    int reserved[6];
+} dsb_config;
+
+/* error classes */
+#define DSB_OK 0
+#define DSB_ERR_ARG (-1)         /* bad argument / shape / state             */
+#define DSB_ERR_UNSUPPORTED (-2) /* configuration outside the hot path       */
+#define DSB_ERR_CUDA (-3)        /* CUDA runtime / driver error              */
+#define DSB_ERR_WEIGHT (-4)      /* missing / mis-shaped weight              */
+
+int dsb_create(const dsb_config* cfg, dsb_handle** out);
+void dsb_destroy(dsb_handle* h);
+const char* dsb_last_error(const dsb_handle* h);
+/* bytes of device memory the handle owns for a batch of B clips (workspace + repacked weights) */
+size_t dsb_workspace_bytes(const dsb_handle* h, int B);
+
+/* fp32 tensor under its reference state_dict key; `data` may be a host or a device pointer. */
+int dsb_load_weight(dsb_handle* h, const char* ref_key, const void* data, const int64_t* shape, int ndim);
+/* BN folding, bf16 repack to K-major [N][tap*Cin+c], conv_in o down1 composition, depthwise tap tables. */
+int dsb_finalize_weights(dsb_handle* h);
+
+/* feat[i]: device fp32 [B, C_i, 8, h_i, w_i] (C = 768,384,192,96; feat[3] is accepted and ignored exactly like
+ * the reference); audio: device fp32 [B,512,9,7,12] or NULL for the visual-only configuration. */
+int dsb_set_condition(dsb_handle* h, const void* const feat[4], const void* audio_or_null, int B, void* stream);
+
+/* x: device fp32 [B,1,224,384]; t: device fp32 [B] (model time, may be fractional); out: device fp32 [B,1,224,384] */
+int dsb_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream);
+
+/* out = sum_k coef[k] * in[k] (nin <= 4) + noise_coef * noise; n elements (multiple of 4), device fp32. */
+int dsb_sampler_update(dsb_handle* h, const float* coef, const float* const* in, int nin, const float* noise_or_null,
+                       float noise_coef, float* out, int64_t n, void* stream);
+
+/* ---- whole sampling loop as a small program over device buffers -------------------------------------------
+ * Buffer ids: 0 = x (the state, in/out), 1 = raw network output of the last EVAL, 2..7 = scratch (model history).
+ * DSB_OP_EVAL : buf[1] = SalUNet(buf[0], t)                      (t = op.t for every clip)
+ * DSB_OP_AXPY : buf[dst] = sum_k coef[k] * buf[src[k]] + noise_coef * noise[noise_index]
+ */
+#define DSB_OP_EVAL 0
+#define DSB_OP_AXPY 1
+typedef struct dsb_sampler_op {
+    int kind;
+    float t;
+    int dst;
+    int nin;
+    int src[4];
+    float coef[4];
+    float noise_coef;
+    int noise_index;    /* -1: none; else index of a [B,1,224,384] slab in `noise` */
+} dsb_sampler_op;
+
+typedef struct dsb_sampler_desc {
+    const dsb_sampler_op* ops;
+    int n_ops;
+    const float* noise; /* device fp32 [n_slabs][B,1,224,384] or NULL */
+    int use_graph;      /* 1: capture the program into a CUDA graph (cached per program) and replay it */
+} dsb_sampler_desc;
+
+int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int B, void* stream);
+
+/* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
+int64_t dsb_last_launch_count(const dsb_handle* h);
+
+/* ---- debugging / parity taps (read-only views of the workspace after dsb_denoise) ------------------------- */
+/* copies an internal fp32 buffer to `dst` (device); names: "noise0".."noise2" ([B,hw,C] frame-8 slices),
+ * "x0".."x3" (stage outputs [B*9,hw,C]), "r0".."r3" ([B,hw,768]), "p" ([B,112,192]).  Returns element count. */
+int64_t dsb_debug_read(dsb_handle* h, const char* name, float* dst, int64_t max_elems, void* stream);
+
+/* ---- single-kernel test entry (tests/test_kernels_gpu.py) ------------------------------------------------- */
+int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt, const void* A,
+                  const void* Wt, const float* scale, const float* shift, const float* rowbias, const float* residual,
+                  int act, float* out_f32, void* out_bf16, int out_fmul, int out_fadd, const float* head_w,
+                  float head_b, float* out_head, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -163,8 +163,9 @@ def transformer_block(sd, p, x5, s, audio):
     return x.permute(0, 2, 1).reshape(B, T, C, H, W).permute(0, 2, 1, 3, 4)
 
 
-def decoder(sd, back_fea, audio):
-    """sal_unet.py:457-491 + transformer.py:259-289.  back_fea[i]: [B,C_i,9,h_i,w_i] for i<3."""
+def decoder(sd, back_fea, audio, taps=None):
+    """sal_unet.py:457-491 + transformer.py:259-289.  back_fea[i]: [B,C_i,9,h_i,w_i] for i<3.
+    ``taps`` (optional dict) receives intermediates in channels-last form for per-stage parity checks."""
     x5 = back_fea[0]
     B = x5.shape[0]
     acc = 0
@@ -180,17 +181,21 @@ def decoder(sd, back_fea, audio):
         x5 = transformer_block(sd, p + ".blocks.0", x5, STAGE_S[i], audio)
         Bc, C, T, H, W = x5.shape
         tok = x5.permute(0, 2, 3, 4, 1)                         # [B,T,H,W,C]
+        if taps is not None:
+            taps["x%d" % i] = tok.contiguous()
         tok = _ln(tok, sd, "invpt_decoder.norm_mts.%d" % i)
         y = tok.permute(0, 4, 1, 2, 3)                          # [B,C,T,H,W]
         y = F.relu(F.conv3d(y, sd["invpt_decoder.redu_chan_up.%d.proj.0.weight" % i], None,
                             stride=(N_REDUCE, 1, 1)))
         y = y.squeeze(2)
+        if taps is not None:
+            taps["r%d" % i] = y.permute(0, 2, 3, 1).contiguous()
         acc = acc + F.interpolate(y, size=MID_HW, mode="bilinear", align_corners=False)
     y = F.conv2d(acc, sd["invpt_decoder.mt_proj.0.weight"], sd["invpt_decoder.mt_proj.0.bias"], padding=1)
     return F.relu(_bn_eval(y, sd, "invpt_decoder.mt_proj.1"))
 
 
-def forward(sd, x, t, feat_list, audio=None):
+def forward(sd, x, t, feat_list, audio=None, taps=None):
     """One denoiser evaluation, sal_unet.py:302-328.  Never mutates feat_list.
     x [B,1,224,384]; t [B] (int or float); feat_list 4 tensors [B,C_i,8,h_i,w_i];
     audio [B,512,9,7,12] or None.  Returns [B,1,224,384] in (0,1)."""
@@ -199,6 +204,10 @@ def forward(sd, x, t, feat_list, audio=None):
         temb = temb_mlp(sd, t)
         noise = noise_encoder(sd, x, temb)
         back = [torch.cat([feat_list[i].float(), noise[i]], dim=2) for i in range(3)]
-        y = decoder(sd, back, None if audio is None else audio.float())
+        y = decoder(sd, back, None if audio is None else audio.float(), taps)
         y = torch.sigmoid(F.conv2d(y, sd["logits.linear_pred.weight"], sd["logits.linear_pred.bias"]))
+        if taps is not None:
+            for i in range(3):
+                taps["noise%d" % i] = noise[i].squeeze(2).permute(0, 2, 3, 1).contiguous()
+            taps["p"] = y.squeeze(1).contiguous()
         return F.interpolate(y, size=OUT_HW, mode="bilinear", align_corners=False)

@@ -1,0 +1,93 @@
+"""GPU: one full denoiser evaluation through the C ABI (dsb_denoise) against the fp32 CPU oracle on the same seeded
+inputs, with per-stage taps so that a failure names the first diverging stage.
+
+Tolerances: the CUDA path rounds GEMM operands to bf16 (fp32 accumulate, fp32 epilogues / norms / residuals), the
+oracle is true fp32.  north_star: per-pixel max-abs <= 1e-2 on min-max-normalised maps."""
+import numpy as np
+import pytest
+import torch
+
+from diff_sal_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _minmax(x):
+    flat = x.reshape(x.shape[0], -1)
+    lo = flat.min(dim=1, keepdim=True).values
+    hi = flat.max(dim=1, keepdim=True).values
+    return ((flat - lo) / (hi - lo)).reshape(x.shape)
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from diff_sal_b200.engine import Engine
+    cache = {}
+
+    def get(kind, audio):
+        key = (kind, audio)
+        if key not in cache:
+            e = Engine(max_batch=2, audio_visual=audio)
+            e.load_state_dict(synth.make_state_dict(kind))
+            cache[key] = e
+        return cache[key]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+@pytest.mark.parametrize("kind,audio,B,t", [("wide", True, 2, [500.0, 37.0]), ("wide", False, 1, [886.9]),
+                                            ("ref_init", True, 1, [37.0])])
+def test_denoise_matches_oracle(engines, kind, audio, B, t):
+    from oracle import salunet
+    sd = synth.make_state_dict(kind)
+    x, feats, aud = synth.make_inputs(B, audio=audio)
+    taps = {}
+    ref = salunet.forward(sd, x, torch.tensor(t), feats, aud, taps=taps)
+    eng = engines(kind, audio)
+    eng.set_condition([f.cuda() for f in feats], None if aud is None else aud.cuda())
+    out = eng.denoise(x.cuda(), torch.tensor(t))
+    torch.cuda.synchronize()
+    report = {}
+    for name in ["noise2", "noise1", "noise0", "x0", "r0", "x1", "r1", "x2", "r2", "x3", "r3", "p"]:
+        got = eng.debug_read(name, taps[name].numel()).reshape(taps[name].shape)
+        report[name] = _rel(got, taps[name])
+    print(kind, audio, {k: "%.2e" % v for k, v in report.items()})
+    for name, v in report.items():
+        assert v < 3e-2, "stage tap %s diverges: rel err %g (all: %s)" % (name, v, report)
+    err = (_minmax(out.cpu()) - _minmax(ref)).abs().max().item()
+    print("min-max-normalised max-abs error:", err)
+    assert err <= 1e-2
+    abs_err = (out.cpu() - ref).abs().max().item()
+    print("absolute max error:", abs_err)
+    assert abs_err < 5e-3
+
+
+def test_golden_single_step(engines):
+    """The committed fixture generated from the unmodified reference (tests/golden/make_golden.py)."""
+    import os
+    gold = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "step_wide_av_t500.npz"))["y"])
+    x, feats, aud = synth.make_inputs(1, audio=True)
+    eng = engines("wide", True)
+    eng.set_condition([f.cuda() for f in feats], aud.cuda())
+    out = eng.denoise(x.cuda(), torch.tensor([500.0])).cpu()
+    assert (_minmax(out) - _minmax(gold)).abs().max().item() <= 1e-2
+
+
+def test_inputs_not_mutated_and_repeatable(engines):
+    x, feats, aud = synth.make_inputs(1, audio=True)
+    eng = engines("wide", True)
+    fc = [f.cuda() for f in feats]
+    keep = [f.clone() for f in fc]
+    eng.set_condition(fc, aud.cuda())
+    a = eng.denoise(x.cuda(), torch.tensor([10.0])).clone()
+    b = eng.denoise(x.cuda(), torch.tensor([10.0])).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    for f, k in zip(fc, keep):
+        assert torch.equal(f, k)
