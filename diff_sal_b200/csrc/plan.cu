@@ -89,6 +89,10 @@ struct dsb_handle {
     int B = 0;
     bool has_audio = false;
     std::vector<Launch> prog;                     // one denoiser evaluation
+    std::vector<std::string> prog_name;           // per launch: label
+    std::vector<double> prog_flops;               // per launch: algorithmic FLOPs (0 for memory-bound kernels)
+    std::vector<double> prog_bytes;               // per launch: algorithmic bytes (memory-bound kernels; 0 if not stated)
+    int64_t cond_launches = 0;
     const float* cur_x = nullptr;
     const float* cur_t = nullptr;
     float* cur_out = nullptr;
@@ -252,15 +256,25 @@ struct Builder {
     std::vector<Launch>* out;
     int err = 0;
 
-    void add(Launch l) { out->push_back(std::move(l)); }
+    void add(Launch l, const char* name = "misc", double bytes = 0.0) {
+        out->push_back(std::move(l));
+        h->prog_name.push_back(name);
+        h->prog_flops.push_back(0.0);
+        h->prog_bytes.push_back(bytes);
+    }
 
-    void conv(ConvOp op) {
+    // algo_flops < 0: 2*M*N*K of the lowered GEMM (M = valid output pixels)
+    void conv(ConvOp op, const char* name, double algo_flops = -1.0) {
         if (err) return;
         ConvLaunch cl;
         int r = conv_lower(op, &cl);
-        if (r) { err = fail(h, DSB_ERR_CUDA, "conv_lower failed (%d) for a %dx%d conv %d->%d", r, op.H, op.W, op.Cin, op.N); return; }
+        if (r) { err = fail(h, DSB_ERR_CUDA, "conv_lower failed (%d) for %s (%dx%d, %d->%d)", r, name, op.H, op.W, op.Cin, op.N); return; }
         const int sms = h->num_sms;
-        add([cl, sms](cudaStream_t s) { return conv_run(cl, sms, s); });
+        out->push_back([cl, sms](cudaStream_t s) { return conv_run(cl, sms, s); });
+        h->prog_name.push_back(std::string("gemm:") + name);
+        const double m = (double)op.F * op.H * op.W;
+        h->prog_flops.push_back(algo_flops >= 0 ? algo_flops : 2.0 * m * op.N * (double)cl.p.taps * op.Cin);
+        h->prog_bytes.push_back(0.0);
     }
 };
 
@@ -274,6 +288,9 @@ ConvOp make_op(int kind, int F, int H, int W, int Cin, int N, const bf16* A, con
 
 int build_program(dsb_handle* h) {
     h->prog.clear();
+    h->prog_name.clear();
+    h->prog_flops.clear();
+    h->prog_bytes.clear();
     Builder b{h, &h->prog};
     const int B = h->B, F = B * kT;
     auto WP = [&](const std::string& k) -> const bf16* {
@@ -296,10 +313,10 @@ int build_program(dsb_handle* h) {
             tw.wp[i] = W(h, r + "weight"); tw.bp[i] = W(h, r + "bias"); tw.cout[i] = cout[i];
         }
         float* tp[3] = {h->tp[0], h->tp[1], h->tp[2]};
-        b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); });
+        b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); }, "temb");
         const float *w5 = WF("stem.w5"), *b5 = WF("stem.b5");
         float* h0 = h->h0;
-        b.add([h, w5, b5, h0, B](cudaStream_t s) { return stem_launch(h->cur_x, B, w5, b5, h0, s); });
+        b.add([h, w5, b5, h0, B](cudaStream_t s) { return stem_launch(h->cur_x, B, w5, b5, h0, s); }, "stem5x5", (double)B * (344064.0 + 2064384.0));
 
         const float* cur = h->h0;
         int Cin = 96, H = 56, Wd = 96;
@@ -312,31 +329,31 @@ int build_program(dsb_handle* h) {
             const float *g2 = W(h, rk + "norm2.weight"), *b2 = W(h, rk + "norm2.bias");
             bf16 *act = h->enc_act, *raw = h->enc_raw, *res = h->enc_res;
             float *c1 = h->enc_c1, *sc = h->enc_sc;
-            b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); });
-            b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); });
+            b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); }, "gn_stats", (double)B * HW * Cin * 4.0);
+            b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); }, "gn_apply", (double)B * HW * Cin * 8.0);
             {   // conv1 + bias + temb projection
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
                 op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
-                b.conv(op);
+                b.conv(op, "res.conv1");
             }
             {   // 1x1 shortcut on the raw block input
                 ConvOp op = make_op(CONV_1X1, B, H, Wd, Cin, Cout, raw, WP(rk + "nin_shortcut.weight"));
                 op.shift = W(h, rk + "nin_shortcut.bias"); op.out_f32 = sc;
-                b.conv(op);
+                b.conv(op, "res.shortcut");
             }
-            b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); });
-            b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); });
+            b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); }, "gn_stats", (double)B * HW * Cout * 4.0);
+            b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); }, "gn_apply", (double)B * HW * Cout * 6.0);
             {   // conv2 + bias + shortcut -> block output (only ever a GEMM operand: bf16)
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
                 op.shift = W(h, rk + "conv2.bias"); op.residual = sc; op.out_bf16 = res;
-                b.conv(op);
+                b.conv(op, "res.conv2");
             }
             const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
             float* d = h->enc_d[i];
             {   // Downsample: pad (0,1,0,1) + 3x3 stride 2
                 ConvOp op = make_op(CONV_3X3_S2, B, H / 2, Wd / 2, Cout, Cout, res, WP(dk + "weight"));
                 op.shift = W(h, dk + "bias"); op.out_f32 = d;
-                b.conv(op);
+                b.conv(op, "res.down");
             }
             // noise slice = frame 8 of the stage input / skip tensor (sal_unet.py:311-317)
             const size_t fe = frame_elems(2 - i);
@@ -344,7 +361,7 @@ int build_program(dsb_handle* h) {
             b.add([=](cudaStream_t s) {
                 return (int)cudaMemcpy2DAsync(dst, (size_t)kT * fe * sizeof(float), d, fe * sizeof(float),
                                               fe * sizeof(float), B, cudaMemcpyDeviceToDevice, s);
-            });
+            }, "noise_slice_copy", (double)B * fe * 8.0);
             cur = d;
             Cin = Cout; H /= 2; Wd /= 2;
         }
@@ -361,26 +378,26 @@ int build_program(dsb_handle* h) {
             const int Cp = kStageC[i - 1];
             const float* prev = h->X2[i - 1];
             bf16* up = h->up;
-            b.add([=](cudaStream_t s) { return upsample2x_launch(prev, F, H / 2, Wd / 2, Cp, up, s); });
+            b.add([=](cudaStream_t s) { return upsample2x_launch(prev, F, H / 2, Wd / 2, Cp, up, s); }, "upsample2x", (double)F * HW * Cp * (1.0 + 2.0));
             const std::string pe = st + "patch_embed.0.proj.";
             {
                 ConvOp op = make_op(CONV_3X3, F, H, Wd, Cp, C, up, WP(pe + "1.weight"));
                 op.dilation = 2; op.scale = WF(pe + "2.scale"); op.shift = WF(pe + "2.shift"); op.act = ACT_RELU;
                 op.out_bf16 = h->mid;
-                b.conv(op);
+                b.conv(op, "upembed.conv1");
             }
             {
                 ConvOp op = make_op(CONV_3X3, F, H, Wd, C, C, h->mid, WP(pe + "4.weight"));
                 op.dilation = 2; op.scale = WF(pe + "5.scale"); op.shift = WF(pe + "5.shift"); op.act = ACT_RELU;
                 op.residual = (i == 1 || i == 2) ? h->back[i] : nullptr;   // stage 3 has no skip (transformer.py:265-270)
                 op.out_f32 = h->X[i];
-                b.conv(op);
+                b.conv(op, "upembed.conv2");
             }
             Xi = h->X[i];
         }
         const long tokens = (long)F * HW;
         float2* stats = h->lnstats;
-        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, s); });
+        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, s); }, "ln_stats", (double)tokens * C * 4.0);
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
         bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
         const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
@@ -391,75 +408,75 @@ int build_program(dsb_handle* h) {
         if (h->has_audio) {
             const float* al = h->a_low[i];
             float* gate = h->gate;
-            b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); });
-            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, s); });
+            b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
+            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, s); }, "kpool_av", (double)B * HW * C * 4.0);
         } else {
-            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, s); });
+            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, s); }, "pool_ln_k", (double)tokens * C * 4.0);
         }
-        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, s); });
-        b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, s); });
+        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, s); }, "q_dwln", (double)tokens * C * 6.0);
+        b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, s); }, "pool_ln_v", (double)tokens * C * 4.0);
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, q_ln, WP(bk + "attn.proj_q.weight"));
             op.shift = W(h, bk + "attn.proj_q.bias"); op.out_bf16 = h->Qp;
-            b.conv(op);
+            b.conv(op, "attn.proj_q");
         }
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
             op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
-            b.conv(op);
+            b.conv(op, "attn.proj_k");
         }
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
             op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
-            b.conv(op);
+            b.conv(op, "attn.proj_v");
         }
         {
             const float *Kp = h->Kp, *Vp = h->Vp;
             bf16 *KB = h->KB, *VB = h->VB;
             const float scale = 1.0f / sqrtf((float)C);          // dim_out ** -0.5 (attention.py:33)
-            b.add([=](cudaStream_t s) { return attn_operands_launch(Kp, Vp, F, C, scale, KB, VB, s); });
+            b.add([=](cudaStream_t s) { return attn_operands_launch(Kp, Vp, F, C, scale, KB, VB, s); }, "attn_operands");
         }
         {   // scores + per-head softmax over the 18 keys
             ConvOp op = make_op(CONV_1X1, F, 1, HW, C, 48, h->Qp, h->KB);
             op.b_rows_per_frame = 48; op.out_softmax = h->P;
-            b.conv(op);
+            b.conv(op, "attn.qk_softmax", 2.0 * (double)tokens * 18 * C);   // reference bmm count (2 heads x C/2)
         }
         {   // P . V
             ConvOp op = make_op(CONV_1X1, F, 1, HW, 64, C, h->P, h->VB);
             op.b_rows_per_frame = C; op.out_bf16 = h->o;
-            b.conv(op);
+            b.conv(op, "attn.pv", 2.0 * (double)tokens * 18 * C);
         }
         {   // output projection + residual
             ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, h->o, WP(bk + "attn.proj.weight"));
             op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
-            b.conv(op);
+            b.conv(op, "attn.proj");
         }
         {
             const float *g2 = W(h, bk + "norm2.weight"), *b2 = W(h, bk + "norm2.bias");
             const float* x1 = h->X1[i];
             bf16* ln2 = h->ln2;
-            b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, 1, 1, s); });
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, 1, 1, s); }, "ln_apply", (double)tokens * C * 6.0);
         }
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
             op.shift = W(h, bk + "mlp.fc1.bias"); op.act = ACT_GELU; op.out_bf16 = h->hid;
-            b.conv(op);
+            b.conv(op, "mlp.fc1");
         }
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, 2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
             op.shift = W(h, bk + "mlp.fc2.bias"); op.residual = h->X1[i]; op.out_f32 = h->X2[i];
-            b.conv(op);
+            b.conv(op, "mlp.fc2");
         }
         {   // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU
             const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";
             const float *gm = W(h, nk + "weight"), *bm = W(h, nk + "bias");
             const float* x2 = h->X2[i];
             bf16* lnm = h->lnm;
-            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s); });
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s); }, "ln_apply_mts", (double)tokens * C * 6.0 * 5.0 / 9.0);
             ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
                                 WP("invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight"));
             op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i];
-            b.conv(op);
+            b.conv(op, "reduce_temp");
         }
     }
 
@@ -470,16 +487,16 @@ int build_program(dsb_handle* h) {
         b.add([=](cudaStream_t s) {
             const float* r4[4] = {rr[0], rr[1], rr[2], rr[3]};
             return ms_sum_launch(r4, B, S, s);
-        });
+        }, "ms_sum", (double)B * (7140.0 * 768 * 4 + 21504.0 * 768 * 2));
         ConvOp op = make_op(CONV_3X3, B, 112, 192, 768, 96, h->S, WP("invpt_decoder.mt_proj.0.weight"));
         op.scale = WF("invpt_decoder.mt_proj.1.scale"); op.shift = WF("invpt_decoder.mt_proj.1.shift");
         op.act = ACT_RELU; op.head_w = W(h, "logits.linear_pred.weight");
         float hb = 0.0f;
         cudaMemcpy(&hb, W(h, "logits.linear_pred.bias"), sizeof(float), cudaMemcpyDeviceToHost);
         op.head_b = hb; op.out_head = h->p;
-        b.conv(op);
+        b.conv(op, "mt_proj_head");
         const float* p = h->p;
-        b.add([h, p, B](cudaStream_t s) { return final_up_launch(p, B, h->cur_out, s); });
+        b.add([h, p, B](cudaStream_t s) { return final_up_launch(p, B, h->cur_out, s); }, "final_up", (double)B * (86016.0 + 344064.0));
     }
     return b.err;
 }
@@ -668,6 +685,7 @@ extern "C" int dsb_set_condition(dsb_handle* h, const void* const feat[4], const
         if (int r = build_program(h)) return r;
     }
     h->cond_epoch++;
+    h->cond_launches = 3 + (audio ? 5 : 0);
     return DSB_OK;
 }
 
@@ -797,3 +815,41 @@ extern "C" int64_t dsb_debug_read(dsb_handle* h, const char* name, float* dst, i
     if (e != cudaSuccess) return fail(h, DSB_ERR_CUDA, "debug copy failed: %s", cudaGetErrorString(e));
     return count;
 }
+
+// Times every launch of one denoiser evaluation with CUDA events on `stream` (the stream the kernels run on).
+// ms / flops / bytes receive up to `cap` entries; returns the number of launches.
+extern "C" int dsb_profile_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream,
+                                   float* ms, double* flops, double* bytes, int cap) {
+    if (!h || !x || !t || !out || !ms || !flops || !bytes) return DSB_ERR_ARG;
+    if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_profile_denoise before dsb_set_condition");
+    if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = (int)h->prog.size();
+    if (cap < n) return fail(h, DSB_ERR_ARG, "profile buffers too small (%d < %d)", cap, n);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
+    h->cur_x = x; h->cur_t = t; h->cur_out = out;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) {
+        cudaEventRecord(ev[i], s);
+        int r = h->prog[i](s);
+        if (r) rc = fail(h, DSB_ERR_CUDA, "launch %d (%s) failed: %d", i, h->prog_name[i].c_str(), r);
+    }
+    cudaEventRecord(ev[n], s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (!rc && e != cudaSuccess) rc = fail(h, DSB_ERR_CUDA, "profile sync: %s", cudaGetErrorString(e));
+    for (int i = 0; i < n && !rc; ++i) {
+        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        flops[i] = h->prog_flops[i];
+        bytes[i] = h->prog_bytes[i];
+    }
+    for (auto& e2 : ev) cudaEventDestroy(e2);
+    return rc ? rc : n;
+}
+
+extern "C" const char* dsb_profile_name(const dsb_handle* h, int i) {
+    if (!h || i < 0 || i >= (int)h->prog_name.size()) return "";
+    return h->prog_name[i].c_str();
+}
+
+extern "C" int64_t dsb_condition_launch_count(const dsb_handle* h) { return h ? h->cond_launches : 0; }

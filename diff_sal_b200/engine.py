@@ -60,6 +60,13 @@ def _bind(lib):
     lib.dsb_last_launch_count.restype = ctypes.c_int64
     lib.dsb_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]
     lib.dsb_debug_read.restype = ctypes.c_int64
+    lib.dsb_condition_launch_count.argtypes = [vp]
+    lib.dsb_condition_launch_count.restype = ctypes.c_int64
+    lib.dsb_profile_denoise.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_double), ci]
+    lib.dsb_profile_denoise.restype = ci
+    lib.dsb_profile_name.argtypes = [vp, ci]
+    lib.dsb_profile_name.restype = ctypes.c_char_p
     lib._dsb_bound = True
     return lib
 
@@ -190,6 +197,23 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.dsb_sample(self._h, ctypes.byref(desc), _lib.ptr(x), x.shape[0], _stream()), "dsb_sample")
         return x
+
+    def profile_denoise(self, x, t):
+        """[(name, ms, algorithmic_flops, algorithmic_bytes)] for every launch of one evaluation (CUDA events)."""
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        t = torch.as_tensor(t).to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        out = torch.empty_like(x)
+        cap = 512
+        ms = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        by = (ctypes.c_double * cap)()
+        with torch.cuda.device(self.device):
+            n = self._check(self.lib.dsb_profile_denoise(self._h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), x.shape[0],
+                                                         _stream(), ms, fl, by, cap), "debug")
+        return [(self.lib.dsb_profile_name(self._h, i).decode(), ms[i], fl[i], by[i]) for i in range(n)]
+
+    def condition_launch_count(self):
+        return int(self.lib.dsb_condition_launch_count(self._h))
 
     def last_launch_count(self):
         return int(self.lib.dsb_last_launch_count(self._h))

@@ -101,6 +101,16 @@ int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int 
 /* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
 int64_t dsb_last_launch_count(const dsb_handle* h);
 
+/* kernel launches enqueued by the last dsb_set_condition call */
+int64_t dsb_condition_launch_count(const dsb_handle* h);
+
+/* ---- measurement: one denoiser evaluation with a CUDA-event pair around every launch (bench.py's roofline) ---
+ * ms[i] = device time of launch i, flops[i] = its algorithmic FLOPs (2*M*N*K as torch's flop counter counts the
+ * reference graph; 0 for memory-bound kernels), bytes[i] = algorithmic bytes where stated.  Returns #launches. */
+int dsb_profile_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream, float* ms,
+                        double* flops, double* bytes, int cap);
+const char* dsb_profile_name(const dsb_handle* h, int i);
+
 /* ---- debugging / parity taps (read-only views of the workspace after dsb_denoise) ------------------------- */
 /* copies an internal fp32 buffer to `dst` (device); names: "noise0".."noise2" ([B,hw,C] frame-8 slices),
  * "x0".."x3" (stage outputs [B*9,hw,C]), "r0".."r3" ([B,hw,768]), "p" ([B,112,192]).  Returns element count. */
