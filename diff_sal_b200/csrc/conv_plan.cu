@@ -41,7 +41,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     const int bn = pick_bn(op.N);
     if (!bn) return -21;
     p.W = op.W; p.H = op.H; p.F = op.F;
-    pick_tile(op.W, op.H, op.F, op.b_rows_per_frame != 0, &p.bw_log2, &p.bh_log2);
+    pick_tile(op.W, op.H, op.F, op.b_rows_per_frame != 0 || op.f_group != 0, &p.bw_log2, &p.bh_log2);
     const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2, bf = 128 >> (p.bw_log2 + p.bh_log2);
     p.tiles_x = (op.W + bw - 1) / bw;
     p.tiles_y = (op.H + bh - 1) / bh;
@@ -99,10 +99,12 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     } else {
         return -23;
     }
+    if (op.f_group) dims[4] = (uint64_t)((op.F + op.f_used - 1) / op.f_used) * op.f_group;   // source frames
     int r = make_tensor_map(&out->tmA, op.A, 5, dims, strides, box);
     if (r) return r;
     const uint64_t K = (uint64_t)p.taps * C;
-    const uint64_t wrows = op.b_rows_per_frame ? (uint64_t)op.F * op.b_rows_per_frame : (uint64_t)op.N;
+    const uint64_t src_frames = op.f_group ? (uint64_t)((op.F + op.f_used - 1) / op.f_used) * op.f_group : (uint64_t)op.F;
+    const uint64_t wrows = op.b_rows_per_frame ? src_frames * op.b_rows_per_frame : (uint64_t)op.N;
     uint64_t wd[2] = {K, wrows};
     uint64_t ws[1] = {K * e};
     uint32_t wb[2] = {(uint32_t)bk, (uint32_t)bn};
@@ -118,6 +120,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.head_w = op.head_w; p.head_b = op.head_b; p.out_head = op.out_head;
     p.b_rows_per_frame = op.b_rows_per_frame;
     p.out_softmax = op.out_softmax;
+    p.f_group = op.f_group; p.f_used = op.f_used; p.out_remap = op.out_remap;
     return 0;
 }
 

@@ -35,6 +35,8 @@ struct ConvOp {
     float* out_head;
     int b_rows_per_frame;   // per-frame B operand (attention): Wt is [F * b_rows_per_frame][K]
     bf16* out_softmax;      // attention-score epilogue (N == 48)
+    int f_group, f_used;    // frame remap: F counts USED frames; tile frame tf -> source (tf/f_used)*f_group + tf%f_used
+    int out_remap;          // write outputs at the source frame index (else compact)
 };
 
 struct ConvLaunch {

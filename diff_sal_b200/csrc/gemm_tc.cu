@@ -1,19 +1,20 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel (see gemm_tc.cuh).  Warp-specialised, persistent:
 //   warp 0      : TMA producer (one lane)           smem ring  full[] / empty[]
 //   warp 1      : tcgen05.mma issuer (one lane)      TMEM double buffer  tmem_full[] / tmem_empty[]
-//   warps 2..5  : epilogue, one TMEM lane quadrant each (tcgen05.ld -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue, two per TMEM lane quadrant (tcgen05.ld -> registers -> fused epilogue -> global)
 #include "gemm_tc.cuh"
 
 #include <stdio.h>
 
 namespace dsb {
 
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 8;            // two warps per TMEM lane quadrant, splitting the column chunks
+static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 static constexpr int kMaxStages = 8;
 static constexpr uint32_t kAccStride = 256;   // TMEM columns between the two accumulator buffers
 static constexpr uint32_t kTmemCols = 512;
 
-struct __align__(8) GemmBarriers {
+struct __align__(16) GemmBarriers {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
     uint64_t tmem_full[2];
@@ -32,6 +33,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     const uint32_t b_bytes = (uint32_t)p.bn * p.bk * 2u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + (size_t)num_stages * stage_bytes);
+    // per-epilogue-warp transpose tile [32 rows][36 words] + row table, behind the barriers
+    float* epi_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(GemmBarriers));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -45,7 +48,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
-            mbar_init(&bars->tmem_empty[a], 128);
+            mbar_init(&bars->tmem_empty[a], 32 * kEpiWarps);
         }
         mbar_fence_init();
     }
@@ -74,7 +77,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 const int tf = mt / (p.tiles_x * p.tiles_y);
                 const int x0 = tx << bw_log2;
                 const int y0 = ty << bh_log2;
-                const int f0 = tf << (7 - bw_log2 - bh_log2);
+                int f0 = tf << (7 - bw_log2 - bh_log2);
+                if (p.f_group) f0 = (f0 / p.f_used) * p.f_group + f0 % p.f_used;
+                const int fb = f0;                                   // per-frame B operand: indexed by SOURCE frame
                 const int y2 = (p.ydim == 2) ? y0 : 0;
                 const int y3 = (p.ydim == 3) ? y0 : 0;
                 for (int tap = 0; tap < p.taps; ++tap) {
@@ -87,7 +92,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         uint8_t* sa = smem + (size_t)s * stage_bytes;
                         tma_load_5d(sa, &tmA, &bars->full[s], p.tap_off[tap][0] + cb * p.bk, c1, c2, c3, f0);
                         tma_load_2d(sa + a_bytes, &tmB, &bars->full[s], (tap * p.cin_blocks + cb) * p.bk,
-                                    nt * p.bn + f0 * p.b_rows_per_frame);
+                                    nt * p.bn + fb * p.b_rows_per_frame);
                         if (++s == num_stages) { s = 0; phase ^= 1u; }
                     }
                 }
@@ -125,8 +130,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;             // which of the quadrant's two warps: takes every other chunk
         const int r = q * 32 + lane;                  // accumulator row == pixel within the tile
         const int rx = r & ((1 << bw_log2) - 1);
         const int ry = (r >> bw_log2) & ((1 << bh_log2) - 1);
@@ -143,8 +149,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const int y = (ty << bh_log2) + ry;
             const int f = (tf << (7 - bw_log2 - bh_log2)) + rf;
             const bool valid = (x < p.W) && (y < p.H) && (f < p.F);
-            const size_t pix_in = ((size_t)f * p.H + y) * p.W + x;
-            const size_t pix_out = ((size_t)(f * p.out_fmul + p.out_fadd) * p.H + y) * p.W + x;
+            const int fs = p.f_group ? (f / p.f_used) * p.f_group + f % p.f_used : f;     // source frame
+            const int fo = p.out_remap ? fs : f;
+            const size_t pix_in = ((size_t)fs * p.H + y) * p.W + x;
+            const size_t pix_out = ((size_t)(fo * p.out_fmul + p.out_fadd) * p.H + y) * p.W + x;
             const int n0 = nt * p.bn;
 
             mbar_wait(&bars->tmem_full[acc], acc_phase);
@@ -152,7 +160,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
             float head = 0.0f;
             if (p.out_softmax) {
-                // 2 heads x 18 keys: the whole score row lives in this thread
+                // 2 heads x 18 keys: the whole score row lives in this thread (one warp per quadrant does it)
+                if (half == 0) {
                 uint32_t raw[48];
                 tmem_ld16(t_addr + 0, *reinterpret_cast<uint32_t(*)[16]>(raw + 0));
                 tmem_ld16(t_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(raw + 16));
@@ -187,63 +196,152 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     op[6] = make_uint4(0u, 0u, 0u, 0u);
                     op[7] = make_uint4(0u, 0u, 0u, 0u);
                 }
-            } else
-            for (int c = 0; c < p.bn; c += 16) {
-                uint32_t raw[16];
-                tmem_ld16(t_addr + c, raw);
-                tmem_ld_wait();
-                if (valid) {
-                    const int n = n0 + c;
-                    float v[16];
+                }
+            } else if (p.head_w) {
+                // fused 96 -> 1 head: each of the quadrant's two warps reduces its chunks, partials meet in smem
+                for (int c = half * 16; c < p.bn; c += 32) {
+                    uint32_t raw[16];
+                    tmem_ld16(t_addr + c, raw);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int n = n0 + c;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-                    if (p.scale) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] *= __ldg(p.scale + n + j);
-                    }
-                    if (p.shift) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.shift + n + j);
-                    }
-                    if (p.rowbias) {
-                        const float* rb = p.rowbias + (size_t)f * p.N + n;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __ldg(rb + j);
-                    }
-                    if (p.act == ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-                    } else if (p.act == ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (p.residual) {
-                        const float4* rp = reinterpret_cast<const float4*>(p.residual + pix_in * p.N + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t = rp[j];
-                            v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        for (int j = 0; j < 16; ++j) {
+                            float v = __uint_as_float(raw[j]);
+                            if (p.scale) v *= __ldg(p.scale + n + j);
+                            if (p.shift) v += __ldg(p.shift + n + j);
+                            if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
+                            head = fmaf(v, __ldg(p.head_w + n + j), head);
                         }
                     }
-                    if (p.head_w) {
+                }
+            } else if (!p.epi_transposed) {
+                // direct epilogue: thread = one output row, 16-column chunks; the residual of a chunk is requested
+                // before the TMEM load so that its DRAM latency overlaps the tcgen05.ld round trip
+                for (int c = half * 16; c < p.bn; c += 32) {
+                    const int n = n0 + c;
+                    float4 res[4];
+                    if (p.residual && valid) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.residual + pix_in * p.N + n);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) head = fmaf(v[j], __ldg(p.head_w + n + j), head);
+                        for (int j = 0; j < 4; ++j) res[j] = rp[j];
                     }
-                    if (p.out_f32) {
-                        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix_out * p.ldo + n);
+                    uint32_t raw[16];
+                    tmem_ld16(t_addr + c, raw);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float v[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                        if (p.scale) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
+                                v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+                            }
+                        }
+                        if (p.shift) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        }
+                        if (p.rowbias) {
+                            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)fs * p.N + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 t = __ldg(rb + j);
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        }
+                        if (p.act == ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        } else if (p.act == ACT_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                        }
+                        if (p.residual) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+                            }
+                        }
+                        if (p.out_f32) {
+                            float4* op = reinterpret_cast<float4*>(p.out_f32 + pix_out * p.ldo + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                        if (p.out_bf16) {
+                            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
+                            op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                               pack_bf16x2(v[6], v[7]));
+                            op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                               pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                        }
                     }
-                    if (p.out_bf16) {
-                        uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
-                        op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                           pack_bf16x2(v[6], v[7]));
-                        op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                }
+            } else {
+                // general epilogue: 32-column chunks are transposed through shared memory so that one warp
+                // instruction touches whole 128-byte rows (coalesced residual loads and output stores)
+                float* tile = epi_base + 128 + (warp - 2) * (32 * 36 + 96);
+                int* rowtab = reinterpret_cast<int*>(tile + 32 * 36);      // [32][3]: pix_out, pix_in, frame (or -1)
+                __syncwarp();
+                rowtab[lane * 3 + 0] = valid ? (int)pix_out : -1;
+                rowtab[lane * 3 + 1] = (int)pix_in;
+                rowtab[lane * 3 + 2] = fs;
+                const int cq = (lane & 7) * 4;                             // this lane's 4 columns inside the chunk
+                const int rq = lane >> 3;                                  // row offset inside a group of 4 rows
+                for (int c = half * 32; c < p.bn; c += 64) {
+                    uint32_t raw[32];
+                    tmem_ld32(t_addr + c, raw);
+                    tmem_ld_wait();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(tile + lane * 36 + 4 * j) =
+                            make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+                    __syncwarp();
+                    const int n = n0 + c + cq;
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+                    if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rq;
+                        const int po = rowtab[row * 3 + 0];
+                        if (po < 0) continue;
+                        float4 v = *reinterpret_cast<const float4*>(tile + row * 36 + cq);
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        if (p.rowbias) {
+                            const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)rowtab[row * 3 + 2] * p.N + n));
+                            v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
+                        }
+                        if (p.act == ACT_RELU) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        } else if (p.act == ACT_GELU) {
+                            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+                        }
+                        if (p.residual) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.residual + (size_t)rowtab[row * 3 + 1] * p.N + n);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
+                        if (p.out_bf16)
+                            *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po * p.ldo + n) =
+                                make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                     }
                 }
             }
-            if (p.head_w && valid) p.out_head[pix_out] = 1.0f / (1.0f + __expf(-(head + p.head_b)));
+            if (p.head_w) {
+                float* hp = epi_base + q * 32 + lane;                           // [4 quadrants][32 rows]
+                if (half == 1) *hp = head;
+                asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 epilogue warps only
+                if (half == 0 && valid) p.out_head[pix_out] = 1.0f / (1.0f + __expf(-(head + *hp + p.head_b)));
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             tc_fence_before();
             mbar_arrive(&bars->tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -317,13 +415,16 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.bw_log2 + p.bh_log2 > 7) return -13;
     if (p.head_w && p.N != p.bn) return -14;
     if (p.out_softmax && (p.N != 48 || p.bn != 48)) return -17;
-    if (p.b_rows_per_frame && (p.bw_log2 + p.bh_log2 != 7)) return -18;
+    if ((p.b_rows_per_frame || p.f_group) && (p.bw_log2 + p.bh_log2 != 7)) return -18;
+    if (p.bn % 32 && !p.out_softmax && !p.head_w) return -19;
+    if (p.f_group && (p.f_used < 1 || p.f_used > p.f_group)) return -19;
     const uint32_t stage_bytes = 128u * p.bk * 2u + (uint32_t)p.bn * p.bk * 2u;
-    const uint32_t budget = 200u * 1024u;
+    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? 8 * (32 * 36 + 96) : 0) + 128 + 8 * (32 * 36 + 96) * 0) * sizeof(float);
+    const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes - 8u * (32 * 36 + 96) * 0u;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -15;
-    const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + epi_bytes + 1024;
     if (int e = gemm_init()) return e;
     const int total = p.tiles_x * p.tiles_y * p.tiles_f * (p.N / p.bn);
     int grid = total < num_sms ? total : num_sms;

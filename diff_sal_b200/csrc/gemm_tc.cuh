@@ -30,12 +30,17 @@ struct GemmParams {
     int N, bn;                      // N % bn == 0, bn % 16 == 0, bn <= 256
     int b_rows_per_frame;           // 0: shared weights; else B rows of frame f start at f * b_rows_per_frame
                                     //    (per-frame attention operands; requires single-frame tiles)
+    // frame remap (dead-frame elimination): tile frame tf reads / adds the residual of source frame
+    // (tf / f_used) * f_group + tf % f_used (e.g. frames 0..4 of every 9); 0 = identity.  Needs single-frame tiles.
+    int f_group, f_used;
+    int out_remap;                  // 1: outputs are written at the source frame index too, 0: compact (tf)
     // epilogue: v = act(acc * scale[n] + shift[n] + rowbias[frame][n]) + residual[pix][n]
     const float* scale;             // [N] or null (== 1)
     const float* shift;             // [N] or null (== 0)
     const float* rowbias;           // [F][N] or null
     const float* residual;          // fp32 [pix][N] or null
     int act;
+    int epi_transposed;             // 1: stage 32-column chunks through smem for row-coalesced global access
     float* out_f32;                 // [pix][ldo] or null
     bf16* out_bf16;                 // [pix][ldo] or null
     int ldo;                        // output row pitch in elements

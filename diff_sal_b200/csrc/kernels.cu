@@ -242,11 +242,13 @@ int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cud
 
 // ------------------------------------------------------------------------------------------ LayerNorm (warp / token)
 template <int NV>
-__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, long tokens, float2* stats) {
+__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, long tokens, float2* stats, int hw,
+                                                      int T, int tmax) {
     constexpr int C = NV * 32;
     const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tok >= tokens) return;
+    if ((int)((tok / hw) % T) >= tmax) return;
     const float* row = x + tok * C;
     float v[NV];
     float s = 0.0f;
@@ -260,13 +262,13 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__
     if (lane == 0) stats[tok] = make_float2(mean, rsqrtf(var + 1e-5f));
 }
 
-int ln_stats_launch(const float* x, long tokens, int C, float2* stats, cudaStream_t s) {
+int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, int T, int tmax, cudaStream_t s) {
     const int g = (int)((tokens + 7) / 8);
     switch (C) {
-        case 96: ln_stats_kernel<3><<<g, 256, 0, s>>>(x, tokens, stats); break;
-        case 192: ln_stats_kernel<6><<<g, 256, 0, s>>>(x, tokens, stats); break;
-        case 384: ln_stats_kernel<12><<<g, 256, 0, s>>>(x, tokens, stats); break;
-        case 768: ln_stats_kernel<24><<<g, 256, 0, s>>>(x, tokens, stats); break;
+        case 96: ln_stats_kernel<3><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
+        case 192: ln_stats_kernel<6><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
+        case 384: ln_stats_kernel<12><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
+        case 768: ln_stats_kernel<24><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
         default: return -31;
     }
     DSB_LAUNCH_CHECK();
@@ -318,13 +320,14 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
                                                     long tokens, int H, int W, const float* __restrict__ ng,
                                                     const float* __restrict__ nb, const float* __restrict__ wq,
                                                     const float* __restrict__ qg, const float* __restrict__ qb,
-                                                    bf16* __restrict__ out) {
+                                                    bf16* __restrict__ out, int T, int tmax) {
     constexpr int C = NV * 32;
     const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const int hw = H * W;
     const long f = tok / hw;
+    if ((int)(f % T) >= tmax) return;
     const int pix = (int)(tok % hw);
     const int y = pix / W, xx = pix % W;
     float g[NV], b[NV], q[NV];
@@ -367,14 +370,14 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
 }
 
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
-                  const float* wq, const float* qg, const float* qb, bf16* out, cudaStream_t s) {
+                  const float* wq, const float* qg, const float* qb, bf16* out, int T, int tmax, cudaStream_t s) {
     const long tokens = (long)F * H * W;
     const int g = (int)((tokens + 7) / 8);
     switch (C) {
-        case 96: q_dwln_kernel<3><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
-        case 192: q_dwln_kernel<6><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
-        case 384: q_dwln_kernel<12><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
-        case 768: q_dwln_kernel<24><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out); break;
+        case 96: q_dwln_kernel<3><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 192: q_dwln_kernel<6><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 384: q_dwln_kernel<12><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 768: q_dwln_kernel<24><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
         default: return -31;
     }
     DSB_LAUNCH_CHECK();
@@ -427,11 +430,12 @@ __device__ __forceinline__ void pool_accumulate(const Src& src, int C, int npx, 
 __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __restrict__ stats, int H, int W, int C,
                                int s_, const float* __restrict__ ng, const float* __restrict__ nb,
                                const float* __restrict__ wv, const float* __restrict__ vg,
-                               const float* __restrict__ vb, bf16* __restrict__ out) {
+                               const float* __restrict__ vb, bf16* __restrict__ out, int T, int tmax) {
     extern __shared__ float sm[];          // part[G][C]; pre[C] aliases part[0]
     __shared__ float red[32];
     const int tokv = blockIdx.x;           // f*18 + Y*6 + X
     const int f = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
+    if (f % T >= tmax) return;
     const size_t fbase = (size_t)f * H * W;
     auto src = [&](int p, int c) -> float {
         const int dy = p / s_, dx = p % s_;
@@ -446,94 +450,106 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
 static int pool_threads(int C) { return C <= 192 ? 192 : 384; }
 
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
-                   const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, cudaStream_t s) {
+                   const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, int T, int tmax,
+                   cudaStream_t s) {
     const int nthr = pool_threads(C);
     const int G = (C <= nthr) ? nthr / C : 1;
     const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
-    pool_ln_kernel<<<F * 18, nthr, smem, s>>>(x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out);
+    pool_ln_kernel<<<F * 18, nthr, smem, s>>>(x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax);
     DSB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------ audio gate
-// one block per (y, b): m[x][c] = mean_t a*x ; softmax over x ; g written as [b][c][y][x]
+// one block per (y, b, 32-channel chunk): m[x][c] = mean_t a*x ; softmax over x ; g written as [b][c][y][x]
 __global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ x, const float* __restrict__ a_low,
                                                      int T, int H, int W, int C, float* __restrict__ g) {
-    extern __shared__ float m[];           // [W][C+1]
-    const int y = blockIdx.x, b = blockIdx.y;
+    __shared__ float m[96 * 33];           // [W][33]
+    const int y = blockIdx.x, b = blockIdx.y, c0 = blockIdx.z * 32;
     const int r = H / 7;
-    const int CP = C + 1;
     const float invT = 1.0f / (float)T;
-    for (int e = threadIdx.x; e < W * C; e += 256) {
-        const int c = e % C, xx = e / C;
+    for (int e = threadIdx.x; e < W * 32; e += 256) {
+        const int c = e & 31, xx = e >> 5;
         float acc = 0.0f;
         for (int t = 0; t < T; ++t) {
             const size_t fr = (size_t)b * T + t;
-            const float xv = x[((fr * H + y) * W + xx) * C + c];
-            const float av = a_low[((fr * 7 + y / r) * 12 + xx / r) * C + c];
+            const float xv = x[((fr * H + y) * W + xx) * C + c0 + c];
+            const float av = a_low[((fr * 7 + y / r) * 12 + xx / r) * C + c0 + c];
             acc = fmaf(av, xv, acc);
         }
-        m[xx * CP + c] = acc * invT;
+        m[xx * 33 + c] = acc * invT;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
+    {   // softmax over x: 8 threads per channel, shuffle-reduced
+        const int c = threadIdx.x >> 3, part = threadIdx.x & 7;
         float mx = -INFINITY;
-        for (int xx = 0; xx < W; ++xx) mx = fmaxf(mx, m[xx * CP + c]);
+        for (int xx = part; xx < W; xx += 8) mx = fmaxf(mx, m[xx * 33 + c]);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float sum = 0.0f;
-        for (int xx = 0; xx < W; ++xx) { const float e = expf(m[xx * CP + c] - mx); m[xx * CP + c] = e; sum += e; }
+        for (int xx = part; xx < W; xx += 8) { const float e = expf(m[xx * 33 + c] - mx); m[xx * 33 + c] = e; sum += e; }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float inv = 1.0f / sum;
-        for (int xx = 0; xx < W; ++xx) m[xx * CP + c] *= inv;
+        for (int xx = part; xx < W; xx += 8) m[xx * 33 + c] *= inv;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < W * C; e += 256) {
+    for (int e = threadIdx.x; e < W * 32; e += 256) {
         const int xx = e % W, c = e / W;
-        g[(((size_t)b * C + c) * H + y) * W + xx] = m[xx * CP + c];
+        g[(((size_t)b * C + c0 + c) * H + y) * W + xx] = m[xx * 33 + c];
     }
 }
 
 int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s) {
-    const size_t smem = (size_t)W * (C + 1) * sizeof(float);
-    av_gate_kernel<<<dim3(H, B), 256, smem, s>>>(x, a_low, T, H, W, C, g);
+    if (W > 96 || C % 32) return -33;
+    av_gate_kernel<<<dim3(H, B, C / 32), 256, 0, s>>>(x, a_low, T, H, W, C, g);
     DSB_LAUNCH_CHECK();
 }
 
 // K source = raw reinterpretation of the contiguous [B][C][T][H][W] buffer (a*g) as [(B T)][H W][C]
 // (transformer.py:146) followed by 'b (h w) c -> b c h w' (attention.py:89): element (bt, pix', c') is the flat
 // element j = (bt % T)*HW*C + pix'*C + c' of clip b = bt / T, and flat j decodes to (c, t, pix) = [C][T][HW].
-__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int T, int H, int W,
-                                int C, int s_, const float* __restrict__ wk, const float* __restrict__ kg,
+template <int C, int H, int W, int S_>
+__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int T, int tmax,
+                                const float* __restrict__ wk, const float* __restrict__ kg,
                                 const float* __restrict__ kb, bf16* __restrict__ out) {
     extern __shared__ float sm[];
     __shared__ float red[32];
+    constexpr int HW = H * W;
+    constexpr int R = H / 7;
     const int tokv = blockIdx.x;                 // bt*18 + Y*6 + X
     const int bt = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
     const int b = bt / T, tt = bt % T;
-    const int HW = H * W;
-    const int r = H / 7;
-    const long clip_base = (long)tt * HW * C;
+    if (tt >= tmax) return;
+    const int clip_base = tt * HW * C;           // < 9 * 516096, fits int
     const int THW = T * HW;
     auto src = [&](int p, int c) -> float {
-        const int dy = p / s_, dx = p % s_;
-        const int pixp = (Y * s_ + dy) * W + (X * s_ + dx);
-        const long j = clip_base + (long)pixp * C + c;
-        const int cs = (int)(j / THW);
-        const int rem = (int)(j % THW);
+        const int dy = p / S_, dx = p % S_;
+        const int pixp = (Y * S_ + dy) * W + (X * S_ + dx);
+        const int j = clip_base + pixp * C + c;
+        const int cs = j / THW;
+        const int rem = j - cs * THW;
         const int ts = rem / HW;
-        const int pix = rem % HW;
-        const int ys = pix / W, xs = pix % W;
-        const float av = a_low[((((size_t)b * T + ts) * 7 + ys / r) * 12 + xs / r) * C + cs];
+        const int pix = rem - ts * HW;
+        const int ys = pix / W, xs = pix - ys * W;
+        const float av = a_low[((((size_t)b * T + ts) * 7 + ys / R) * 12 + xs / R) * C + cs];
         const float gv = g[((size_t)b * C + cs) * HW + pix];
         return wk[p * C + c] * (av * gv);
     };
-    pool_accumulate(src, C, s_ * s_, sm);
+    pool_accumulate(src, C, S_ * S_, sm);
     pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
 }
 
 int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_, const float* wk,
-                    const float* kg, const float* kb, bf16* out, cudaStream_t s) {
+                    const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s) {
     const int nthr = pool_threads(C);
     const int G = (C <= nthr) ? nthr / C : 1;
     const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
-    kpool_av_kernel<<<B * T * 18, nthr, smem, s>>>(g, a_low, T, H, W, C, s_, wk, kg, kb, out);
+    const int grid = B * T * 18;
+    if (C == 768 && H == 7 && W == 12 && s_ == 2) kpool_av_kernel<768, 7, 12, 2><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
+    else if (C == 384 && H == 14 && W == 24 && s_ == 4) kpool_av_kernel<384, 14, 24, 4><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
+    else if (C == 192 && H == 28 && W == 48 && s_ == 8) kpool_av_kernel<192, 28, 48, 8><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
+    else if (C == 96 && H == 56 && W == 96 && s_ == 16) kpool_av_kernel<96, 56, 96, 16><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
+    else return -34;
     DSB_LAUNCH_CHECK();
 }
 
@@ -575,43 +591,63 @@ int attn_operands_launch(const float* kp, const float* vp, int F, int C, float s
 // ------------------------------------------------------------------------------------------ multi-scale sum
 struct MsSrc { const float* r[4]; };
 
-__global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, int B, bf16* __restrict__ S) {
-    constexpr int C = 768, CV = C / 4, OH = 112, OW = 192;
-    const long total = (long)B * OH * OW * CV;
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        const int cv = (int)(i % CV);
-        long p = i / CV;
-        const int xo = (int)(p % OW); p /= OW;
-        const int yo = (int)(p % OH);
-        const int b = (int)(p / OH);
-        float4 acc = make_float4(0, 0, 0, 0);
+// thread = (4-channel vector, output row); walks 32 output columns keeping the vertically interpolated left / right
+// source columns of each scale in registers, so a source element is loaded ~once per row instead of once per output
+__global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
+    constexpr int C = 768, CV = C / 4, OH = 112, OW = 192, XT = 32;
+    const int cv = blockIdx.z % 12 * 16 + (threadIdx.x & 15);
+    const int b = blockIdx.z / 12;
+    const int yo = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const int xo0 = blockIdx.x * XT;
+    const float4* base[4];
+    int y0[4], y1[4];
+    float ly[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int H = 7 << k, W = 12 << k;
+        base[k] = reinterpret_cast<const float4*>(src.r[k] + (size_t)b * H * W * C) + cv;
+        bil_src(yo, (float)H / (float)OH, H, y0[k], y1[k], ly[k]);
+    }
+    float4 colL[4], colR[4];
+    int xl[4] = {-1, -1, -1, -1}, xr[4] = {-1, -1, -1, -1};
+    auto vload = [&](int k, int xs) -> float4 {
+        const int W = 12 << k;
+        const float4 a = base[k][((size_t)y0[k] * W + xs) * CV], c = base[k][((size_t)y1[k] * W + xs) * CV];
+        const float h0 = 1.0f - ly[k], h1 = ly[k];
+        return make_float4(h0 * a.x + h1 * c.x, h0 * a.y + h1 * c.y, h0 * a.z + h1 * c.z, h0 * a.w + h1 * c.w);
+    };
+    uint2* orow = reinterpret_cast<uint2*>(S) + (((size_t)b * OH + yo) * OW + xo0) * CV + cv;
+    for (int dx = 0; dx < XT; ++dx) {
+        const int xo = xo0 + dx;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int H = 7 << k, W = 12 << k;
-            const float scale = (float)H / (float)OH;
-            int y0, y1, x0, x1; float ly, lx;
-            bil_src(yo, scale, H, y0, y1, ly);
-            bil_src(xo, scale, W, x0, x1, lx);
-            const float4* s4 = reinterpret_cast<const float4*>(src.r[k] + (size_t)b * H * W * C);
-            const float4 v00 = s4[((size_t)y0 * W + x0) * CV + cv], v01 = s4[((size_t)y0 * W + x1) * CV + cv];
-            const float4 v10 = s4[((size_t)y1 * W + x0) * CV + cv], v11 = s4[((size_t)y1 * W + x1) * CV + cv];
-            const float hy0 = 1.0f - ly, hx0 = 1.0f - lx;
-            acc.x += hy0 * (hx0 * v00.x + lx * v01.x) + ly * (hx0 * v10.x + lx * v11.x);
-            acc.y += hy0 * (hx0 * v00.y + lx * v01.y) + ly * (hx0 * v10.y + lx * v11.y);
-            acc.z += hy0 * (hx0 * v00.z + lx * v01.z) + ly * (hx0 * v10.z + lx * v11.z);
-            acc.w += hy0 * (hx0 * v00.w + lx * v01.w) + ly * (hx0 * v10.w + lx * v11.w);
+            const int W = 12 << k;
+            int x0, x1;
+            float lx;
+            bil_src(xo, (float)W / (float)OW, W, x0, x1, lx);
+            if (x0 != xl[k]) {
+                if (x0 == xr[k]) colL[k] = colR[k]; else colL[k] = vload(k, x0);
+                xl[k] = x0;
+            }
+            if (x1 != xr[k]) {
+                if (x1 == xl[k]) colR[k] = colL[k]; else colR[k] = vload(k, x1);
+                xr[k] = x1;
+            }
+            const float w0 = 1.0f - lx;
+            acc.x += w0 * colL[k].x + lx * colR[k].x;
+            acc.y += w0 * colL[k].y + lx * colR[k].y;
+            acc.z += w0 * colL[k].z + lx * colR[k].z;
+            acc.w += w0 * colL[k].w + lx * colR[k].w;
         }
-        reinterpret_cast<uint2*>(S)[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+        orow[(size_t)dx * CV] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
     }
 }
 
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {
     MsSrc src;
     for (int k = 0; k < 4; ++k) src.r[k] = r[k];
-    const long total = (long)B * 112 * 192 * 192;
-    long g = (total + 255) / 256;
-    if (g > 148 * 16) g = 148 * 16;
-    ms_sum_kernel<<<(int)g, 256, 0, s>>>(src, B, S);
+    ms_sum_kernel<<<dim3(192 / 32, 112 / 16, B * 12), 256, 0, s>>>(src, S);
     DSB_LAUNCH_CHECK();
 }
 

@@ -30,25 +30,26 @@ int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, con
 int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s);
 
 // LayerNorm(eps 1e-5) statistics per token: stats[token] = (mean, rstd)
-int ln_stats_launch(const float* x, long tokens, int C, float2* stats, cudaStream_t s);
+// tokens of frames with (frame % T) >= tmax are skipped (hw = tokens per frame)
+int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, int T, int tmax, cudaStream_t s);
 // out = bf16(LN(x) * gamma + beta); tokens of frames with (frame % T) >= tmax are skipped (hw = tokens per frame)
 int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
                     int T, int tmax, cudaStream_t s);
 
 // q = LN_q( depthwise3x3( LN_norm(x) ) )  -> bf16 [tokens][C]      (attention.py:36-48,92 ; transformer.py:151)
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
-                  const float* wq /*[9][C]*/, const float* qg, const float* qb, bf16* out, cudaStream_t s);
+                  const float* wq /*[9][C]*/, const float* qg, const float* qb, bf16* out, int T, int tmax, cudaStream_t s);
 
 // v (or visual-only k) = LN( depthwise sxs stride s ( LN_norm(x) ) ) -> bf16 [F*18][C]   (attention.py:53-76,93)
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
-                   const float* nb, const float* wv /*[s*s][C]*/, const float* vg, const float* vb, bf16* out,
-                   cudaStream_t s);
+                   const float* nb, const float* wv /*[s*s][C]*/, const float* vg, const float* vb, bf16* out, int T,
+                   int tmax, cudaStream_t s);
 
 // audio gate: g[b][c][y][x] = softmax_x( mean_t( a[b,t,y/r,x/r,c] * x[b,t,y,x,c] ) )   (transformer.py:140-144)
 int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s);
 // k = LN( depthwise sxs stride s ( scrambled (a*g) ) ) -> bf16 [B*T*18][C]   (transformer.py:145-146, attention.py:89-91)
 int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_,
-                    const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, cudaStream_t s);
+                    const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s);
 
 // per-frame tensor-core operands of the 18-key, 2-head attention:
 //   KB[f][h*18+j][c] = scale * K[f,j,c] if c in head h else 0        ([F][48][C], rows 36..47 zero)

@@ -396,8 +396,20 @@ int build_program(dsb_handle* h) {
             Xi = h->X[i];
         }
         const long tokens = (long)F * HW;
+        // Stage 3 is the last stage and ReduceTemp reads frames 0..4 only (sal_unet.py:449-454,469-481): its
+        // attention / MLP for frames 5..8 of every clip is dead work and is skipped (the gate still sees all 9).
+        const int tmax = (i == 3) ? kReduce : kT;
+        const bool remap = tmax < kT;
+        const int Fu = B * tmax;
+        const double live = (double)tmax / kT;
+        auto token_op = [&](int Cin_, int N_, const bf16* A_, const bf16* Wt_) {
+            // token-linear GEMM over the live frames (all tokens as one long row when nothing is skipped)
+            ConvOp op = remap ? make_op(CONV_1X1, Fu, 1, HW, Cin_, N_, A_, Wt_) : make_op(CONV_1X1, 1, 1, (int)tokens, Cin_, N_, A_, Wt_);
+            if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
+            return op;
+        };
         float2* stats = h->lnstats;
-        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, s); }, "ln_stats", (double)tokens * C * 4.0);
+        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, HW, kT, tmax, s); }, "ln_stats", (double)tokens * C * 4.0 * live);
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
         bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
         const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
@@ -409,16 +421,17 @@ int build_program(dsb_handle* h) {
             const float* al = h->a_low[i];
             float* gate = h->gate;
             b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
-            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, s); }, "kpool_av", (double)B * HW * C * 4.0);
+            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
         } else {
-            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, s); }, "pool_ln_k", (double)tokens * C * 4.0);
+            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
         }
-        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, s); }, "q_dwln", (double)tokens * C * 6.0);
-        b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, s); }, "pool_ln_v", (double)tokens * C * 4.0);
+        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
+        b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, kT, tmax, s); }, "pool_ln_v", (double)tokens * C * 4.0 * live);
+        // algorithmic FLOPs are always the reference's (all 9 frames), also where dead frames are skipped
         {
-            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, q_ln, WP(bk + "attn.proj_q.weight"));
+            ConvOp op = token_op(C, C, q_ln, WP(bk + "attn.proj_q.weight"));
             op.shift = W(h, bk + "attn.proj_q.bias"); op.out_bf16 = h->Qp;
-            b.conv(op, "attn.proj_q");
+            b.conv(op, "attn.proj_q", 2.0 * (double)tokens * C * C);
         }
         {
             ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
@@ -437,35 +450,37 @@ int build_program(dsb_handle* h) {
             b.add([=](cudaStream_t s) { return attn_operands_launch(Kp, Vp, F, C, scale, KB, VB, s); }, "attn_operands");
         }
         {   // scores + per-head softmax over the 18 keys
-            ConvOp op = make_op(CONV_1X1, F, 1, HW, C, 48, h->Qp, h->KB);
+            ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, C, 48, h->Qp, h->KB);
             op.b_rows_per_frame = 48; op.out_softmax = h->P;
+            if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
             b.conv(op, "attn.qk_softmax", 2.0 * (double)tokens * 18 * C);   // reference bmm count (2 heads x C/2)
         }
         {   // P . V
-            ConvOp op = make_op(CONV_1X1, F, 1, HW, 64, C, h->P, h->VB);
+            ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, 64, C, h->P, h->VB);
             op.b_rows_per_frame = C; op.out_bf16 = h->o;
+            if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
             b.conv(op, "attn.pv", 2.0 * (double)tokens * 18 * C);
         }
         {   // output projection + residual
-            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, C, h->o, WP(bk + "attn.proj.weight"));
+            ConvOp op = token_op(C, C, h->o, WP(bk + "attn.proj.weight"));
             op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
-            b.conv(op, "attn.proj");
+            b.conv(op, "attn.proj", 2.0 * (double)tokens * C * C);
         }
         {
             const float *g2 = W(h, bk + "norm2.weight"), *b2 = W(h, bk + "norm2.bias");
             const float* x1 = h->X1[i];
             bf16* ln2 = h->ln2;
-            b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, 1, 1, s); }, "ln_apply", (double)tokens * C * 6.0);
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, kT, tmax, s); }, "ln_apply", (double)tokens * C * 6.0 * live);
         }
         {
-            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
+            ConvOp op = token_op(C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
             op.shift = W(h, bk + "mlp.fc1.bias"); op.act = ACT_GELU; op.out_bf16 = h->hid;
-            b.conv(op, "mlp.fc1");
+            b.conv(op, "mlp.fc1", 4.0 * (double)tokens * C * C);
         }
         {
-            ConvOp op = make_op(CONV_1X1, 1, 1, (int)tokens, 2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
+            ConvOp op = token_op(2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
             op.shift = W(h, bk + "mlp.fc2.bias"); op.residual = h->X1[i]; op.out_f32 = h->X2[i];
-            b.conv(op, "mlp.fc2");
+            b.conv(op, "mlp.fc2", 4.0 * (double)tokens * C * C);
         }
         {   // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU
             const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";

@@ -56,7 +56,10 @@ def test_denoise_matches_oracle(engines, kind, audio, B, t):
     report = {}
     for name in ["noise2", "noise1", "noise0", "x0", "r0", "x1", "r1", "x2", "r2", "x3", "r3", "p"]:
         got = eng.debug_read(name, taps[name].numel()).reshape(taps[name].shape)
-        report[name] = _rel(got, taps[name])
+        want = taps[name]
+        if name == "x3":      # stage 3: frames 5..8 never reach the output and are skipped by the CUDA path
+            got, want = got[:, :5], want[:, :5]
+        report[name] = _rel(got, want)
     print(kind, audio, {k: "%.2e" % v for k, v in report.items()})
     for name, v in report.items():
         assert v < 3e-2, "stage tap %s diverges: rel err %g (all: %s)" % (name, v, report)
