@@ -51,6 +51,27 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.N = op.N;
     p.bn = bn;
     p.ydim = 2;
+    {
+        const long tiles = (long)p.tiles_x * p.tiles_y * p.tiles_f * (op.N / bn);
+        const bool eligible = !op.b_rows_per_frame && !op.out_softmax && (bn / 2) % 8 == 0;
+        p.two_cta = (op.two_cta > 0 || (op.two_cta == 0 && tiles >= 148)) && eligible ? 1 : 0;
+    }
+
+    {
+        // K sub-blocks per stage: long enough stages that the single-thread MMA issue loop (wait + commit per stage)
+        // stays shorter than the MMAs it issues (>= ~384 tensor cycles per stage), within ~56 KB per stage
+        const int n_eff = p.two_cta ? bn / 2 : bn;
+        const int sub_bytes = (128 + n_eff) * bk * 2;
+        const int sub_cycles = (bk / 16) * (bn / 2);
+        int ks = 1;
+        for (int cand = 1; cand <= p.cin_blocks; ++cand) {
+            if (p.cin_blocks % cand) continue;
+            if (cand * sub_bytes > 49152) break;
+            ks = cand;
+            if (cand * sub_cycles >= 384) break;
+        }
+        p.ksub = ks;
+    }
 
     uint64_t dims[5], strides[4];
     uint32_t box[5];
@@ -107,7 +128,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     const uint64_t wrows = op.b_rows_per_frame ? src_frames * op.b_rows_per_frame : (uint64_t)op.N;
     uint64_t wd[2] = {K, wrows};
     uint64_t ws[1] = {K * e};
-    uint32_t wb[2] = {(uint32_t)bk, (uint32_t)bn};
+    uint32_t wb[2] = {(uint32_t)bk, (uint32_t)(p.two_cta ? bn / 2 : bn)};
     r = make_tensor_map(&out->tmB, op.Wt, 2, wd, ws, wb);
     if (r) return r;
 

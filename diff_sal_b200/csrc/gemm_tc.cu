@@ -5,6 +5,7 @@
 #include "gemm_tc.cuh"
 
 #include <stdio.h>
+#include <string.h>
 
 namespace dsb {
 
@@ -23,14 +24,24 @@ struct __align__(16) GemmBarriers {
     uint32_t pad;
 };
 
+template <bool TWO>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const int num_stages) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_bytes = 128u * p.bk * 2u;
-    const uint32_t b_bytes = (uint32_t)p.bn * p.bk * 2u;
+    // two_cta: the CTA pair of a cluster shares one M = 256 tcgen05.mma (cta_group::2); each CTA stages its own 128
+    // A rows and HALF of the B rows, which halves the shared-memory operand traffic per MMA
+    constexpr bool two = TWO;            // separate instantiations: the 1-CTA kernel holds no cta_group::2 code
+    uint32_t rank = 0u;
+    if constexpr (two) rank = cluster_ctarank();
+    // a pipeline stage holds `ksub` K sub-blocks of bk channels: [ksub][128][bk] of A then [ksub][bn_local][bk] of B
+    const uint32_t a_sub = 128u * p.bk * 2u;
+    const uint32_t bn_local = two ? (uint32_t)p.bn / 2u : (uint32_t)p.bn;
+    const uint32_t b_sub = bn_local * p.bk * 2u;
+    const uint32_t a_bytes = a_sub * p.ksub;
+    const uint32_t b_bytes = b_sub * p.ksub;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + (size_t)num_stages * stage_bytes);
     // per-epilogue-warp transpose tile [32 rows][36 words] + row table, behind the barriers
@@ -43,89 +54,144 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < num_stages; ++s) {
-            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->full[s], two ? 2 : 1);         // pair: one arrive per CTA's producer, on the leader
             mbar_init(&bars->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars->tmem_full[a], 1);
-            mbar_init(&bars->tmem_empty[a], 32 * kEpiWarps);
+            mbar_init(&bars->tmem_empty[a], (two ? 2 : 1) * 32 * kEpiWarps);
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (warp == 1) {
+        if constexpr (two) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+        else tmem_alloc(&bars->tmem_base, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (two) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     const int n_tiles = p.N / p.bn;
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
-    const int total_tiles = m_tiles * n_tiles;
-    const int nk = p.taps * p.cin_blocks;
+    // work units: one (M tile, N tile) per CTA, or one (M-tile pair, N tile) per CTA pair
+    const int total_tiles = two ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+    const int unit0 = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nk = p.taps * p.cin_blocks / p.ksub;          // pipeline stages per tile
     const int bh_log2 = p.bh_log2, bw_log2 = p.bw_log2;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int s = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % n_tiles;
-                const int mt = tile / n_tiles;
-                const int tx = mt % p.tiles_x;
-                const int ty = (mt / p.tiles_x) % p.tiles_y;
-                const int tf = mt / (p.tiles_x * p.tiles_y);
-                const int x0 = tx << bw_log2;
-                const int y0 = ty << bh_log2;
-                int f0 = tf << (7 - bw_log2 - bh_log2);
-                if (p.f_group) f0 = (f0 / p.f_used) * p.f_group + f0 % p.f_used;
-                const int fb = f0;                                   // per-frame B operand: indexed by SOURCE frame
-                const int y2 = (p.ydim == 2) ? y0 : 0;
-                const int y3 = (p.ydim == 3) ? y0 : 0;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int c1 = p.tap_off[tap][1] + x0;
-                    const int c2 = p.tap_off[tap][2] + y2;
-                    const int c3 = p.tap_off[tap][3] + y3;
-                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                        mbar_wait(&bars->empty[s], phase ^ 1u);
+        // (whole warp convergent, one elected lane issues: keeps coordinates in uniform registers)
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            const int nt = tile % n_tiles;
+            const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;   // may be one past the end
+            const int tx = mt % p.tiles_x;
+            const int ty = (mt / p.tiles_x) % p.tiles_y;
+            const int tf = mt / (p.tiles_x * p.tiles_y);
+            const int x0 = tx << bw_log2;
+            const int y0 = ty << bh_log2;
+            int f0 = tf << (7 - bw_log2 - bh_log2);
+            if (p.f_group) f0 = (f0 / p.f_used) * p.f_group + f0 % p.f_used;
+            const int y2 = (p.ydim == 2) ? y0 : 0;
+            const int y3 = (p.ydim == 3) ? y0 : 0;
+            // per-frame B operand is indexed by the SOURCE frame; a pair splits the B rows between its CTAs
+            const int brow = nt * p.bn + (two ? (int)(rank * bn_local) : f0 * p.b_rows_per_frame);
+            int tap = 0, cb = 0;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&bars->empty[s], phase ^ 1u);
+                if (elect_one()) {
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    if constexpr (!two) {
                         mbar_expect_tx(&bars->full[s], stage_bytes);
-                        uint8_t* sa = smem + (size_t)s * stage_bytes;
-                        tma_load_5d(sa, &tmA, &bars->full[s], p.tap_off[tap][0] + cb * p.bk, c1, c2, c3, f0);
-                        tma_load_2d(sa + a_bytes, &tmB, &bars->full[s], (tap * p.cin_blocks + cb) * p.bk,
-                                    nt * p.bn + fb * p.b_rows_per_frame);
-                        if (++s == num_stages) { s = 0; phase ^= 1u; }
+                    } else {
+                        // both CTAs' bytes are credited to the leader's barrier
+                        if (rank == 0) mbar_expect_tx(&bars->full[s], 2u * stage_bytes);
+                        else mbar_arrive_leader(&bars->full[s]);
+                    }
+                    int tp = tap, c = cb;
+                    for (int j = 0; j < p.ksub; ++j) {
+                        const int c0 = p.tap_off[tp][0] + c * p.bk;
+                        const int c1 = p.tap_off[tp][1] + x0;
+                        const int c2 = p.tap_off[tp][2] + y2;
+                        const int c3 = p.tap_off[tp][3] + y3;
+                        const int kcol = (tp * p.cin_blocks + c) * p.bk;
+                        if constexpr (!two) {
+                            tma_load_5d(sa + j * a_sub, &tmA, &bars->full[s], c0, c1, c2, c3, f0);
+                            tma_load_2d(sa + a_bytes + j * b_sub, &tmB, &bars->full[s], kcol, brow);
+                        } else {
+                            tma_load_5d_2sm(sa + j * a_sub, &tmA, &bars->full[s], c0, c1, c2, c3, f0);
+                            tma_load_2d_2sm(sa + a_bytes + j * b_sub, &tmB, &bars->full[s], kcol, brow);
+                        }
+                        if (++c == p.cin_blocks) { c = 0; ++tp; }
                     }
                 }
+                __syncwarp();
+                cb += p.ksub;
+                if (cb >= p.cin_blocks) { cb -= p.cin_blocks; ++tap; }     // ksub divides cin_blocks
+                if (++s == num_stages) { s = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16((uint32_t)p.bn);
+        // The whole warp runs the loop convergently (uniform registers, no per-instruction election); one elected
+        // lane issues.  Descriptors are base + constant offsets: the issue loop must stay far shorter than the MMA
+        // time of a K block (192 cycles at N = 96), or the tensor pipe starves on instruction issue.
+        if (rank == 0) {                                    // in a pair only the leader issues
+            const uint32_t idesc = two ? umma_idesc_bf16_m256((uint32_t)p.bn) : umma_idesc_bf16((uint32_t)p.bn);
             const uint32_t row_bytes = (uint32_t)p.bk * 2u;
-            const int ksteps = p.bk / 16;
+            const uint64_t da0 = umma_smem_desc(smem_u32(smem), row_bytes);
+            const uint64_t db0 = umma_smem_desc(smem_u32(smem) + a_bytes, row_bytes);
+            const uint32_t stage_step = stage_bytes >> 4;   // descriptor start-address units (16 B)
+            const uint64_t a_sub_step = a_sub >> 4, b_sub_step = b_sub >> 4;
+            const bool k64 = p.bk == 64;
             int s = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < nk; ++kb) {
                     mbar_wait(&bars->full[s], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t b_addr = a_addr + a_bytes;
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t da = umma_smem_desc(a_addr + k * 32, row_bytes);
-                        const uint64_t db = umma_smem_desc(b_addr + k * 32, row_bytes);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+                    if (elect_one()) {
+                        uint64_t da = da0 + (uint64_t)((uint32_t)s * stage_step);
+                        uint64_t db = db0 + (uint64_t)((uint32_t)s * stage_step);
+                        for (int j = 0; j < p.ksub; ++j) {
+                            const uint32_t first = (kb | j) ? 1u : 0u;
+                            if constexpr (two) {
+                                umma_bf16_2sm(d_tmem, da, db, idesc, first);
+                                umma_bf16_2sm(d_tmem, da + 2, db + 2, idesc, 1u);
+                                if (k64) {
+                                    umma_bf16_2sm(d_tmem, da + 4, db + 4, idesc, 1u);
+                                    umma_bf16_2sm(d_tmem, da + 6, db + 6, idesc, 1u);
+                                }
+                            } else {
+                                umma_bf16(d_tmem, da, db, idesc, first);
+                                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+                                if (k64) {
+                                    umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                                    umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                                }
+                            }
+                            da += a_sub_step;
+                            db += b_sub_step;
+                        }
+                        // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+                        if constexpr (two) umma_commit_2sm(&bars->empty[s]); else umma_commit(&bars->empty[s]);
                     }
-                    umma_commit(&bars->empty[s]);     // frees the smem slot once these MMAs have read it
+                    __syncwarp();
                     if (++s == num_stages) { s = 0; phase ^= 1u; }
                 }
-                umma_commit(&bars->tmem_full[acc]);   // accumulator complete -> epilogue
+                if (elect_one()) {                                   // accumulator complete -> epilogue(s)
+                    if constexpr (two) umma_commit_2sm(&bars->tmem_full[acc]); else umma_commit(&bars->tmem_full[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -139,9 +205,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         const int rf = r >> (bw_log2 + bh_log2);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
             const int nt = tile % n_tiles;
-            const int mt = tile / n_tiles;
+            const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;
             const int tx = mt % p.tiles_x;
             const int ty = (mt / p.tiles_x) % p.tiles_y;
             const int tf = mt / (p.tiles_x * p.tiles_y);
@@ -343,16 +409,16 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             tc_fence_before();
-            mbar_arrive(&bars->tmem_empty[acc]);
+            if constexpr (two) mbar_arrive_leader(&bars->tmem_empty[acc]); else mbar_arrive(&bars->tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (two) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (two) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -400,7 +466,9 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 int gemm_init() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -418,7 +486,9 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if ((p.b_rows_per_frame || p.f_group) && (p.bw_log2 + p.bh_log2 != 7)) return -18;
     if (p.bn % 32 && !p.out_softmax && !p.head_w) return -19;
     if (p.f_group && (p.f_used < 1 || p.f_used > p.f_group)) return -19;
-    const uint32_t stage_bytes = 128u * p.bk * 2u + (uint32_t)p.bn * p.bk * 2u;
+    if (p.two_cta && (p.b_rows_per_frame || p.out_softmax || (p.bn / 2) % 8)) return -20;
+    if (p.ksub < 1 || (p.taps * p.cin_blocks) % p.ksub) return -21;
+    const uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
     const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? 8 * (32 * 36 + 96) : 0) + 128 + 8 * (32 * 36 + 96) * 0) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes - 8u * (32 * 36 + 96) * 0u;
     int stages = (int)(budget / stage_bytes);
@@ -426,11 +496,31 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (stages < 2) return -15;
     const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + epi_bytes + 1024;
     if (int e = gemm_init()) return e;
-    const int total = p.tiles_x * p.tiles_y * p.tiles_f * (p.N / p.bn);
-    int grid = total < num_sms ? total : num_sms;
-    if (grid < 1) return -16;
-    gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(p, tmA, tmB, stages);
-    return (int)cudaGetLastError();
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
+    if (!p.two_cta) {
+        const int total = m_tiles * (p.N / p.bn);
+        int grid = total < num_sms ? total : num_sms;
+        if (grid < 1) return -16;
+        gemm_tc_kernel<false><<<grid, kGemmThreads, smem, stream>>>(p, tmA, tmB, stages);
+        return (int)cudaGetLastError();
+    }
+    const int pairs = ((m_tiles + 1) / 2) * (p.N / p.bn);
+    int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    if (clusters < 1) return -16;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, p, tmA, tmB, stages);
 }
 
 }  // namespace dsb

@@ -24,10 +24,12 @@ struct GemmParams {
     int taps;                       // 1..9
     int cin_blocks;                 // Cin / BK
     int bk;                         // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int ksub;                       // K sub-blocks of bk channels per pipeline stage (amortises barrier round trips)
     int ydim;                       // which tensor-map dimension carries y (2 normally, 3 for the s2d view)
     int tap_off[9][4];              // per tap: coordinate offsets for tensor-map dims 0..3
     // N tiling
     int N, bn;                      // N % bn == 0, bn % 16 == 0, bn <= 256
+    int two_cta;                    // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs with M = 256
     int b_rows_per_frame;           // 0: shared weights; else B rows of frame f start at f * b_rows_per_frame
                                     //    (per-frame attention operands; requires single-frame tiles)
     // frame remap (dead-frame elimination): tile frame tf reads / adds the residual of source frame

@@ -18,12 +18,14 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
 }
 
 // ------------------------------------------------------------------------------------------ timestep embedding
+// All weights are pre-transposed to [in][out] so that thread j reads column j with coalesced loads.
+// grid (B, 4): every block recomputes the 2-layer MLP (cheap) and produces a quarter of the 1344 projection outputs.
 __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, TembWeights w, float* tp0, float* tp1,
                                                   float* tp2) {
     __shared__ float emb[96];
     __shared__ float h1[384];
     __shared__ float h2[384];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const float tv = t[b];
     if (tid < 48) {
         const float fr = expf((float)tid * -0.19596468876545072f);   // exp(-k * ln(1e4) / 47)
@@ -32,39 +34,36 @@ __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, 
         emb[48 + tid] = cosf(a);
     }
     __syncthreads();
-    for (int r = wid; r < 384; r += 12) {
-        const float* row = w.w0 + r * 96;
-        float acc = row[lane] * emb[lane] + row[lane + 32] * emb[lane + 32] + row[lane + 64] * emb[lane + 64];
-        acc = warp_sum(acc);
-        if (lane == 0) h1[r] = swishf(acc + w.b0[r]);
+    {
+        float acc = w.b0[tid];
+#pragma unroll 8
+        for (int k = 0; k < 96; ++k) acc = fmaf(w.w0[k * 384 + tid], emb[k], acc);
+        h1[tid] = swishf(acc);
     }
     __syncthreads();
-    for (int r = wid; r < 384; r += 12) {
-        const float* row = w.w1 + r * 384;
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc = fmaf(row[lane + 32 * k], h1[lane + 32 * k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) h2[r] = swishf(acc + w.b1[r]);      // only swish(temb) is consumed (sal_unet.py:129)
+    {
+        float acc = w.b1[tid];
+#pragma unroll 8
+        for (int k = 0; k < 384; ++k) acc = fmaf(w.w1[k * 384 + tid], h1[k], acc);
+        h2[tid] = swishf(acc);                               // only swish(temb) is consumed (sal_unet.py:129)
     }
     __syncthreads();
-    float* outs[3] = {tp0, tp1, tp2};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    const int o = blockIdx.y * 336 + tid;                    // 1344 = 192 + 384 + 768 outputs, 336 per block
+    if (tid < 336) {
+        int i, r;
+        if (o < 192) { i = 0; r = o; } else if (o < 576) { i = 1; r = o - 192; } else { i = 2; r = o - 576; }
         const int co = w.cout[i];
-        for (int r = wid; r < co; r += 12) {
-            const float* row = w.wp[i] + r * 384;
-            float acc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) acc = fmaf(row[lane + 32 * k], h2[lane + 32 * k], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) outs[i][(size_t)b * co + r] = acc + w.bp[i][r];
-        }
+        const float* wt = w.wp[i];
+        float acc = w.bp[i][r];
+#pragma unroll 8
+        for (int k = 0; k < 384; ++k) acc = fmaf(wt[k * co + r], h2[k], acc);
+        float* out = i == 0 ? tp0 : (i == 1 ? tp1 : tp2);
+        out[(size_t)b * co + r] = acc;
     }
 }
 
 int temb_launch(const float* t, int B, const TembWeights& w, float* const tp[3], cudaStream_t s) {
-    temb_kernel<<<B, 384, 0, s>>>(t, w, tp[0], tp[1], tp[2]);
+    temb_kernel<<<dim3(B, 4), 384, 0, s>>>(t, w, tp[0], tp[1], tp[2]);
     DSB_LAUNCH_CHECK();
 }
 
@@ -207,36 +206,50 @@ __device__ __forceinline__ void bil_src(int dst, float scale, int in_size, int& 
     l1 = src - (float)i0;
 }
 
-__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int F, int H, int W, int C,
-                                                        bf16* __restrict__ out) {
+// thread = (4-channel vector, output row); walks XT output columns keeping the vertically interpolated left / right
+// source columns in registers (each source element is loaded ~once per output row instead of once per output)
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int H, int W, int C,
+                                                        bf16* __restrict__ out, int XT) {
     const int cv_n = C >> 2;
-    const long total = (long)F * 4 * H * W * cv_n;
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-        const int cv = (int)(i % cv_n);
-        long p = i / cv_n;
-        const int xo = (int)(p % (2 * W)); p /= (2 * W);
-        const int yo = (int)(p % (2 * H));
-        const int f = (int)(p / (2 * H));
-        int y0, y1, x0, x1; float ly, lx;
-        bil_src(yo, 0.5f, H, y0, y1, ly);
-        bil_src(xo, 0.5f, W, x0, x1, lx);
-        const float4* src = reinterpret_cast<const float4*>(x + (size_t)f * H * W * C);
-        const float4 v00 = src[((size_t)y0 * W + x0) * cv_n + cv], v01 = src[((size_t)y0 * W + x1) * cv_n + cv];
-        const float4 v10 = src[((size_t)y1 * W + x0) * cv_n + cv], v11 = src[((size_t)y1 * W + x1) * cv_n + cv];
-        const float hy0 = 1.0f - ly, hx0 = 1.0f - lx;
-        const float r0 = hy0 * (hx0 * v00.x + lx * v01.x) + ly * (hx0 * v10.x + lx * v11.x);
-        const float r1 = hy0 * (hx0 * v00.y + lx * v01.y) + ly * (hx0 * v10.y + lx * v11.y);
-        const float r2 = hy0 * (hx0 * v00.z + lx * v01.z) + ly * (hx0 * v10.z + lx * v11.z);
-        const float r3 = hy0 * (hx0 * v00.w + lx * v01.w) + ly * (hx0 * v10.w + lx * v11.w);
-        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+    const int lanes = blockDim.x;                        // vector lanes per row group
+    const int cv = blockIdx.z * lanes + threadIdx.x;
+    const int yo = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.x / ((2 * W) / XT);
+    const int xo0 = (blockIdx.x % ((2 * W) / XT)) * XT;
+    if (cv >= cv_n || yo >= 2 * H) return;
+    int y0, y1;
+    float ly;
+    bil_src(yo, 0.5f, H, y0, y1, ly);
+    const float4* base = reinterpret_cast<const float4*>(x + (size_t)f * H * W * C) + cv;
+    auto vload = [&](int xs) -> float4 {
+        const float4 a = base[((size_t)y0 * W + xs) * cv_n], c = base[((size_t)y1 * W + xs) * cv_n];
+        const float h0 = 1.0f - ly, h1 = ly;
+        return make_float4(h0 * a.x + h1 * c.x, h0 * a.y + h1 * c.y, h0 * a.z + h1 * c.z, h0 * a.w + h1 * c.w);
+    };
+    float4 colL = make_float4(0, 0, 0, 0), colR = make_float4(0, 0, 0, 0);
+    int xl = -1, xr = -1;
+    uint2* orow = reinterpret_cast<uint2*>(out) + (((size_t)f * 2 * H + yo) * 2 * W + xo0) * cv_n + cv;
+    for (int dx = 0; dx < XT; ++dx) {
+        int x0, x1;
+        float lx;
+        bil_src(xo0 + dx, 0.5f, W, x0, x1, lx);
+        if (x0 != xl) { colL = (x0 == xr) ? colR : vload(x0); xl = x0; }
+        if (x1 != xr) { colR = (x1 == xl) ? colL : vload(x1); xr = x1; }
+        const float w0 = 1.0f - lx;
+        orow[(size_t)dx * cv_n] = make_uint2(pack_bf16x2(w0 * colL.x + lx * colR.x, w0 * colL.y + lx * colR.y),
+                                             pack_bf16x2(w0 * colL.z + lx * colR.z, w0 * colL.w + lx * colR.w));
     }
 }
 
 int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s) {
-    const long total = (long)F * 4 * H * W * (C / 4);
-    long g = (total + 255) / 256;
-    if (g > 148 * 16) g = 148 * 16;
-    upsample2x_kernel<<<(int)g, 256, 0, s>>>(x, F, H, W, C, out);
+    const int cv_n = C / 4;
+    const int lanes = (cv_n % 32 == 0) ? 32 : ((cv_n % 24 == 0) ? 24 : 16);
+    if (cv_n % lanes) return -35;
+    const int rows = 7;                                  // 2H is 14, 28 or 56
+    const int XT = 24;                                   // 2W is 24, 48, 96 or 192: all multiples of 24
+    if ((2 * W) % XT || (2 * H) % rows) return -35;
+    dim3 grid(F * ((2 * W) / XT), (2 * H) / rows, cv_n / lanes);
+    upsample2x_kernel<<<grid, dim3(lanes, rows), 0, s>>>(x, H, W, C, out, XT);
     DSB_LAUNCH_CHECK();
 }
 

@@ -305,12 +305,12 @@ int build_program(dsb_handle* h) {
     // ------------------------------------------------------------ noise encoder (sal_unet.py:279-300)
     {
         TembWeights tw;
-        tw.w0 = W(h, "temb.dense.0.weight"); tw.b0 = W(h, "temb.dense.0.bias");
-        tw.w1 = W(h, "temb.dense.1.weight"); tw.b1 = W(h, "temb.dense.1.bias");
+        tw.w0 = WF("temb.dense.0.weight.T"); tw.b0 = W(h, "temb.dense.0.bias");      // transposed [in][out]
+        tw.w1 = WF("temb.dense.1.weight.T"); tw.b1 = W(h, "temb.dense.1.bias");
         const int cout[3] = {192, 384, 768};
         for (int i = 0; i < 3; ++i) {
             const std::string r = "res_encoder." + std::to_string(i) + ".0.temb_proj.";
-            tw.wp[i] = W(h, r + "weight"); tw.bp[i] = W(h, r + "bias"); tw.cout[i] = cout[i];
+            tw.wp[i] = WF(r + "weight.T"); tw.bp[i] = W(h, r + "bias"); tw.cout[i] = cout[i];
         }
         float* tp[3] = {h->tp[0], h->tp[1], h->tp[2]};
         b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); }, "temb");
@@ -607,10 +607,22 @@ extern "C" int dsb_finalize_weights(dsb_handle* h) {
         h->wf["stem.w5"] = w5;
         h->wf["stem.b5"] = b5;
     }
+    auto transposed = [&](const std::string& key, int R, int Cc) -> int {
+        const Weight* w = find_w(h, key);
+        if (!w || w->numel != (long)R * Cc) return fail(h, DSB_ERR_WEIGHT, "missing / mis-shaped weight '%s'", key.c_str());
+        float* dst = nullptr;
+        if (int r = dev_alloc(h, &dst, (size_t)R * Cc)) return r;
+        if (int r = transpose_launch(w->p, R, Cc, dst, 0)) return fail(h, DSB_ERR_CUDA, "transpose launch %d", r);
+        h->wf[key + ".T"] = dst;
+        return 0;
+    };
+    if (int r = transposed("temb.dense.0.weight", 384, 96)) return r;
+    if (int r = transposed("temb.dense.1.weight", 384, 384)) return r;
     int cin = 96;
     const int cout[3] = {192, 384, 768};
     for (int i = 0; i < 3; ++i) {
         const std::string rk = "res_encoder." + std::to_string(i) + ".0.";
+        if (int r = transposed(rk + "temb_proj.weight", cout[i], 384)) return r;
         for (const char* k : {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "conv1.bias", "conv2.bias",
                               "nin_shortcut.bias", "temb_proj.weight", "temb_proj.bias"})
             if (!W(h, rk + k)) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s%s'", rk.c_str(), k);

@@ -13,6 +13,10 @@ static int num_sms_cached() {
     return n;
 }
 
+static int g_test_two_cta = 0;
+// -1: never use CTA pairs, 0: automatic, 1: always (for the per-kernel tests)
+extern "C" void dsb_test_set_two_cta(int mode) { g_test_two_cta = mode; }
+
 extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt,
                              const void* A, const void* Wt, const float* scale, const float* shift,
                              const float* rowbias, const float* residual, int act, float* out_f32, void* out_bf16,
@@ -25,6 +29,7 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     op.scale = scale; op.shift = shift; op.rowbias = rowbias; op.residual = residual; op.act = act;
     op.out_f32 = out_f32; op.out_bf16 = (bf16*)out_bf16; op.out_fmul = out_fmul; op.out_fadd = out_fadd;
     op.head_w = head_w; op.head_b = head_b; op.out_head = out_head;
+    op.two_cta = g_test_two_cta;
     ConvLaunch l;
     int r = conv_lower(op, &l);
     if (r) return r;

@@ -49,6 +49,18 @@ int bn_fold_launch(const float* w, const float* b, const float* mean, const floa
     return (int)cudaGetLastError();
 }
 
+__global__ void transpose_kernel(const float* __restrict__ src, int R, int Cc, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * Cc) return;
+    const int r = i / Cc, c = i % Cc;
+    dst[(size_t)c * R + r] = src[i];
+}
+
+int transpose_launch(const float* src, int R, int Cc, float* dst, cudaStream_t s) {
+    transpose_kernel<<<(R * Cc + 255) / 256, 256, 0, s>>>(src, R, Cc, dst);
+    return (int)cudaGetLastError();
+}
+
 // w5[(r*5+q)*96 + co] = sum_ci sum_{dy+a=r, dx+b=q} w_d[co][ci][dy][dx] * w_in[ci][a][b]
 // b5[co] = b_d[co] + sum_{ci,dy,dx} w_d[co][ci][dy][dx] * b_in[ci]
 __global__ void stem_compose_kernel(const float* w_in, const float* b_in, const float* w_d, const float* b_d, float* w5,

@@ -8,6 +8,8 @@ namespace dsb {
 int pack_weight_launch(const float* src, int N, int Cin, int taps, bf16* dst, cudaStream_t s);
 // depthwise: dst[tap*C + c] = src[c*src_stride + src_off + tap]
 int pack_dw_launch(const float* src, int C, int taps, int src_stride, int src_off, float* dst, cudaStream_t s);
+// src [R][Cc] -> dst [Cc][R]
+int transpose_launch(const float* src, int R, int Cc, float* dst, cudaStream_t s);
 // eval BatchNorm folded to y = conv*scale + shift; conv_bias may be null
 int bn_fold_launch(const float* w, const float* b, const float* mean, const float* var, const float* conv_bias, int C,
                    float eps, float* scale, float* shift, cudaStream_t s);

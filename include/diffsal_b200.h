@@ -122,6 +122,9 @@ int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, i
                   int act, float* out_f32, void* out_bf16, int out_fmul, int out_fadd, const float* head_w,
                   float head_b, float* out_head, void* stream);
 
+/* CTA-pair (cta_group::2) policy of dsb_test_conv: -1 never, 0 automatic, 1 always */
+void dsb_test_set_two_cta(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,3 +124,28 @@ def test_head_epilogue(L):
     ref = F.relu(F.conv2d(x.float(), w.float(), None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
     ref = torch.sigmoid((ref * hw[None, :, None, None]).sum(1) + 0.25)
     close(out, ref, 2e-3)
+
+
+@pytest.fixture
+def two_cta(L):
+    lib = L.lib()
+    lib.dsb_test_set_two_cta(1)
+    yield
+    lib.dsb_test_set_two_cta(0)
+
+
+@pytest.mark.parametrize("Fr,H,W,Cin,N,dil", [(2, 28, 48, 192, 384, 1), (3, 14, 24, 768, 384, 2), (1, 56, 96, 96, 192, 1),
+                                              (9, 56, 96, 96, 96, 2), (5, 7, 12, 768, 768, 1), (1, 28, 48, 384, 768, 1)])
+def test_conv3x3_cta_pairs(L, two_cta, Fr, H, W, Cin, N, dil):
+    """Same contraction through the cta_group::2 path (cluster of 2 CTAs, M = 256 MMA, B split across the pair),
+    including odd M-tile counts (the pair's second tile is a dummy)."""
+    test_conv3x3(L, Fr, H, W, Cin, N, dil)
+
+
+def test_linear_and_head_cta_pairs(L, two_cta):
+    test_linear(L, 1000, 192, 384, ACT_GELU, False)
+    test_linear(L, 777, 96, 96, ACT_NONE, True)
+    test_linear(L, 64 * 1024, 96, 192, ACT_NONE, False)
+    test_head_epilogue(L)
+    test_temporal_reduce(L, 3, 28, 48, 192)
+    test_conv3x3_stride2_into_frame_slot(L, 3, 28, 48, 192)
