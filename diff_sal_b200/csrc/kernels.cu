@@ -346,23 +346,48 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
     float g[NV], b[NV], q[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) { g[i] = ng[lane + 32 * i]; b[i] = nb[lane + 32 * i]; q[i] = 0.0f; }
+    if constexpr (NV >= 12) {
+    // wide rows (few tokens): issue the 9 statistics loads first, then the row loads of all in-image taps
+    float2 st[9];
+    bool ok[9];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xn = xx + k % 3 - 1;
+        ok[k] = (yy >= 0) && (yy < H) && (xn >= 0) && (xn < W);
+        st[k] = ok[k] ? stats[f * hw + (long)yy * W + xn] : make_float2(0.f, 0.f);
+    }
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xn = xx + dx;
-            if (xn < 0 || xn >= W) continue;
-            const long nt = f * hw + (long)yy * W + xn;
-            const float2 st = stats[nt];
-            const float* row = x + nt * C;
-            const float* wr = wq + ((dy + 1) * 3 + (dx + 1)) * C;
+    for (int k = 0; k < 9; ++k) {
+        if (!ok[k]) continue;
+        const int yy = y + k / 3 - 1, xn = xx + k % 3 - 1;
+        const float* row = x + (f * hw + (long)yy * W + xn) * C;
+        const float* wr = wq + k * C;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = lane + 32 * i;
-                const float xv = (row[c] - st.x) * st.y * g[i] + b[i];
-                q[i] = fmaf(wr[c], xv, q[i]);
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            const float xv = (row[c] - st[k].x) * st[k].y * g[i] + b[i];
+            q[i] = fmaf(wr[c], xv, q[i]);
+        }
+    }
+    } else {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xn = xx + dx;
+                if (xn < 0 || xn >= W) continue;
+                const long nt = f * hw + (long)yy * W + xn;
+                const float2 st = stats[nt];
+                const float* row = x + nt * C;
+                const float* wr = wq + ((dy + 1) * 3 + (dx + 1)) * C;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int c = lane + 32 * i;
+                    const float xv = (row[c] - st.x) * st.y * g[i] + b[i];
+                    q[i] = fmaf(wr[c], xv, q[i]);
+                }
             }
         }
     }
@@ -483,12 +508,16 @@ __global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ 
     for (int e = threadIdx.x; e < W * 32; e += 256) {
         const int c = e & 31, xx = e >> 5;
         float acc = 0.0f;
-        for (int t = 0; t < T; ++t) {
-            const size_t fr = (size_t)b * T + t;
-            const float xv = x[((fr * H + y) * W + xx) * C + c0 + c];
-            const float av = a_low[((fr * 7 + y / r) * 12 + xx / r) * C + c0 + c];
-            acc = fmaf(av, xv, acc);
+        const float* xp = x + ((((size_t)b * T) * H + y) * W + xx) * C + c0 + c;
+        const float* ap = a_low + ((((size_t)b * T) * 7 + y / r) * 12 + xx / r) * C + c0 + c;
+        const size_t xs = (size_t)H * W * C, as = (size_t)84 * C;
+        int t = 0;
+        for (; t + 3 <= T; t += 3) {                       // 6 independent loads in flight
+            const float x0 = xp[(size_t)t * xs], x1 = xp[(size_t)(t + 1) * xs], x2 = xp[(size_t)(t + 2) * xs];
+            const float a0 = ap[(size_t)t * as], a1 = ap[(size_t)(t + 1) * as], a2 = ap[(size_t)(t + 2) * as];
+            acc = fmaf(a0, x0, acc); acc = fmaf(a1, x1, acc); acc = fmaf(a2, x2, acc);
         }
+        for (; t < T; ++t) acc = fmaf(ap[(size_t)t * as], xp[(size_t)t * xs], acc);
         m[xx * 33 + c] = acc * invT;
     }
     __syncthreads();
