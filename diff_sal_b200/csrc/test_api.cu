@@ -35,3 +35,79 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     if (r) return r;
     return conv_run(l, num_sms_cached(), (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// single-kernel entries for the memory-bound kernels (all buffers are caller-owned device memory)
+#include "kernels.cuh"
+#include "weights.cuh"
+
+extern "C" int dsb_test_groupnorm_swish(const float* x, int F, int HW, int C, const float* gamma, const float* beta,
+                                        double* scratch /*[F*64*64]*/, void* out_act, void* out_raw, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = gn_stats_launch(x, F, HW, C, scratch, s)) return r;
+    return gn_apply_launch(x, F, HW, C, scratch, gamma, beta, (bf16*)out_act, (bf16*)out_raw, s);
+}
+
+extern "C" int dsb_test_layernorm(const float* x, long tokens, int C, const float* gamma, const float* beta, void* out,
+                                  int hw, int T, int tmax, void* stream) {
+    return ln_apply_launch(x, tokens, C, gamma, beta, (bf16*)out, hw, T, tmax, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_test_q_dwln(const float* x, int F, int H, int W, int C, const float* ng, const float* nb,
+                               const float* wq9, const float* qg, const float* qb, void* stats_scratch, void* out,
+                               int T, int tmax, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = ln_stats_launch(x, (long)F * H * W, C, (float2*)stats_scratch, H * W, T, tmax, s)) return r;
+    return q_dwln_launch(x, (const float2*)stats_scratch, F, H, W, C, ng, nb, wq9, qg, qb, (bf16*)out, T, tmax, s);
+}
+
+extern "C" int dsb_test_pool_ln(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
+                                const float* w, const float* g, const float* b, void* stats_scratch, void* out, int T,
+                                int tmax, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = ln_stats_launch(x, (long)F * H * W, C, (float2*)stats_scratch, H * W, T, tmax, s)) return r;
+    return pool_ln_launch(x, (const float2*)stats_scratch, F, H, W, C, sk, ng, nb, w, g, b, (bf16*)out, T, tmax, s);
+}
+
+extern "C" int dsb_test_av_key(const float* x, const float* a_low, int B, int T, int H, int W, int C, int sk,
+                               const float* wk, const float* kg, const float* kb, float* gate, void* out_k, int tmax,
+                               void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = av_gate_launch(x, a_low, B, T, H, W, C, gate, s)) return r;
+    return kpool_av_launch(gate, a_low, B, T, H, W, C, sk, wk, kg, kb, (bf16*)out_k, tmax, s);
+}
+
+extern "C" int dsb_test_upsample2x(const float* x, int F, int H, int W, int C, void* out, void* stream) {
+    return upsample2x_launch(x, F, H, W, C, (bf16*)out, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_test_ms_sum(const float* r0, const float* r1, const float* r2, const float* r3, int B, void* out,
+                               void* stream) {
+    const float* r[4] = {r0, r1, r2, r3};
+    return ms_sum_launch(r, B, (bf16*)out, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_test_final_up(const float* p, int B, float* out, void* stream) {
+    return final_up_launch(p, B, out, (cudaStream_t)stream);
+}
+
+extern "C" int dsb_test_stem(const float* x, int B, const float* w_in, const float* b_in, const float* w_d,
+                             const float* b_d, float* w5_scratch /*[2400]*/, float* b5_scratch /*[96]*/, float* h0,
+                             void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = stem_compose_launch(w_in, b_in, w_d, b_d, w5_scratch, b5_scratch, s)) return r;
+    return stem_launch(x, B, w5_scratch, b5_scratch, h0, s);
+}
+
+// weights are given TRANSPOSED ([in][out]) like the handle prepares them
+extern "C" int dsb_test_temb(const float* t, int B, const float* w0t, const float* b0, const float* w1t, const float* b1,
+                             const float* wp0t, const float* bp0, const float* wp1t, const float* bp1, const float* wp2t,
+                             const float* bp2, float* tp0, float* tp1, float* tp2, void* stream) {
+    TembWeights w;
+    w.w0 = w0t; w.b0 = b0; w.w1 = w1t; w.b1 = b1;
+    w.wp[0] = wp0t; w.wp[1] = wp1t; w.wp[2] = wp2t;
+    w.bp[0] = bp0; w.bp[1] = bp1; w.bp[2] = bp2;
+    w.cout[0] = 192; w.cout[1] = 384; w.cout[2] = 768;
+    float* tp[3] = {tp0, tp1, tp2};
+    return temb_launch(t, B, w, tp, (cudaStream_t)stream);
+}

@@ -122,6 +122,27 @@ int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, i
                   int act, float* out_f32, void* out_bf16, int out_fmul, int out_fadd, const float* head_w,
                   float head_b, float* out_head, void* stream);
 
+/* memory-bound kernels, one entry each (tests/test_kernels_gpu.py); all buffers are caller-owned device memory */
+int dsb_test_groupnorm_swish(const float* x, int F, int HW, int C, const float* gamma, const float* beta,
+                             double* scratch, void* out_act, void* out_raw, void* stream);
+int dsb_test_layernorm(const float* x, long tokens, int C, const float* gamma, const float* beta, void* out, int hw,
+                       int T, int tmax, void* stream);
+int dsb_test_q_dwln(const float* x, int F, int H, int W, int C, const float* ng, const float* nb, const float* wq9,
+                    const float* qg, const float* qb, void* stats_scratch, void* out, int T, int tmax, void* stream);
+int dsb_test_pool_ln(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
+                     const float* w, const float* g, const float* b, void* stats_scratch, void* out, int T, int tmax,
+                     void* stream);
+int dsb_test_av_key(const float* x, const float* a_low, int B, int T, int H, int W, int C, int sk, const float* wk,
+                    const float* kg, const float* kb, float* gate, void* out_k, int tmax, void* stream);
+int dsb_test_upsample2x(const float* x, int F, int H, int W, int C, void* out, void* stream);
+int dsb_test_ms_sum(const float* r0, const float* r1, const float* r2, const float* r3, int B, void* out, void* stream);
+int dsb_test_final_up(const float* p, int B, float* out, void* stream);
+int dsb_test_stem(const float* x, int B, const float* w_in, const float* b_in, const float* w_d, const float* b_d,
+                  float* w5_scratch, float* b5_scratch, float* h0, void* stream);
+int dsb_test_temb(const float* t, int B, const float* w0t, const float* b0, const float* w1t, const float* b1,
+                  const float* wp0t, const float* bp0, const float* wp1t, const float* bp1, const float* wp2t,
+                  const float* bp2, float* tp0, float* tp1, float* tp2, void* stream);
+
 /* CTA-pair (cta_group::2) policy of dsb_test_conv: -1 never, 0 automatic, 1 always */
 void dsb_test_set_two_cta(int mode);
 
