@@ -9,7 +9,8 @@
 
 namespace dsb {
 
-static constexpr int kEpiWarps = 8;            // two warps per TMEM lane quadrant, splitting the column chunks
+static constexpr int kEpiWarps = 12;           // kPerQuad warps per TMEM lane quadrant, splitting the column chunks
+static constexpr int kPerQuad = kEpiWarps / 4;
 static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 static constexpr int kMaxStages = 8;
 static constexpr uint32_t kAccStride = 256;   // TMEM columns between the two accumulator buffers
@@ -265,7 +266,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 }
             } else if (p.head_w) {
                 // fused 96 -> 1 head: each of the quadrant's two warps reduces its chunks, partials meet in smem
-                for (int c = half * 16; c < p.bn; c += 32) {
+                for (int c = half * 16; c < p.bn; c += 16 * kPerQuad) {
                     uint32_t raw[16];
                     tmem_ld16(t_addr + c, raw);
                     tmem_ld_wait();
@@ -284,7 +285,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             } else if (!p.epi_transposed) {
                 // direct epilogue: thread = one output row, 16-column chunks; the residual of a chunk is requested
                 // before the TMEM load so that its DRAM latency overlaps the tcgen05.ld round trip
-                for (int c = half * 16; c < p.bn; c += 32) {
+                for (int c = half * 16; c < p.bn; c += 16 * kPerQuad) {
                     const int n = n0 + c;
                     float4 res[4];
                     if (p.residual && valid) {
@@ -351,7 +352,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             } else {
                 // general epilogue: 32-column chunks are transposed through shared memory so that one warp
                 // instruction touches whole 128-byte rows (coalesced residual loads and output stores)
-                float* tile = epi_base + 128 + (warp - 2) * (32 * 36 + 96);
+                float* tile = epi_base + 128 * kPerQuad + (warp - 2) * (32 * 36 + 96);
                 int* rowtab = reinterpret_cast<int*>(tile + 32 * 36);      // [32][3]: pix_out, pix_in, frame (or -1)
                 __syncwarp();
                 rowtab[lane * 3 + 0] = valid ? (int)pix_out : -1;
@@ -359,7 +360,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 rowtab[lane * 3 + 2] = fs;
                 const int cq = (lane & 7) * 4;                             // this lane's 4 columns inside the chunk
                 const int rq = lane >> 3;                                  // row offset inside a group of 4 rows
-                for (int c = half * 32; c < p.bn; c += 64) {
+                for (int c = half * 32; c < p.bn; c += 32 * kPerQuad) {
                     uint32_t raw[32];
                     tmem_ld32(t_addr + c, raw);
                     tmem_ld_wait();
@@ -403,10 +404,14 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             }
             if (p.head_w) {
                 float* hp = epi_base + q * 32 + lane;                           // [4 quadrants][32 rows]
-                if (half == 1) *hp = head;
-                asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 epilogue warps only
-                if (half == 0 && valid) p.out_head[pix_out] = 1.0f / (1.0f + __expf(-(head + *hp + p.head_b)));
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half > 0) hp[(half - 1) * 128] = head;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // the epilogue warps only
+                if (half == 0 && valid) {
+#pragma unroll
+                    for (int k = 1; k < kPerQuad; ++k) head += hp[(k - 1) * 128];
+                    p.out_head[pix_out] = 1.0f / (1.0f + __expf(-(head + p.head_b)));
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             }
             tc_fence_before();
             if constexpr (two) mbar_arrive_leader(&bars->tmem_empty[acc]); else mbar_arrive(&bars->tmem_empty[acc]);
@@ -489,8 +494,8 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.two_cta && (p.b_rows_per_frame || p.out_softmax || (p.bn / 2) % 8)) return -20;
     if (p.ksub < 1 || (p.taps * p.cin_blocks) % p.ksub) return -21;
     const uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
-    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? 8 * (32 * 36 + 96) : 0) + 128 + 8 * (32 * 36 + 96) * 0) * sizeof(float);
-    const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes - 8u * (32 * 36 + 96) * 0u;
+    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 96) : 0) + 128 * kPerQuad) * sizeof(float);
+    const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -15;

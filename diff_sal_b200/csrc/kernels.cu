@@ -749,6 +749,45 @@ int axpy_launch(int nin, const float* const in[4], const float c[4], const float
     DSB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------ post-processing
+// inverse_data_transform (clamp to [0,1], datasets/__init__.py:35) followed by normalize_data (per-map min-max to
+// uint8, util/utils.py:11-16): one block per clip, two passes over its 86 016 pixels.
+__global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restrict__ x, int n, float* __restrict__ clamped,
+                                                          uint8_t* __restrict__ u8) {
+    __shared__ float red[32];
+    __shared__ float smin, smax;
+    const float* xb = x + (size_t)blockIdx.x * n;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = fminf(fmaxf(xb[i], 0.0f), 1.0f);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    mn = -warp_max(-mn);
+    if (lane == 0) red[wid] = mn;
+    __syncthreads();
+    if (wid == 0) { float t = lane < (blockDim.x >> 5) ? red[lane] : INFINITY; t = -warp_max(-t); if (lane == 0) smin = t; }
+    __syncthreads();
+    mx = warp_max(mx);
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    if (wid == 0) { float t = lane < (blockDim.x >> 5) ? red[lane] : -INFINITY; t = warp_max(t); if (lane == 0) smax = t; }
+    __syncthreads();
+    const float lo = smin;
+    const float scale = 255.0f / (smax - lo);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = fminf(fmaxf(xb[i], 0.0f), 1.0f);
+        if (clamped) clamped[(size_t)blockIdx.x * n + i] = v;
+        if (u8) u8[(size_t)blockIdx.x * n + i] = (uint8_t)fminf(fmaxf((v - lo) * scale, 0.0f), 255.0f);
+    }
+}
+
+int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s) {
+    postprocess_kernel<<<B, 1024, 0, s>>>(x, n, clamped, u8);
+    DSB_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------ layout conversion
 // [B][C][Tv][HW] -> [(b*T+t)][HW][C] through a 32x32 smem transpose (coalesced on both sides)
 __global__ void __launch_bounds__(256) nct_to_frames_kernel(const float* __restrict__ vis, int C, int Tv, int HW, int T,

@@ -66,6 +66,10 @@ int final_up_launch(const float* p, int B, float* out, cudaStream_t s);
 int axpy_launch(int nin, const float* const in[4], const float c[4], const float* noise, float cn, float* out, long n,
                 cudaStream_t s);
 
+// clamp(x, 0, 1) (inverse_data_transform, datasets/__init__.py:26-35) and per-map min-max -> uint8 (normalize_data,
+// util/utils.py:11-16); either output may be null.  n = pixels per map.
+int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s);
+
 // vis[B][C][Tv][HW] fp32 -> frames[(b*T + t)][HW][C] for t < Tv  (T = frames per clip in dst)
 int nct_to_frames_launch(const float* vis, int B, int C, int Tv, int HW, int T, float* dst, cudaStream_t s);
 // audio[B][512][T][84] fp32 -> tokens[(b*T+t)*84 + p][512] bf16

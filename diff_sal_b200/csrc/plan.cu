@@ -92,6 +92,13 @@ struct dsb_handle {
     std::vector<std::string> prog_name;           // per launch: label
     std::vector<double> prog_flops;               // per launch: algorithmic FLOPs (0 for memory-bound kernels)
     std::vector<double> prog_bytes;               // per launch: algorithmic bytes (memory-bound kernels; 0 if not stated)
+    // Independent branches of an evaluation (the q / k / v token producers of a block) run on side streams:
+    // kind 0 = launch on stream prog_stream[i]; 1 = record event prog_ev[i] on that stream; 2 = that stream waits for it
+    std::vector<int> prog_kind, prog_stream, prog_ev;
+    int prog_launches = 0;
+    std::vector<int> profile_idx;
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
     int64_t cond_launches = 0;
     const float* cur_x = nullptr;
     const float* cur_t = nullptr;
@@ -256,12 +263,33 @@ struct Builder {
     std::vector<Launch>* out;
     int err = 0;
 
+    int cur = 0;                                  // stream index subsequent launches go to (0 = caller's stream)
+
+    void meta(int kind, int ev) {
+        h->prog_kind.push_back(kind);
+        h->prog_stream.push_back(cur);
+        h->prog_ev.push_back(ev);
+        if (kind == 0) h->prog_launches++;
+    }
     void add(Launch l, const char* name = "misc", double bytes = 0.0) {
         out->push_back(std::move(l));
         h->prog_name.push_back(name);
         h->prog_flops.push_back(0.0);
         h->prog_bytes.push_back(bytes);
+        meta(0, -1);
     }
+    void sync_op(int kind, int ev, int stream) {
+        const int keep = cur;
+        cur = stream;
+        out->push_back(Launch());
+        h->prog_name.push_back(kind == 1 ? "record" : "wait");
+        h->prog_flops.push_back(0.0);
+        h->prog_bytes.push_back(0.0);
+        meta(kind, ev);
+        cur = keep;
+    }
+    // event `ev` marks "everything enqueued so far on `from`"; stream `to` will not run past it
+    void depend(int ev, int from, int to) { sync_op(1, ev, from); sync_op(2, ev, to); }
 
     // algo_flops < 0: 2*M*N*K of the lowered GEMM (M = valid output pixels)
     void conv(ConvOp op, const char* name, double algo_flops = -1.0) {
@@ -275,6 +303,7 @@ struct Builder {
         const double m = (double)op.F * op.H * op.W;
         h->prog_flops.push_back(algo_flops >= 0 ? algo_flops : 2.0 * m * op.N * (double)cl.p.taps * op.Cin);
         h->prog_bytes.push_back(0.0);
+        meta(0, -1);
     }
 };
 
@@ -291,6 +320,10 @@ int build_program(dsb_handle* h) {
     h->prog_name.clear();
     h->prog_flops.clear();
     h->prog_bytes.clear();
+    h->prog_kind.clear();
+    h->prog_stream.clear();
+    h->prog_ev.clear();
+    h->prog_launches = 0;
     Builder b{h, &h->prog};
     const int B = h->B, F = B * kT;
     auto WP = [&](const std::string& k) -> const bf16* {
@@ -409,7 +442,11 @@ int build_program(dsb_handle* h) {
             return op;
         };
         float2* stats = h->lnstats;
+        // three independent producers read the stage input: K (audio gate -> scramble -> pool, side stream 2),
+        // V (side stream 1) and Q (caller's stream); they rejoin before the attention operands are built
+        b.depend(0, 0, 2);                                  // Xi is complete -> K branch may start
         b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, HW, kT, tmax, s); }, "ln_stats", (double)tokens * C * 4.0 * live);
+        b.depend(1, 0, 1);                                  // LayerNorm statistics ready -> V branch may start
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
         bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
         const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
@@ -417,6 +454,8 @@ int build_program(dsb_handle* h) {
         const float *qg = W(h, bk + "attn.conv_proj_q.bn.weight"), *qb = W(h, bk + "attn.conv_proj_q.bn.bias");
         const float *kg = W(h, bk + "attn.conv_proj_k.bn.weight"), *kb = W(h, bk + "attn.conv_proj_k.bn.bias");
         const float *vg = W(h, bk + "attn.conv_proj_v.bn.weight"), *vb = W(h, bk + "attn.conv_proj_v.bn.bias");
+        b.cur = 2;
+        if (!h->has_audio) b.depend(1, 0, 2);               // visual-only K also needs the statistics
         if (h->has_audio) {
             const float* al = h->a_low[i];
             float* gate = h->gate;
@@ -425,24 +464,28 @@ int build_program(dsb_handle* h) {
         } else {
             b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
         }
-        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
+            op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
+            b.conv(op, "attn.proj_k");
+        }
+        b.cur = 1;
         b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, kT, tmax, s); }, "pool_ln_v", (double)tokens * C * 4.0 * live);
+        {
+            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
+            op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
+            b.conv(op, "attn.proj_v");
+        }
+        b.cur = 0;
+        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
         // algorithmic FLOPs are always the reference's (all 9 frames), also where dead frames are skipped
         {
             ConvOp op = token_op(C, C, q_ln, WP(bk + "attn.proj_q.weight"));
             op.shift = W(h, bk + "attn.proj_q.bias"); op.out_bf16 = h->Qp;
             b.conv(op, "attn.proj_q", 2.0 * (double)tokens * C * C);
         }
-        {
-            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
-            op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
-            b.conv(op, "attn.proj_k");
-        }
-        {
-            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
-            op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
-            b.conv(op, "attn.proj_v");
-        }
+        b.depend(2, 1, 0);                                  // join V
+        b.depend(3, 2, 0);                                  // join K
         {
             const float *Kp = h->Kp, *Vp = h->Vp;
             bf16 *KB = h->KB, *VB = h->VB;
@@ -516,13 +559,19 @@ int build_program(dsb_handle* h) {
     return b.err;
 }
 
-int run_program(dsb_handle* h, cudaStream_t s) {
+int run_program(dsb_handle* h, cudaStream_t s, bool serial = false) {
     for (size_t i = 0; i < h->prog.size(); ++i) {
-        int r = h->prog[i](s);
-        if (r) return fail(h, DSB_ERR_CUDA, "denoiser launch %zu failed: %s (%d)", i,
+        const int kind = h->prog_kind[i], si = h->prog_stream[i];
+        cudaStream_t st = (serial || si == 0) ? s : h->side[si - 1];
+        int r = 0;
+        if (kind == 0) r = h->prog[i](st);
+        else if (serial) continue;
+        else if (kind == 1) r = (int)cudaEventRecord(h->ev[h->prog_ev[i]], st);
+        else r = (int)cudaStreamWaitEvent(st, h->ev[h->prog_ev[i]], 0);
+        if (r) return fail(h, DSB_ERR_CUDA, "denoiser step %zu (%s) failed: %s (%d)", i, h->prog_name[i].c_str(),
                            r > 0 ? cudaGetErrorString((cudaError_t)r) : "launcher error", r);
     }
-    h->last_launches += (int64_t)h->prog.size();
+    h->last_launches += (int64_t)h->prog_launches;
     return 0;
 }
 
@@ -545,6 +594,10 @@ extern "C" int dsb_create(const dsb_config* cfg, dsb_handle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (gemm_init()) { delete h; return DSB_ERR_CUDA; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
     *out = h;
     return DSB_OK;
 }
@@ -554,6 +607,10 @@ extern "C" void dsb_destroy(dsb_handle* h) {
     for (auto& g : h->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i)
+        if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    for (int i = 0; i < 8; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
 }
 
@@ -810,7 +867,7 @@ extern "C" int dsb_sample(dsb_handle* h, const dsb_sampler_desc* d, float* x_ino
             // launches counted as if enqueued individually
             int evals = 0, axpys = 0;
             for (int i = 0; i < d->n_ops; ++i) (d->ops[i].kind == DSB_OP_EVAL ? evals : axpys)++;
-            h->last_launches = (int64_t)evals * (int64_t)h->prog.size() + axpys;
+            h->last_launches = (int64_t)evals * (int64_t)h->prog_launches + axpys;
         }
         CUDA_TRY(h, cudaGraphLaunch(it->second.exec, s));
     } else {
@@ -819,6 +876,12 @@ extern "C" int dsb_sample(dsb_handle* h, const dsb_sampler_desc* d, float* x_ino
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_inout, h->sbuf[0], bytes, cudaMemcpyDeviceToDevice, s));
     return DSB_OK;
+}
+
+extern "C" int dsb_postprocess(const float* x, int B, int64_t pixels_per_map, float* clamped_or_null,
+                               uint8_t* u8_or_null, void* stream) {
+    if (!x || B < 1 || pixels_per_map < 1 || (!clamped_or_null && !u8_or_null)) return DSB_ERR_ARG;
+    return postprocess_launch(x, B, (int)pixels_per_map, clamped_or_null, u8_or_null, (cudaStream_t)stream) ? DSB_ERR_CUDA : DSB_OK;
 }
 
 extern "C" int64_t dsb_last_launch_count(const dsb_handle* h) { return h ? h->last_launches : 0; }
@@ -851,32 +914,36 @@ extern "C" int dsb_profile_denoise(dsb_handle* h, const float* x, const float* t
     if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_profile_denoise before dsb_set_condition");
     if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
     cudaStream_t s = (cudaStream_t)stream;
-    const int n = (int)h->prog.size();
+    std::vector<int> idx;
+    for (size_t i = 0; i < h->prog.size(); ++i)
+        if (h->prog_kind[i] == 0) idx.push_back((int)i);
+    const int n = (int)idx.size();
     if (cap < n) return fail(h, DSB_ERR_ARG, "profile buffers too small (%d < %d)", cap, n);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
     h->cur_x = x; h->cur_t = t; h->cur_out = out;
     int rc = 0;
-    for (int i = 0; i < n && !rc; ++i) {
-        cudaEventRecord(ev[i], s);
-        int r = h->prog[i](s);
-        if (r) rc = fail(h, DSB_ERR_CUDA, "launch %d (%s) failed: %d", i, h->prog_name[i].c_str(), r);
+    for (int k = 0; k < n && !rc; ++k) {          // everything serialised on `s`: per-launch times are exclusive
+        cudaEventRecord(ev[k], s);
+        int r = h->prog[idx[k]](s);
+        if (r) rc = fail(h, DSB_ERR_CUDA, "launch %d (%s) failed: %d", k, h->prog_name[idx[k]].c_str(), r);
     }
     cudaEventRecord(ev[n], s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (!rc && e != cudaSuccess) rc = fail(h, DSB_ERR_CUDA, "profile sync: %s", cudaGetErrorString(e));
-    for (int i = 0; i < n && !rc; ++i) {
-        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
-        flops[i] = h->prog_flops[i];
-        bytes[i] = h->prog_bytes[i];
+    for (int k = 0; k < n && !rc; ++k) {
+        cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        flops[k] = h->prog_flops[idx[k]];
+        bytes[k] = h->prog_bytes[idx[k]];
     }
     for (auto& e2 : ev) cudaEventDestroy(e2);
+    h->profile_idx = idx;
     return rc ? rc : n;
 }
 
 extern "C" const char* dsb_profile_name(const dsb_handle* h, int i) {
-    if (!h || i < 0 || i >= (int)h->prog_name.size()) return "";
-    return h->prog_name[i].c_str();
+    if (!h || i < 0 || i >= (int)h->profile_idx.size()) return "";
+    return h->prog_name[h->profile_idx[i]].c_str();
 }
 
 extern "C" int64_t dsb_condition_launch_count(const dsb_handle* h) { return h ? h->cond_launches : 0; }

@@ -499,6 +499,44 @@ class DiffusionSampler:
         raise NotImplementedError(st)
 
 
+# ============================================================================================ output side
+
+
+def _postprocess(x, want_u8):
+    import ctypes
+    from . import _lib
+    from .engine import _bind, _stream
+    if not x.is_cuda:
+        raise RuntimeError("diff_sal_b200 post-processing runs on the GPU only")
+    lib = _bind(_lib.lib())
+    lib.dsb_postprocess.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    x = x.to(dtype=torch.float32).contiguous()
+    B = x.shape[0]
+    n = x.numel() // B
+    clamped = torch.empty_like(x)
+    u8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
+    with torch.cuda.device(x.device):
+        rc = lib.dsb_postprocess(_lib.ptr(x), B, n, _lib.ptr(clamped), _lib.ptr(u8), _stream())
+    if rc != 0:
+        raise RuntimeError("dsb_postprocess failed (%d)" % rc)
+    return clamped, u8
+
+
+def inverse_data_transform(config, X):
+    """datasets/__init__.py:26-35 for the shipped data config (no image_mean, no logit transform, not rescaled,
+    cfgs/diffusion.yml:1-8): clamp to [0, 1].  Other data configs are outside the hot path and raise."""
+    d = getattr(config, "data", None)
+    if hasattr(config, "image_mean") or (d is not None and (getattr(d, "logit_transform", False) or getattr(d, "rescaled", False))):
+        raise NotImplementedError("only the shipped data config (no mean / logit / rescale) is on the hot path")
+    return _postprocess(X, False)[0]
+
+
+def normalize_data(maps):
+    """util/utils.py:11-16 per map: (x - min) * 255 / (max - min) clipped to [0, 255] as uint8 (of the clamped map,
+    which is what DiffusionTrainer.save_img feeds it, diffusion_trainer.py:898-935).  maps: [B,1,H,W] CUDA tensor."""
+    return _postprocess(maps, True)[1]
+
+
 # ============================================================================================ util/denoising.py
 
 

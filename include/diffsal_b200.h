@@ -98,6 +98,12 @@ typedef struct dsb_sampler_desc {
 
 int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int B, void* stream);
 
+/* output side of the loop: clamp(x,0,1) = inverse_data_transform (datasets/__init__.py:26-35, cfgs/diffusion.yml data.*)
+ * and the per-map min-max -> uint8 of normalize_data (util/utils.py:11-16).  x: device fp32 [B][pixels_per_map];
+ * either output may be NULL. */
+int dsb_postprocess(const float* x, int B, int64_t pixels_per_map, float* clamped_or_null, uint8_t* u8_or_null,
+                    void* stream);
+
 /* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
 int64_t dsb_last_launch_count(const dsb_handle* h);
 

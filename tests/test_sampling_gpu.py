@@ -159,3 +159,20 @@ def test_metrics_within_half_percent(nets):
     for k in a:
         assert abs(b[k]) > 0.1
         assert abs(a[k] - b[k]) <= 5e-3 * abs(b[k]), (k, a[k], b[k])
+
+
+def test_output_postprocessing_matches_reference_formulas():
+    """inverse_data_transform (clamp) and normalize_data (min-max -> uint8) on the GPU vs the numpy formulas of
+    datasets/__init__.py:35 and util/utils.py:11-16."""
+    from diff_sal_b200 import sampler as S
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(3, 1, 224, 384, generator=g) * 1.4 - 0.2).cuda()
+    cfg = types.SimpleNamespace(data=types.SimpleNamespace(logit_transform=False, rescaled=False))
+    c = S.inverse_data_transform(cfg, x)
+    assert torch.equal(c, torch.clamp(x, 0.0, 1.0))
+    u8 = S.normalize_data(x).cpu().numpy()
+    for i in range(3):
+        d = torch.clamp(x[i], 0.0, 1.0).cpu().numpy()
+        ref = np.clip((d - d.min()) * (255.0 / (d.max() - d.min())), 0, 255).astype(np.uint8)
+        diff = np.abs(u8[i].astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
