@@ -1,0 +1,342 @@
+// Fused transformer MLP for the narrow stages (C = 96, 192):
+//
+//     out[m, :] = x1[m, :] + W2 * gelu(W1 * ln2[m, :] + b1) + b2          (common_block.py:125-147, transformer.py:157)
+//
+// One CTA owns a tile of 128 tokens.  The hidden activation (2C wide) never leaves the SM: it is produced 64 columns at
+// a time into a TMEM accumulator, passed through bias + exact-erf GELU by the epilogue warps, written as a bf16 K-major
+// SWIZZLE_128B operand tile into shared memory and consumed by the second GEMM, whose accumulator (C columns) stays in
+// TMEM for the whole tile.  HBM traffic per token-channel drops from 24 B (ln2 read, hidden write + read, residual
+// read, output write, through two kernels) to 10 B.
+//
+//   warp 0     : TMA producer for the A tile (once per tile) and the W1 chunk ring;  warp 10: W2 chunk ring
+//   warp 1     : tcgen05.mma issuer (GEMM1 of chunk h+1 is issued before GEMM2 of chunk h)
+//   warps 2..9 : epilogue (stage 1: TMEM -> GELU -> smem operand;  stage 2: TMEM + bias + residual -> global)
+#include "mlp_fused.cuh"
+
+#include <string.h>
+
+namespace dsb {
+
+static constexpr int kMlpThreads = 480;           // warps: 0 A+W1 producer, 1 MMA, 2..9 GELU stage, 10..13 output stage, 14 W2 producer
+static constexpr int kHC = 64;                    // hidden columns per chunk
+static constexpr uint32_t kAcc2Col = 128;         // TMEM column of the second accumulator (acc1 buffers at 0 and 64)
+
+struct __align__(16) MlpBarriers {
+    uint64_t a_full, a_empty;
+    uint64_t w1_full[4], w1_empty[4];     // W1 chunk ring (freed as soon as GEMM1 of the chunk has read it)
+    uint64_t w2_full[4], w2_empty[4];     // W2 chunk ring (freed after GEMM2 of the chunk)
+    uint64_t acc1_full[2], acc1_empty[2];
+    uint64_t a2_full[2], a2_empty[2];
+    uint64_t acc2_full[2], acc2_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const int NS) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int C = p.C, bk = p.bk;
+    const int ksub = C / bk;                       // K sub-blocks of GEMM1
+    const int NC = 2 * C / kHC;                    // hidden chunks per tile
+    const uint32_t a_sub = 128u * bk * 2u;
+    const uint32_t a_bytes = a_sub * ksub;
+    const uint32_t w1_sub = (uint32_t)kHC * bk * 2u;
+    const uint32_t w1_bytes = w1_sub * ksub;
+    const uint32_t w2_bytes = (uint32_t)C * kHC * 2u;
+    const uint32_t a2_bytes = 128u * kHC * 2u;
+    uint8_t* sA = smem;
+    uint8_t* sA2 = sA + a_bytes;
+    uint8_t* sW1 = sA2 + 2 * a2_bytes;
+    uint8_t* sW2 = sW1 + (size_t)NS * w1_bytes;
+    MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(sW2 + (size_t)NS * w2_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW1);
+        tma_prefetch_desc(&tmW2);
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars->w1_full[i], 1);
+            mbar_init(&bars->w1_empty[i], 1);
+            mbar_init(&bars->w2_full[i], 1);
+            mbar_init(&bars->w2_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->acc1_full[i], 1);
+            mbar_init(&bars->acc1_empty[i], 8);       // one arrive per GELU-stage warp
+            mbar_init(&bars->a2_full[i], 8);
+            mbar_init(&bars->a2_empty[i], 1);
+            mbar_init(&bars->acc2_full[i], 1);
+            mbar_init(&bars->acc2_empty[i], 4);       // one arrive per output-stage warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const int tiles_per_frame = (p.HW + 127) >> 7;
+    const int total_tiles = tiles_per_frame * p.F;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        uint32_t g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int f = tile / tiles_per_frame;
+            const int x0 = (tile % tiles_per_frame) << 7;
+            const int fs = p.f_group ? (f / p.f_used) * p.f_group + f % p.f_used : f;
+            mbar_wait(&bars->a_empty, (it & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(&bars->a_full, a_bytes);
+                for (int j = 0; j < ksub; ++j) tma_load_3d(sA + j * a_sub, &tmA, &bars->a_full, j * bk, x0, fs);
+            }
+            __syncwarp();
+            for (int h = 0; h < NC; ++h, ++g) {
+                const uint32_t s = g % (uint32_t)NS, ph = (g / (uint32_t)NS) & 1u;
+                mbar_wait(&bars->w1_empty[s], ph ^ 1u);
+                if (elect_one()) {
+                    uint8_t* w = sW1 + s * w1_bytes;
+                    mbar_expect_tx(&bars->w1_full[s], w1_bytes);
+                    for (int j = 0; j < ksub; ++j) tma_load_2d(w + j * w1_sub, &tmW1, &bars->w1_full[s], j * bk, h * kHC);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 14) {
+        // ------------------------------------------------------------------ W2 producer (its ring drains later than W1's)
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int h = 0; h < NC; ++h, ++g) {
+                const uint32_t s = g % (uint32_t)NS, ph = (g / (uint32_t)NS) & 1u;
+                mbar_wait(&bars->w2_empty[s], ph ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(&bars->w2_full[s], w2_bytes);
+                    tma_load_2d(sW2 + s * w2_bytes, &tmW2, &bars->w2_full[s], h * kHC, 0);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc1 = umma_idesc_bf16(kHC);
+        const uint32_t idesc2 = umma_idesc_bf16((uint32_t)C);
+        const uint32_t rb1 = (uint32_t)bk * 2u;
+        const uint64_t dA = umma_smem_desc(smem_u32(sA), rb1);
+        const uint64_t dW1 = umma_smem_desc(smem_u32(sW1), rb1);
+        const uint64_t dW2 = umma_smem_desc(smem_u32(sW2), 128u);
+        const uint64_t dA2 = umma_smem_desc(smem_u32(sA2), 128u);
+        const int k1 = bk / 16;
+        uint32_t gbase = 0, it = 0;
+
+        auto issue_g1 = [&](int h) {
+            const uint32_t gg = gbase + (uint32_t)h, s = gg & 1u, ph = (gg >> 1) & 1u;
+            const uint32_t ws = gg % (uint32_t)NS, wph = (gg / (uint32_t)NS) & 1u;
+            mbar_wait(&bars->w1_full[ws], wph);
+            if (h == 0) mbar_wait(&bars->a_full, it & 1u);
+            mbar_wait(&bars->acc1_empty[s], ph ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + s * kHC;
+                for (int j = 0; j < ksub; ++j) {
+                    const uint64_t da = dA + (uint64_t)((j * a_sub) >> 4);
+                    const uint64_t dw = dW1 + (uint64_t)((ws * w1_bytes + j * w1_sub) >> 4);
+                    for (int k = 0; k < k1; ++k) umma_bf16(d, da + 2 * k, dw + 2 * k, idesc1, (j | k) ? 1u : 0u);
+                }
+                umma_commit(&bars->w1_empty[ws]);
+                umma_commit(&bars->acc1_full[s]);
+                if (h == NC - 1) umma_commit(&bars->a_empty);      // the A tile is free once every GEMM1 has read it
+            }
+            __syncwarp();
+        };
+
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            issue_g1(0);
+            for (int h = 0; h < NC; ++h) {
+                if (h + 1 < NC) issue_g1(h + 1);
+                const uint32_t gg = gbase + (uint32_t)h, s = gg & 1u, ph = (gg >> 1) & 1u;
+                const uint32_t ws = gg % (uint32_t)NS, wph = (gg / (uint32_t)NS) & 1u;
+                const uint32_t ab = it & 1u;                               // acc2 buffer of this tile
+                if (h == 0) mbar_wait(&bars->acc2_empty[ab], ((it >> 1) & 1u) ^ 1u);
+                mbar_wait(&bars->w2_full[ws], wph);
+                mbar_wait(&bars->a2_full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + kAcc2Col + ab * (uint32_t)C;
+                    const uint64_t da = dA2 + (uint64_t)((s * a2_bytes) >> 4);
+                    const uint64_t dw = dW2 + (uint64_t)((ws * w2_bytes) >> 4);
+#pragma unroll
+                    for (int k = 0; k < kHC / 16; ++k) umma_bf16(d, da + 2 * k, dw + 2 * k, idesc2, (h | k) ? 1u : 0u);
+                    umma_commit(&bars->w2_empty[ws]);
+                    umma_commit(&bars->a2_empty[s]);
+                    if (h == NC - 1) umma_commit(&bars->acc2_full[ab]);
+                }
+                __syncwarp();
+            }
+            gbase += (uint32_t)NC;
+        }
+    } else if (warp < 10) {
+        // ------------------------------------------------------------------ GELU stage (warps 2..9)
+        // hidden chunk: TMEM -> + b1 -> exact-erf GELU -> bf16 -> K-major SWIZZLE_128B operand tile of GEMM2
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t gg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int h = 0; h < NC; ++h, ++gg) {
+                const uint32_t s = gg & 1u, ph = (gg >> 1) & 1u;
+                mbar_wait(&bars->acc1_full[s], ph);
+                tc_fence_after();
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + lane_addr + s * kHC + half * 32, raw);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc1_empty[s]);
+                const float* b1 = p.b1 + h * kHC + half * 32;
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v0 = gelu_erf(__uint_as_float(raw[2 * j]) + __ldg(b1 + 2 * j));
+                    const float v1 = gelu_erf(__uint_as_float(raw[2 * j + 1]) + __ldg(b1 + 2 * j + 1));
+                    packed[j] = pack_bf16x2(v0, v1);
+                }
+                mbar_wait(&bars->a2_empty[s], ph ^ 1u);
+                uint8_t* dst = sA2 + s * a2_bytes + row * 128;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int piece = half * 4 + jj;                      // 16-byte piece inside the 128-byte row
+                    *reinterpret_cast<uint4*>(dst + ((piece ^ (row & 7)) << 4)) =
+                        make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a2_full[s]);
+            }
+        }
+    } else if (warp < 14) {
+        // ------------------------------------------------------------------ output stage (warps 10..13)
+        // out = acc2 + b2 + residual, overlapped with the GELU stage of the next tile (acc2 is double-buffered);
+        // the residual of chunk c+1 is requested before chunk c is processed
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int nch = C / 32;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int f = tile / tiles_per_frame;
+            const int x = ((tile % tiles_per_frame) << 7) + row;
+            const int fs = p.f_group ? (f / p.f_used) * p.f_group + f % p.f_used : f;
+            const bool valid = x < p.HW;
+            const size_t tok = (size_t)fs * p.HW + x;
+            const uint32_t ab = it & 1u;
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + tok * C);
+            float4* op = reinterpret_cast<float4*>(p.out + tok * C);
+            float4 res[2][8];
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) res[0][j] = rp[j];
+            }
+            mbar_wait(&bars->acc2_full[ab], (it >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < nch; cc += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c = cc + u;
+                    if (c >= nch) break;
+                    if (valid && c + 1 < nch) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) res[(u + 1) & 1][j] = rp[(c + 1) * 8 + j];
+                    }
+                    uint32_t raw[32];
+                    tmem_ld32(tmem_base + lane_addr + kAcc2Col + ab * (uint32_t)C + c * 32, raw);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + j);
+                            op[c * 8 + j] = make_float4(__uint_as_float(raw[4 * j]) + b.x + res[u][j].x,
+                                                        __uint_as_float(raw[4 * j + 1]) + b.y + res[u][j].y,
+                                                        __uint_as_float(raw[4 * j + 2]) + b.z + res[u][j].z,
+                                                        __uint_as_float(raw[4 * j + 3]) + b.w + res[u][j].w);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc2_empty[ab]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int mlp_fused_lower(const MlpOp& op, MlpLaunch* out) {
+    memset(out, 0, sizeof(*out));
+    const int C = op.C;
+    if (C != 96 && C != 192) return -40;
+    MlpParams& p = out->p;
+    p.C = C;
+    p.bk = (C % 64 == 0) ? 64 : 32;
+    p.HW = op.HW; p.F = op.F; p.f_group = op.f_group; p.f_used = op.f_used;
+    p.b1 = op.b1; p.b2 = op.b2; p.residual = op.residual; p.out = op.out;
+    const uint64_t e = 2;
+    const int src_frames = op.f_group ? ((op.F + op.f_used - 1) / op.f_used) * op.f_group : op.F;
+    {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)op.HW, (uint64_t)src_frames};
+        uint64_t str[2] = {C * e, (uint64_t)op.HW * C * e};
+        uint32_t box[3] = {(uint32_t)p.bk, 128u, 1u};
+        if (int r = make_tensor_map(&out->tmA, op.A, 3, dims, str, box)) return r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)C, (uint64_t)(2 * C)};
+        uint64_t str[1] = {C * e};
+        uint32_t box[2] = {(uint32_t)p.bk, (uint32_t)kHC};
+        if (int r = make_tensor_map(&out->tmW1, op.W1, 2, dims, str, box)) return r;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)C};
+        uint64_t str[1] = {2 * C * e};
+        uint32_t box[2] = {(uint32_t)kHC, (uint32_t)C};
+        if (int r = make_tensor_map(&out->tmW2, op.W2, 2, dims, str, box)) return r;
+    }
+    return 0;
+}
+
+int mlp_fused_run(const MlpLaunch& l, int num_sms, cudaStream_t stream) {
+    const MlpParams& p = l.p;
+    const int ksub = p.C / p.bk;
+    const size_t a_bytes = (size_t)128 * p.bk * 2 * ksub;
+    const size_t w_stage = (size_t)kHC * p.bk * 2 * ksub + (size_t)p.C * kHC * 2;
+    const size_t fixed = a_bytes + 2 * (128 * kHC * 2) + sizeof(MlpBarriers) + 1024;
+    int NS = (int)((230000 - fixed) / w_stage);
+    if (NS > 4) NS = 4;
+    if (NS < 2) return -42;
+    const size_t smem = fixed + (size_t)NS * w_stage;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const int tiles = ((p.HW + 127) / 128) * p.F;
+    int grid = tiles < num_sms ? tiles : num_sms;
+    if (grid < 1) return -41;
+    mlp_fused_kernel<<<grid, kMlpThreads, smem, stream>>>(p, l.tmA, l.tmW1, l.tmW2, NS);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dsb

@@ -16,6 +16,7 @@
 
 #include "conv_plan.cuh"
 #include "kernels.cuh"
+#include "mlp_fused.cuh"
 #include "weights.cuh"
 
 using namespace dsb;
@@ -515,15 +516,31 @@ int build_program(dsb_handle* h) {
             bf16* ln2 = h->ln2;
             b.add([=](cudaStream_t s) { return ln_apply_launch(x1, tokens, C, g2, b2, ln2, HW, kT, tmax, s); }, "ln_apply", (double)tokens * C * 6.0 * live);
         }
-        {
-            ConvOp op = token_op(C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
-            op.shift = W(h, bk + "mlp.fc1.bias"); op.act = ACT_GELU; op.out_bf16 = h->hid;
-            b.conv(op, "mlp.fc1", 4.0 * (double)tokens * C * C);
-        }
-        {
-            ConvOp op = token_op(2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
-            op.shift = W(h, bk + "mlp.fc2.bias"); op.residual = h->X1[i]; op.out_f32 = h->X2[i];
-            b.conv(op, "mlp.fc2", 4.0 * (double)tokens * C * C);
+        if (C <= 192) {
+            // narrow stages: fc1 -> GELU -> fc2 -> +residual in one kernel, hidden activation kept on chip
+            MlpOp mo;
+            memset(&mo, 0, sizeof(mo));
+            mo.C = C; mo.HW = remap ? HW : (int)tokens; mo.F = remap ? Fu : 1;
+            mo.f_group = remap ? kT : 0; mo.f_used = remap ? tmax : 0;
+            mo.A = h->ln2; mo.W1 = WP(bk + "mlp.fc1.weight"); mo.W2 = WP(bk + "mlp.fc2.weight");
+            mo.b1 = W(h, bk + "mlp.fc1.bias"); mo.b2 = W(h, bk + "mlp.fc2.bias");
+            mo.residual = h->X1[i]; mo.out = h->X2[i];
+            MlpLaunch ml;
+            if (int r = mlp_fused_lower(mo, &ml)) return fail(h, DSB_ERR_CUDA, "mlp_fused_lower failed (%d)", r);
+            const int sms = h->num_sms;
+            b.add([ml, sms](cudaStream_t s) { return mlp_fused_run(ml, sms, s); }, "gemm:mlp.fused");
+            h->prog_flops.back() = 8.0 * (double)tokens * C * C;      // fc1 + fc2, reference count over all 9 frames
+        } else {
+            {
+                ConvOp op = token_op(C, 2 * C, h->ln2, WP(bk + "mlp.fc1.weight"));
+                op.shift = W(h, bk + "mlp.fc1.bias"); op.act = ACT_GELU; op.out_bf16 = h->hid;
+                b.conv(op, "mlp.fc1", 4.0 * (double)tokens * C * C);
+            }
+            {
+                ConvOp op = token_op(2 * C, C, h->hid, WP(bk + "mlp.fc2.weight"));
+                op.shift = W(h, bk + "mlp.fc2.bias"); op.residual = h->X1[i]; op.out_f32 = h->X2[i];
+                b.conv(op, "mlp.fc2", 4.0 * (double)tokens * C * C);
+            }
         }
         {   // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU
             const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";

@@ -111,3 +111,18 @@ extern "C" int dsb_test_temb(const float* t, int B, const float* w0t, const floa
     float* tp[3] = {tp0, tp1, tp2};
     return temb_launch(t, B, w, tp, (cudaStream_t)stream);
 }
+
+#include "mlp_fused.cuh"
+
+extern "C" int dsb_test_mlp_fused(int C, int HW, int F, int f_group, int f_used, const void* A, const void* W1,
+                                  const void* W2, const float* b1, const float* b2, const float* residual, float* out,
+                                  void* stream) {
+    MlpOp op;
+    memset(&op, 0, sizeof(op));
+    op.C = C; op.HW = HW; op.F = F; op.f_group = f_group; op.f_used = f_used;
+    op.A = (const bf16*)A; op.W1 = (const bf16*)W1; op.W2 = (const bf16*)W2;
+    op.b1 = b1; op.b2 = b2; op.residual = residual; op.out = out;
+    MlpLaunch l;
+    if (int r = mlp_fused_lower(op, &l)) return r;
+    return mlp_fused_run(l, num_sms_cached(), (cudaStream_t)stream);
+}

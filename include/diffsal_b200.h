@@ -149,6 +149,10 @@ int dsb_test_temb(const float* t, int B, const float* w0t, const float* b0, cons
                   const float* wp0t, const float* bp0, const float* wp1t, const float* bp1, const float* wp2t,
                   const float* bp2, float* tp0, float* tp1, float* tp2, void* stream);
 
+/* fused fc1 -> GELU -> fc2 -> +residual (C = 96 or 192): A bf16 [frames][HW][C], W1 bf16 [2C][C], W2 bf16 [C][2C] */
+int dsb_test_mlp_fused(int C, int HW, int F, int f_group, int f_used, const void* A, const void* W1, const void* W2,
+                       const float* b1, const float* b2, const float* residual, float* out, void* stream);
+
 /* CTA-pair (cta_group::2) policy of dsb_test_conv: -1 never, 0 automatic, 1 always */
 void dsb_test_set_two_cta(int mode);
 

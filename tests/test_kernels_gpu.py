@@ -149,3 +149,26 @@ def test_linear_and_head_cta_pairs(L, two_cta):
     test_head_epilogue(L)
     test_temporal_reduce(L, 3, 28, 48, 192)
     test_conv3x3_stride2_into_frame_slot(L, 3, 28, 48, 192)
+
+
+@pytest.mark.parametrize("C,HW,F_,fg,fu", [(192, 1344, 3, 0, 0), (96, 5376, 2, 0, 0), (96, 640, 10, 9, 5), (192, 200, 4, 0, 0)])
+def test_fused_mlp(L, C, HW, F_, fg, fu):
+    """fc1 -> exact-erf GELU -> fc2 -> + residual with the hidden activation kept on chip (TMEM -> smem operand)."""
+    src_frames = F_ if not fg else (F_ // fu) * fg
+    a = _rand(src_frames, HW, C, seed=1).to(torch.bfloat16)
+    w1 = _rand(2 * C, C, seed=2, scale=C ** -0.5).to(torch.bfloat16)
+    w2 = _rand(C, 2 * C, seed=3, scale=(2 * C) ** -0.5).to(torch.bfloat16)
+    b1, b2 = _rand(2 * C, seed=4, scale=0.2), _rand(C, seed=5, scale=0.2)
+    res = _rand(src_frames, HW, C, seed=6)
+    out = torch.full((src_frames, HW, C), 7.0, device="cuda")
+    r = L.lib().dsb_test_mlp_fused(C, HW, F_, fg, fu, L.ptr(a), L.ptr(w1), L.ptr(w2), L.ptr(b1), L.ptr(b2), L.ptr(res),
+                                   L.ptr(out), L.stream_ptr())
+    assert r == 0, r
+    torch.cuda.synchronize()
+    hid = F.gelu(F.linear(a.float(), w1.float(), b1)).to(torch.bfloat16).float()     # the operand of fc2 is bf16
+    ref = F.linear(hid, w2.float(), b2) + res
+    live = [f for f in range(src_frames) if not fg or f % fg < fu]
+    dead = [f for f in range(src_frames) if f not in live]
+    close(out[live], ref[live], 3e-3)
+    if dead:
+        assert (out[dead] == 7.0).all()
