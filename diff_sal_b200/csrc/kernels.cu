@@ -630,6 +630,52 @@ int attn_operands_launch(const float* kp, const float* vp, int F, int C, float s
     DSB_LAUNCH_CHECK();
 }
 
+// Folded attention operands of the narrow stages (consumed by the fused attention chain, mlp_fused.cu mode 1):
+//   K1[f][hj][c]   = scale * sum_{d in head h} K[f,j,d] * Wq[d][c]      (bf16 [F][64][C], rows 36..63 zero)
+//   sb[f][hj]      = scale * sum_{d in head h} K[f,j,d] * bq[d]         (fp32 [F][64])
+//   V2[f][c][hj]   = sum_{d in head h} Wp[c][d] * V[f,j,d]              (bf16 [F][C][64], columns 36..63 zero)
+// one block per (hj, f), one thread per channel c
+__global__ void attn_fold_kernel(const float* __restrict__ kp, const float* __restrict__ vp, const float* __restrict__ wq,
+                                 const float* __restrict__ bq, const float* __restrict__ wpT, int C, float scale, int T,
+                                 int tmax, bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
+    __shared__ float sk[384];
+    __shared__ float sv[384];
+    const int hj = blockIdx.x, f = blockIdx.y, c = threadIdx.x;
+    if (f % T >= tmax) return;
+    if (hj >= 36) {
+        K1[((size_t)f * 64 + hj) * C + c] = __float2bfloat16(0.0f);
+        V2[((size_t)f * C + c) * 64 + hj] = __float2bfloat16(0.0f);
+        if (c == 0) sb[(size_t)f * 64 + hj] = 0.0f;
+        return;
+    }
+    const int h = hj / 18, j = hj % 18, d = C >> 1, d0 = h * d;
+    for (int i = c; i < d; i += blockDim.x) {
+        sk[i] = kp[((size_t)f * 18 + j) * C + d0 + i];
+        sv[i] = vp[((size_t)f * 18 + j) * C + d0 + i];
+    }
+    __syncthreads();
+    float ak = 0.0f, av = 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < d; ++i) {
+        ak = fmaf(sk[i], wq[(size_t)(d0 + i) * C + c], ak);
+        av = fmaf(sv[i], wpT[(size_t)(d0 + i) * C + c], av);
+    }
+    K1[((size_t)f * 64 + hj) * C + c] = __float2bfloat16(ak * scale);
+    V2[((size_t)f * C + c) * 64 + hj] = __float2bfloat16(av);
+    if (c == 0) {
+        float b = 0.0f;
+        for (int i = 0; i < d; ++i) b = fmaf(sk[i], bq[d0 + i], b);
+        sb[(size_t)f * 64 + hj] = b * scale;
+    }
+}
+
+int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
+                     float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s) {
+    if (C > 384) return -36;
+    attn_fold_kernel<<<dim3(64, F), C, 0, s>>>(kp, vp, wq, bq, wpT, C, scale, T, tmax, K1, sb, V2);
+    DSB_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------ multi-scale sum
 struct MsSrc { const float* r[4]; };
 

@@ -57,6 +57,10 @@ int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int
 int attn_operands_launch(const float* kp, const float* vp, int F, int C, float scale, bf16* KB, bf16* VB,
                          cudaStream_t s);
 
+// folded per-frame attention operands for the fused attention chain (Wq folded into K, Wp into V; see kernels.cu)
+int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
+                     float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s);
+
 // S[b][y][x][c] = sum_i bilinear(r_i -> 112x192)[b,y,x,c]  (bf16)   (sal_unet.py:482-487)
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s);
 // bilinear x2 on a single-channel map: p[B][112][192] -> out[B][224][384]   (sal_unet.py:325-327)

@@ -11,6 +11,12 @@
 //   warp 0     : TMA producer for the A tile (once per tile) and the W1 chunk ring;  warp 10: W2 chunk ring
 //   warp 1     : tcgen05.mma issuer (GEMM1 of chunk h+1 is issued before GEMM2 of chunk h)
 //   warps 2..9 : epilogue (stage 1: TMEM -> GELU -> smem operand;  stage 2: TMEM + bias + residual -> global)
+//
+// The same two-GEMM chain also runs the narrow stages' attention (mode 1): GEMM1 = LayerNormed query tokens times the
+// per-frame folded key operand K'_f = scale * K_f Wq (N = 2 heads x 18 keys), "activation" = + folded bias and per-head
+// softmax, GEMM2 = P times the per-frame folded value operand V''_f = Wp V_f (K = 64), + proj bias + residual.  Folding
+// Wq / Wp into the 18-token K / V operands removes the Q-projection and output-projection GEMMs and keeps Q, the
+// scores and the probabilities on chip (attention.py:97-113).
 #include "mlp_fused.cuh"
 
 #include <string.h>
@@ -39,7 +45,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int C = p.C, bk = p.bk;
     const int ksub = C / bk;                       // K sub-blocks of GEMM1
-    const int NC = 2 * C / kHC;                    // hidden chunks per tile
+    const int NC = p.mode ? 1 : 2 * C / kHC;       // hidden chunks per tile (attention: one chunk of 2 x 18 (+28) keys)
     const uint32_t a_sub = 128u * bk * 2u;
     const uint32_t a_bytes = a_sub * ksub;
     const uint32_t w1_sub = (uint32_t)kHC * bk * 2u;
@@ -103,7 +109,8 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                 if (elect_one()) {
                     uint8_t* w = sW1 + s * w1_bytes;
                     mbar_expect_tx(&bars->w1_full[s], w1_bytes);
-                    for (int j = 0; j < ksub; ++j) tma_load_2d(w + j * w1_sub, &tmW1, &bars->w1_full[s], j * bk, h * kHC);
+                    for (int j = 0; j < ksub; ++j)
+                        tma_load_2d(w + j * w1_sub, &tmW1, &bars->w1_full[s], j * bk, h * kHC + (p.mode ? fs * kHC : 0));
                 }
                 __syncwarp();
             }
@@ -112,12 +119,14 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
         // ------------------------------------------------------------------ W2 producer (its ring drains later than W1's)
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int f = tile / tiles_per_frame;
+            const int fs = p.f_group ? (f / p.f_used) * p.f_group + f % p.f_used : f;
             for (int h = 0; h < NC; ++h, ++g) {
                 const uint32_t s = g % (uint32_t)NS, ph = (g / (uint32_t)NS) & 1u;
                 mbar_wait(&bars->w2_empty[s], ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&bars->w2_full[s], w2_bytes);
-                    tma_load_2d(sW2 + s * w2_bytes, &tmW2, &bars->w2_full[s], h * kHC, 0);
+                    tma_load_2d(sW2 + s * w2_bytes, &tmW2, &bars->w2_full[s], h * kHC, p.mode ? fs * C : 0);
                 }
                 __syncwarp();
             }
@@ -189,6 +198,8 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t gg = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int f_t = tile / tiles_per_frame;
+            const int fs_row = p.f_group ? (f_t / p.f_used) * p.f_group + f_t % p.f_used : f_t;
             for (int h = 0; h < NC; ++h, ++gg) {
                 const uint32_t s = gg & 1u, ph = (gg >> 1) & 1u;
                 mbar_wait(&bars->acc1_full[s], ph);
@@ -199,13 +210,67 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->acc1_empty[s]);
-                const float* b1 = p.b1 + h * kHC + half * 32;
                 uint32_t packed[16];
+                if (p.mode == 0) {
+                    const float* b1 = p.b1 + h * kHC + half * 32;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v0 = gelu_erf(__uint_as_float(raw[2 * j]) + __ldg(b1 + 2 * j));
-                    const float v1 = gelu_erf(__uint_as_float(raw[2 * j + 1]) + __ldg(b1 + 2 * j + 1));
-                    packed[j] = pack_bf16x2(v0, v1);
+                    for (int j = 0; j < 16; ++j) {
+                        const float v0 = gelu_erf(__uint_as_float(raw[2 * j]) + __ldg(b1 + 2 * j));
+                        const float v1 = gelu_erf(__uint_as_float(raw[2 * j + 1]) + __ldg(b1 + 2 * j + 1));
+                        packed[j] = pack_bf16x2(v0, v1);
+                    }
+                } else {
+                    // scores of head 0 live in columns 0..17, head 1 in 18..35: the warp with half == 0 holds columns
+                    // 0..31, the other 32..63; the four head-1 scores 32..35 are exchanged through shared memory
+                    // (sx: [8 warps][32 rows][4]) so that each thread can normalise its own columns
+                    float v[32];
+                    const float* rb = p.b1 + (size_t)fs_row * kHC + half * 32;        // folded bias, per frame
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + __ldg(rb + j);
+                    float* sx = reinterpret_cast<float*>(bars + 1);                     // [2 halves][128 rows][4]
+                    // half 0 publishes (max, sum-exp partials need both halves): do it in two passes
+                    // pass 1: per-head partial maxima
+                    float m0 = -INFINITY, m1 = -INFINITY;
+                    if (half == 0) {
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) m0 = fmaxf(m0, v[j]);
+#pragma unroll
+                        for (int j = 18; j < 32; ++j) m1 = fmaxf(m1, v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m1 = fmaxf(m1, v[j]);
+                    }
+                    sx[(half * 128 + row) * 4 + 0] = m1;
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    m1 = fmaxf(m1, sx[((half ^ 1) * 128 + row) * 4 + 0]);
+                    // pass 2: exponentials and per-head partial sums
+                    float s0 = 0.0f, s1 = 0.0f;
+                    if (half == 0) {
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) { v[j] = __expf(v[j] - m0); s0 += v[j]; }
+#pragma unroll
+                        for (int j = 18; j < 32; ++j) { v[j] = __expf(v[j] - m1); s1 += v[j]; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { v[j] = __expf(v[j] - m1); s1 += v[j]; }
+#pragma unroll
+                        for (int j = 4; j < 32; ++j) v[j] = 0.0f;
+                    }
+                    sx[(half * 128 + row) * 4 + 1] = s1;
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    s1 += sx[((half ^ 1) * 128 + row) * 4 + 1];
+                    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+                    if (half == 0) {
+#pragma unroll
+                        for (int j = 0; j < 18; ++j) v[j] *= i0;
+#pragma unroll
+                        for (int j = 18; j < 32; ++j) v[j] *= i1;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] *= i1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
                 }
                 mbar_wait(&bars->a2_empty[s], ph ^ 1u);
                 uint8_t* dst = sA2 + s * a2_bytes + row * 128;
@@ -289,6 +354,7 @@ int mlp_fused_lower(const MlpOp& op, MlpLaunch* out) {
     const int C = op.C;
     if (C != 96 && C != 192) return -40;
     MlpParams& p = out->p;
+    p.mode = op.mode;
     p.C = C;
     p.bk = (C % 64 == 0) ? 64 : 32;
     p.HW = op.HW; p.F = op.F; p.f_group = op.f_group; p.f_used = op.f_used;
@@ -302,14 +368,16 @@ int mlp_fused_lower(const MlpOp& op, MlpLaunch* out) {
         if (int r = make_tensor_map(&out->tmA, op.A, 3, dims, str, box)) return r;
     }
     {
-        uint64_t dims[2] = {(uint64_t)C, (uint64_t)(2 * C)};
+        // MLP: fc1.weight [2C][C];  attention: folded keys [src frames * 64][C]
+        uint64_t dims[2] = {(uint64_t)C, op.mode ? (uint64_t)src_frames * kHC : (uint64_t)(2 * C)};
         uint64_t str[1] = {C * e};
         uint32_t box[2] = {(uint32_t)p.bk, (uint32_t)kHC};
         if (int r = make_tensor_map(&out->tmW1, op.W1, 2, dims, str, box)) return r;
     }
     {
-        uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)C};
-        uint64_t str[1] = {2 * C * e};
+        // MLP: fc2.weight [C][2C];  attention: folded values [src frames * C][64]
+        uint64_t dims[2] = {op.mode ? (uint64_t)kHC : (uint64_t)(2 * C), op.mode ? (uint64_t)src_frames * C : (uint64_t)C};
+        uint64_t str[1] = {(op.mode ? (uint64_t)kHC : (uint64_t)(2 * C)) * e};
         uint32_t box[2] = {(uint32_t)kHC, (uint32_t)C};
         if (int r = make_tensor_map(&out->tmW2, op.W2, 2, dims, str, box)) return r;
     }
@@ -321,7 +389,7 @@ int mlp_fused_run(const MlpLaunch& l, int num_sms, cudaStream_t stream) {
     const int ksub = p.C / p.bk;
     const size_t a_bytes = (size_t)128 * p.bk * 2 * ksub;
     const size_t w_stage = (size_t)kHC * p.bk * 2 * ksub + (size_t)p.C * kHC * 2;
-    const size_t fixed = a_bytes + 2 * (128 * kHC * 2) + sizeof(MlpBarriers) + 1024;
+    const size_t fixed = a_bytes + 2 * (128 * kHC * 2) + sizeof(MlpBarriers) + 4096 + 1024;
     int NS = (int)((230000 - fixed) / w_stage);
     if (NS > 4) NS = 4;
     if (NS < 2) return -42;

@@ -5,16 +5,18 @@
 namespace dsb {
 
 struct MlpParams {
+    int mode;                  // 0: MLP (GELU between the GEMMs); 1: attention (folded bias + per-head softmax)
     int C, bk;                 // channels; K sub-block of GEMM1 (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
     int HW, F;                 // tokens per frame, number of (live) frames
     int f_group, f_used;       // frame remap as in GemmParams (0 = identity)
-    const float* b1;           // [2C]
+    const float* b1;           // MLP: fc1 bias [2C];  attention: folded score bias [src frames][64]
     const float* b2;           // [C]
     const float* residual;     // fp32 [src frames][HW][C]
     float* out;                // fp32 [src frames][HW][C]
 };
 
 struct MlpOp {
+    int mode;
     int C, HW, F, f_group, f_used;
     const bf16* A;             // LayerNormed tokens, bf16 [src frames][HW][C]
     const bf16* W1;            // [2C][C]  (fc1.weight, K-major)

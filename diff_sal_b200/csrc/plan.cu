@@ -78,6 +78,8 @@ struct dsb_handle {
     float* r[4] = {};
     bf16 *up = nullptr, *mid = nullptr, *q_ln = nullptr, *Qp = nullptr, *k_ln = nullptr, *v_ln = nullptr;
     float *Kp = nullptr, *Vp = nullptr, *gate = nullptr;
+    bf16 *K1 = nullptr, *V2 = nullptr;            // folded attention operands (narrow stages)
+    float* sbias = nullptr;
     bf16 *KB = nullptr, *VB = nullptr, *P = nullptr, *o = nullptr, *ln2 = nullptr, *hid = nullptr, *lnm = nullptr;
     float2* lnstats = nullptr;
     bf16* S = nullptr;
@@ -243,6 +245,9 @@ int alloc_workspace(dsb_handle* h) {
     if (int r = dev_alloc(h, &h->KB, F * 48 * 768)) return r;
     if (int r = dev_alloc(h, &h->VB, F * 768 * 64)) return r;
     if (int r = dev_alloc(h, &h->P, F * 5376 * 64)) return r;
+    if (int r = dev_alloc(h, &h->K1, F * 64 * 192)) return r;
+    if (int r = dev_alloc(h, &h->V2, F * 192 * 64)) return r;
+    if (int r = dev_alloc(h, &h->sbias, F * 64)) return r;
     if (int r = dev_alloc(h, &h->o, F * kMaxFrame)) return r;
     if (int r = dev_alloc(h, &h->ln2, F * kMaxFrame)) return r;
     if (int r = dev_alloc(h, &h->hid, F * kMaxFrame * 2)) return r;
@@ -480,6 +485,32 @@ int build_program(dsb_handle* h) {
         b.cur = 0;
         b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
         // algorithmic FLOPs are always the reference's (all 9 frames), also where dead frames are skipped
+        const bool fused_attn = C <= 192;
+        if (fused_attn) {
+            // narrow stages: Wq is folded into the 18 keys and Wp into the 18 values of every frame, then one chained
+            // kernel does  q_ln . K'^T -> +bias -> per-head softmax -> P . V'' -> + proj bias + residual
+            b.depend(2, 1, 0);                                  // join V
+            b.depend(3, 2, 0);                                  // join K
+            const float *Kp = h->Kp, *Vp = h->Vp;
+            const float *wqf = W(h, bk + "attn.proj_q.weight"), *bqf = W(h, bk + "attn.proj_q.bias");
+            const float* wpT = WF(bk + "attn.proj.weight.T");
+            bf16 *K1 = h->K1, *V2 = h->V2;
+            float* sb = h->sbias;
+            const float scale = 1.0f / sqrtf((float)C);
+            b.add([=](cudaStream_t s) { return attn_fold_launch(Kp, Vp, wqf, bqf, wpT, F, C, scale, kT, tmax, K1, sb, V2, s); }, "attn_fold");
+            MlpOp mo;
+            memset(&mo, 0, sizeof(mo));
+            mo.mode = 1;
+            mo.C = C; mo.HW = HW; mo.F = remap ? Fu : F;
+            mo.f_group = remap ? kT : 0; mo.f_used = remap ? tmax : 0;
+            mo.A = q_ln; mo.W1 = h->K1; mo.W2 = h->V2; mo.b1 = h->sbias; mo.b2 = W(h, bk + "attn.proj.bias");
+            mo.residual = Xi; mo.out = h->X1[i];
+            MlpLaunch ml;
+            if (int r = mlp_fused_lower(mo, &ml)) return fail(h, DSB_ERR_CUDA, "attention chain lower failed (%d)", r);
+            const int sms = h->num_sms;
+            b.add([ml, sms](cudaStream_t s) { return mlp_fused_run(ml, sms, s); }, "gemm:attn.fused");
+            h->prog_flops.back() = 4.0 * (double)tokens * C * C + 4.0 * (double)tokens * 18 * C;   // q, proj, QK^T, PV
+        } else {
         {
             ConvOp op = token_op(C, C, q_ln, WP(bk + "attn.proj_q.weight"));
             op.shift = W(h, bk + "attn.proj_q.bias"); op.out_bf16 = h->Qp;
@@ -509,6 +540,7 @@ int build_program(dsb_handle* h) {
             ConvOp op = token_op(C, C, h->o, WP(bk + "attn.proj.weight"));
             op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
             b.conv(op, "attn.proj", 2.0 * (double)tokens * C * C);
+        }
         }
         {
             const float *g2 = W(h, bk + "norm2.weight"), *b2 = W(h, bk + "norm2.bias");
@@ -726,6 +758,8 @@ extern "C" int dsb_finalize_weights(dsb_handle* h) {
             if (!W(h, bk + k)) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s%s'", bk.c_str(), k);
         for (const char* k : {"attn.proj_q.weight", "attn.proj_k.weight", "attn.proj_v.weight", "attn.proj.weight"})
             if (int r = pack_gemm_weight(h, bk + k, C, C, 1)) return r;
+        if (C <= 192)
+            if (int r = transposed(bk + "attn.proj.weight", C, C)) return r;
         if (int r = pack_gemm_weight(h, bk + "mlp.fc1.weight", 2 * C, C, 1)) return r;
         if (int r = pack_gemm_weight(h, bk + "mlp.fc2.weight", C, 2 * C, 1)) return r;
         // depthwise Conv3d(3,3,3) on a depth-1 volume: only the middle temporal tap touches data (attention.py:36-44)
