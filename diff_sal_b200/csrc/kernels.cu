@@ -407,10 +407,94 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
     }
 }
 
+// Shared-memory tiled variant for the narrow, token-rich stages (C = 96, 192): a block stages the LayerNormed inputs
+// of 3 rows x (XT + 2) tokens once (normalisation applied while loading), then each warp produces tokens from shared
+// memory -- every input element is loaded from L2 ~3 times instead of 9 and normalised once instead of 9 times.
+template <int NV, int XT>
+__global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                                          int H, int W, const float* __restrict__ ng,
+                                                          const float* __restrict__ nb, const float* __restrict__ wq,
+                                                          const float* __restrict__ qg, const float* __restrict__ qb,
+                                                          bf16* __restrict__ out, int T, int tmax) {
+    constexpr int C = NV * 32;
+    constexpr int TW = XT + 2;
+    extern __shared__ float tile[];                      // [3][TW][C]
+    const int nseg = W / XT;
+    const int seg = blockIdx.x % nseg;
+    const int y = (blockIdx.x / nseg) % H;
+    const int f = blockIdx.x / (nseg * H);
+    if (f % T >= tmax) return;
+    const int x0 = seg * XT;
+    const size_t fbase = (size_t)f * H * W;
+    {
+        // one token per warp iteration: statistics loaded once, affine parameters in registers, coalesced row loads
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float g[NV], b[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { g[i] = ng[lane + 32 * i]; b[i] = nb[lane + 32 * i]; }
+        for (int t = warp; t < 3 * TW; t += 8) {
+            const int col = t % TW, r = t / TW;
+            const int yy = y + r - 1, xx = x0 + col - 1;
+            float* dst = tile + t * C;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t tok = fbase + (size_t)yy * W + xx;
+                const float2 st = stats[tok];
+                const float* row = x + tok * C;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = (row[lane + 32 * i] - st.x) * st.y * g[i] + b[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wt[9][NV], gq[NV], bq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        gq[i] = qg[c]; bq[i] = qb[c];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wt[k][i] = wq[k * C + c];
+    }
+    for (int tk = warp; tk < XT; tk += 8) {
+        float q[NV];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            float a = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a = fmaf(wt[r * 3 + k][i], tile[(r * TW + tk + k) * C + c], a);
+            q[i] = a;
+            s += a;
+        }
+        const float mean = warp_sum(s) * (1.0f / C);
+        float v2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { const float d = q[i] - mean; v2 = fmaf(d, d, v2); }
+        const float rstd = rsqrtf(warp_sum(v2) * (1.0f / C) + 1e-5f);
+        bf16* o = out + (fbase + (size_t)y * W + x0 + tk) * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[lane + 32 * i] = __float2bfloat16((q[i] - mean) * rstd * gq[i] + bq[i]);
+    }
+}
+
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
                   const float* wq, const float* qg, const float* qb, bf16* out, int T, int tmax, cudaStream_t s) {
     const long tokens = (long)F * H * W;
     const int g = (int)((tokens + 7) / 8);
+    if (C == 96 && W % 32 == 0) {
+        q_dwln_tiled_kernel<3, 32><<<F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        DSB_LAUNCH_CHECK();
+    }
+    if (C == 192 && W % 16 == 0) {
+        q_dwln_tiled_kernel<6, 16><<<F * H * (W / 16), 256, 3 * 18 * 192 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        DSB_LAUNCH_CHECK();
+    }
     switch (C) {
         case 96: q_dwln_kernel<3><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
         case 192: q_dwln_kernel<6><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
@@ -564,20 +648,67 @@ __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __rest
     if (tt >= tmax) return;
     const int clip_base = tt * HW * C;           // < 9 * 516096, fits int
     const int THW = T * HW;
-    auto src = [&](int p, int c) -> float {
-        const int dy = p / S_, dx = p % S_;
-        const int pixp = (Y * S_ + dy) * W + (X * S_ + dx);
-        const int j = clip_base + pixp * C + c;
-        const int cs = j / THW;
-        const int rem = j - cs * THW;
-        const int ts = rem / HW;
-        const int pix = rem - ts * HW;
-        const int ys = pix / W, xs = pix - ys * W;
-        const float av = a_low[((((size_t)b * T + ts) * 7 + ys / R) * 12 + xs / R) * C + cs];
-        const float gv = g[((size_t)b * C + cs) * HW + pix];
-        return wk[p * C + c] * (av * gv);
-    };
-    pool_accumulate(src, C, S_ * S_, sm);
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    // Thread (c, gq) walks window rows dy = gq, gq+G, ... and, inside a row, the S_ pixels dx.  The flat index of the
+    // scrambled source advances by C per dx, so (channel, frame, y, x) of the source are stepped with adds and carries
+    // (where C < HW: at most one carry per step) instead of being re-derived with divisions for every element.
+    constexpr int G_MAX = 4;
+    const int G = (C <= nthr) ? nthr / C : 1;
+    const float* a_b = a_low + (size_t)b * T * 84 * C;
+    const float* g_b = g + (size_t)b * C * HW;
+    for (int c = (C <= nthr ? tid % C : tid), pass = 0; c < C && (C > nthr || pass == 0); c += nthr, ++pass) {
+        const int gq = (C <= nthr) ? tid / C : 0;
+        float acc = 0.0f;
+        if (gq < G) {
+            for (int dy = gq; dy < S_; dy += G) {
+                const int pixp = (Y * S_ + dy) * W + X * S_;
+                int j = clip_base + pixp * C + c;
+                int cs = j / THW;
+                int rem = j - cs * THW;
+                int ts = rem / HW;
+                int pix = rem - ts * HW;
+                int ys = pix / W, xs = pix - ys * W;
+                const float* wrow = wk + (dy * S_) * C + c;
+#pragma unroll 4
+                for (int dx = 0; dx < S_; ++dx) {
+                    const float av = a_b[(((size_t)ts * 7 + (ys / R)) * 12 + (xs / R)) * C + cs];
+                    const float gv = g_b[(size_t)cs * HW + pix];
+                    acc = fmaf(wrow[dx * C], av * gv, acc);
+                    if constexpr (C < HW) {
+                        // advance the flat source index by C with adds and carries
+                        pix += C;
+                        xs += C % W;
+                        ys += C / W;
+                        if (xs >= W) { xs -= W; ++ys; }
+                        if (pix >= HW) {
+                            pix -= HW; ys -= H;
+                            if (++ts == T) { ts = 0; ++cs; }
+                        }
+                    } else {
+                        // wide, small stages (C >= HW): several wraps per step, re-derive
+                        j += C;
+                        cs = j / THW;
+                        rem = j - cs * THW;
+                        ts = rem / HW;
+                        pix = rem - ts * HW;
+                        ys = pix / W;
+                        xs = pix - ys * W;
+                    }
+                }
+            }
+            if (C <= nthr) sm[gq * C + c] = acc; else sm[c] = acc;
+        }
+    }
+    (void)G_MAX;
+    __syncthreads();
+    if (C <= nthr && G > 1) {
+        float a = 0.0f;
+        if (tid < C)
+            for (int k = 0; k < G; ++k) a += sm[k * C + tid];
+        __syncthreads();
+        if (tid < C) sm[tid] = a;
+        __syncthreads();
+    }
     pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
 }
 
