@@ -42,10 +42,15 @@ __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, 
     }
     __syncthreads();
     {
-        float acc = w.b1[tid];
-#pragma unroll 8
-        for (int k = 0; k < 384; ++k) acc = fmaf(w.w1[k * 384 + tid], h1[k], acc);
-        h2[tid] = swishf(acc);                               // only swish(temb) is consumed (sal_unet.py:129)
+        float a0 = w.b1[tid], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;   // 4 independent chains: loads stay in flight
+#pragma unroll 4
+        for (int k = 0; k < 384; k += 4) {
+            a0 = fmaf(w.w1[k * 384 + tid], h1[k], a0);
+            a1 = fmaf(w.w1[(k + 1) * 384 + tid], h1[k + 1], a1);
+            a2 = fmaf(w.w1[(k + 2) * 384 + tid], h1[k + 2], a2);
+            a3 = fmaf(w.w1[(k + 3) * 384 + tid], h1[k + 3], a3);
+        }
+        h2[tid] = swishf((a0 + a1) + (a2 + a3));             // only swish(temb) is consumed (sal_unet.py:129)
     }
     __syncthreads();
     const int o = blockIdx.y * 336 + tid;                    // 1344 = 192 + 384 + 768 outputs, 336 per block
@@ -54,11 +59,16 @@ __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, 
         if (o < 192) { i = 0; r = o; } else if (o < 576) { i = 1; r = o - 192; } else { i = 2; r = o - 576; }
         const int co = w.cout[i];
         const float* wt = w.wp[i];
-        float acc = w.bp[i][r];
-#pragma unroll 8
-        for (int k = 0; k < 384; ++k) acc = fmaf(wt[k * co + r], h2[k], acc);
+        float a0 = w.bp[i][r], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < 384; k += 4) {
+            a0 = fmaf(wt[k * co + r], h2[k], a0);
+            a1 = fmaf(wt[(k + 1) * co + r], h2[k + 1], a1);
+            a2 = fmaf(wt[(k + 2) * co + r], h2[k + 2], a2);
+            a3 = fmaf(wt[(k + 3) * co + r], h2[k + 3], a3);
+        }
         float* out = i == 0 ? tp0 : (i == 1 ? tp1 : tp2);
-        out[(size_t)b * co + r] = acc;
+        out[(size_t)b * co + r] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -206,8 +216,51 @@ __device__ __forceinline__ void bil_src(int dst, float scale, int in_size, int& 
     l1 = src - (float)i0;
 }
 
-// thread = (4-channel vector, output row); walks XT output columns keeping the vertically interpolated left / right
-// source columns in registers (each source element is loaded ~once per output row instead of once per output)
+// Horizontal source offset / weight of output column xo0 + dx for an exact 2^-N bilinear upscale (xo0 a multiple of
+// 2^N): src = (dx + 0.5) / 2^N - 0.5 relative to xo0 >> N.  Compile-time functions of dx.
+template <int N>
+struct PowX {
+    static __device__ __forceinline__ constexpr int off(int dx) {
+        const int num = 2 * dx + 1 - (1 << N);
+        return num >= 0 ? num / (1 << (N + 1)) : -((-num + (1 << (N + 1)) - 1) / (1 << (N + 1)));
+    }
+    static __device__ __forceinline__ constexpr float lx(int dx) {
+        const int num = 2 * dx + 1 - (1 << N);
+        return (float)(num - off(dx) * (1 << (N + 1))) / (float)(1 << (N + 1));
+    }
+};
+
+// thread = (4-channel vector, output row); produces 24 consecutive output columns with the walk fully unrolled: for
+// the x2 upscale the reload points and the 0.25 / 0.75 weights are compile-time constants (index clamping at the edges
+// reproduces PyTorch's source-coordinate clamp exactly).
+template <int DX>
+struct Up2Walk {
+    static __device__ __forceinline__ void run(const float4* __restrict__ base, int y0, int y1, float ly, int W, int cv_n,
+                                               int xb, float4& colL, float4& colR, uint2* __restrict__ orow) {
+        constexpr int o = PowX<1>::off(DX);
+        constexpr float lxv = PowX<1>::lx(DX);
+        constexpr bool reload = (DX == 0) || (PowX<1>::off(DX) != PowX<1>::off(DX > 0 ? DX - 1 : 0));
+        if constexpr (reload) {
+            const int xu = xb + o;
+            const int x1 = min(max(xu + 1, 0), W - 1);
+            const float h0 = 1.0f - ly;
+            if constexpr (DX == 0) {
+                const int x0 = min(max(xu, 0), W - 1);
+                const float4 a = base[((size_t)y0 * W + x0) * cv_n], c = base[((size_t)y1 * W + x0) * cv_n];
+                colL = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
+            } else {
+                colL = colR;                                   // the walk advanced by exactly one source column
+            }
+            const float4 a = base[((size_t)y0 * W + x1) * cv_n], c = base[((size_t)y1 * W + x1) * cv_n];
+            colR = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
+        }
+        constexpr float w0 = 1.0f - lxv;
+        orow[(size_t)DX * cv_n] = make_uint2(pack_bf16x2(w0 * colL.x + lxv * colR.x, w0 * colL.y + lxv * colR.y),
+                                             pack_bf16x2(w0 * colL.z + lxv * colR.z, w0 * colL.w + lxv * colR.w));
+        if constexpr (DX + 1 < 24) Up2Walk<DX + 1>::run(base, y0, y1, ly, W, cv_n, xb, colL, colR, orow);
+    }
+};
+
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int H, int W, int C,
                                                         bf16* __restrict__ out, int XT) {
     const int cv_n = C >> 2;
@@ -215,30 +268,15 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
     const int cv = blockIdx.z * lanes + threadIdx.x;
     const int yo = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.x / ((2 * W) / XT);
-    const int xo0 = (blockIdx.x % ((2 * W) / XT)) * XT;
+    const int xo0 = (blockIdx.x % ((2 * W) / XT)) * XT;  // XT == 24
     if (cv >= cv_n || yo >= 2 * H) return;
     int y0, y1;
     float ly;
     bil_src(yo, 0.5f, H, y0, y1, ly);
     const float4* base = reinterpret_cast<const float4*>(x + (size_t)f * H * W * C) + cv;
-    auto vload = [&](int xs) -> float4 {
-        const float4 a = base[((size_t)y0 * W + xs) * cv_n], c = base[((size_t)y1 * W + xs) * cv_n];
-        const float h0 = 1.0f - ly, h1 = ly;
-        return make_float4(h0 * a.x + h1 * c.x, h0 * a.y + h1 * c.y, h0 * a.z + h1 * c.z, h0 * a.w + h1 * c.w);
-    };
-    float4 colL = make_float4(0, 0, 0, 0), colR = make_float4(0, 0, 0, 0);
-    int xl = -1, xr = -1;
+    float4 colL, colR;
     uint2* orow = reinterpret_cast<uint2*>(out) + (((size_t)f * 2 * H + yo) * 2 * W + xo0) * cv_n + cv;
-    for (int dx = 0; dx < XT; ++dx) {
-        int x0, x1;
-        float lx;
-        bil_src(xo0 + dx, 0.5f, W, x0, x1, lx);
-        if (x0 != xl) { colL = (x0 == xr) ? colR : vload(x0); xl = x0; }
-        if (x1 != xr) { colR = (x1 == xl) ? colL : vload(x1); xr = x1; }
-        const float w0 = 1.0f - lx;
-        orow[(size_t)dx * cv_n] = make_uint2(pack_bf16x2(w0 * colL.x + lx * colR.x, w0 * colL.y + lx * colR.y),
-                                             pack_bf16x2(w0 * colL.z + lx * colR.z, w0 * colL.w + lx * colR.w));
-    }
+    Up2Walk<0>::run(base, y0, y1, ly, W, cv_n, xo0 >> 1, colL, colR, orow);
 }
 
 int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s) {
@@ -559,17 +597,20 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
     const int f = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
     if (f % T >= tmax) return;
     const size_t fbase = (size_t)f * H * W;
+    const int sl = 31 - __clz(s_);                       // s is a power of two (2, 4, 8, 16)
+    const float* xw = x + (fbase + (size_t)(Y * s_) * W + X * s_) * C;
+    const float2* sw = stats + fbase + (size_t)(Y * s_) * W + X * s_;
     auto src = [&](int p, int c) -> float {
-        const int dy = p / s_, dx = p % s_;
-        const size_t t = fbase + (size_t)(Y * s_ + dy) * W + (X * s_ + dx);
-        const float2 st = stats[t];
-        return wv[p * C + c] * ((x[t * C + c] - st.x) * st.y * ng[c] + nb[c]);
+        const int dy = p >> sl, dx = p & (s_ - 1);
+        const int t = dy * W + dx;
+        const float2 st = sw[t];
+        return wv[p * C + c] * ((xw[(size_t)t * C + c] - st.x) * st.y * ng[c] + nb[c]);
     };
     pool_accumulate(src, C, s_ * s_, sm);
     pooled_ln_store(sm, C, vg, vb, out + (size_t)tokv * C, red);
 }
 
-static int pool_threads(int C) { return C <= 192 ? 192 : 384; }
+static int pool_threads(int C) { return C <= 384 ? 768 : 768; }   // channels x pixel groups (G = 768 / C)
 
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
                    const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, int T, int tmax,
@@ -810,8 +851,54 @@ int attn_fold_launch(const float* kp, const float* vp, const float* wq, const fl
 // ------------------------------------------------------------------------------------------ multi-scale sum
 struct MsSrc { const float* r[4]; };
 
-// thread = (4-channel vector, output row); walks 32 output columns keeping the vertically interpolated left / right
-// source columns of each scale in registers, so a source element is loaded ~once per row instead of once per output
+// thread = (4-channel vector, output row); produces 32 consecutive output columns.  All four scales are exact powers
+// of two (1/2 .. 1/16), so for an output column xo0 + dx the left source column is (xo0 >> n) + off(dx, n) and the
+// horizontal weight lx(dx, n) are COMPILE-TIME constants of dx: the walk is fully unrolled, the reload points of the
+// vertically interpolated source columns are static and the weights fold into immediates.  Index clamping at the
+// image edges reproduces PyTorch's "clamp the source coordinate at 0 / last" exactly (both taps hit the same pixel).
+template <int N, int DX>
+__device__ __forceinline__ void ms_accum(const float4* __restrict__ base, int y0, int y1, float ly, int xb, int& xl,
+                                         float4& colL, float4& colR, float4& acc) {
+    constexpr int W = 192 >> N, CV = 192;
+    constexpr int o = PowX<N>::off(DX);
+    constexpr float lxv = PowX<N>::lx(DX);
+    constexpr bool reload = (DX == 0) || (PowX<N>::off(DX) != PowX<N>::off(DX > 0 ? DX - 1 : 0));
+    if constexpr (reload) {
+        const int xu = xb + o;
+        const int x0 = min(max(xu, 0), W - 1), x1 = min(max(xu + 1, 0), W - 1);
+        const float h0 = 1.0f - ly;
+        if (DX != 0 && x0 == xl + 1) {
+            colL = colR;                                         // the walk advanced by one source column
+        } else {
+            const float4 a = base[((size_t)y0 * W + x0) * CV], c = base[((size_t)y1 * W + x0) * CV];
+            colL = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
+        }
+        const float4 a = base[((size_t)y0 * W + x1) * CV], c = base[((size_t)y1 * W + x1) * CV];
+        colR = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
+        xl = x0;
+    }
+    constexpr float w0 = 1.0f - lxv;
+    acc.x += w0 * colL.x + lxv * colR.x;
+    acc.y += w0 * colL.y + lxv * colR.y;
+    acc.z += w0 * colL.z + lxv * colR.z;
+    acc.w += w0 * colL.w + lxv * colR.w;
+}
+
+template <int DX>
+struct MsWalk {
+    static __device__ __forceinline__ void run(const float4* const (&base)[4], const int (&y0)[4], const int (&y1)[4],
+                                               const float (&ly)[4], const int (&xb)[4], int (&xl)[4],
+                                               float4 (&colL)[4], float4 (&colR)[4], uint2* __restrict__ orow) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        ms_accum<4, DX>(base[0], y0[0], y1[0], ly[0], xb[0], xl[0], colL[0], colR[0], acc);   // 7x12   (1/16)
+        ms_accum<3, DX>(base[1], y0[1], y1[1], ly[1], xb[1], xl[1], colL[1], colR[1], acc);   // 14x24  (1/8)
+        ms_accum<2, DX>(base[2], y0[2], y1[2], ly[2], xb[2], xl[2], colL[2], colR[2], acc);   // 28x48  (1/4)
+        ms_accum<1, DX>(base[3], y0[3], y1[3], ly[3], xb[3], xl[3], colL[3], colR[3], acc);   // 56x96  (1/2)
+        orow[(size_t)DX * 192] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+        if constexpr (DX + 1 < 32) MsWalk<DX + 1>::run(base, y0, y1, ly, xb, xl, colL, colR, orow);
+    }
+};
+
 __global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
     constexpr int C = 768, CV = C / 4, OH = 112, OW = 192, XT = 32;
     const int cv = blockIdx.z % 12 * 16 + (threadIdx.x & 15);
@@ -819,48 +906,18 @@ __global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, bf16* __restrict
     const int yo = blockIdx.y * 16 + (threadIdx.x >> 4);
     const int xo0 = blockIdx.x * XT;
     const float4* base[4];
-    int y0[4], y1[4];
+    int y0[4], y1[4], xb[4], xl[4] = {-9, -9, -9, -9};
     float ly[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int H = 7 << k, W = 12 << k;
         base[k] = reinterpret_cast<const float4*>(src.r[k] + (size_t)b * H * W * C) + cv;
         bil_src(yo, (float)H / (float)OH, H, y0[k], y1[k], ly[k]);
+        xb[k] = xo0 >> (4 - k);
     }
     float4 colL[4], colR[4];
-    int xl[4] = {-1, -1, -1, -1}, xr[4] = {-1, -1, -1, -1};
-    auto vload = [&](int k, int xs) -> float4 {
-        const int W = 12 << k;
-        const float4 a = base[k][((size_t)y0[k] * W + xs) * CV], c = base[k][((size_t)y1[k] * W + xs) * CV];
-        const float h0 = 1.0f - ly[k], h1 = ly[k];
-        return make_float4(h0 * a.x + h1 * c.x, h0 * a.y + h1 * c.y, h0 * a.z + h1 * c.z, h0 * a.w + h1 * c.w);
-    };
     uint2* orow = reinterpret_cast<uint2*>(S) + (((size_t)b * OH + yo) * OW + xo0) * CV + cv;
-    for (int dx = 0; dx < XT; ++dx) {
-        const int xo = xo0 + dx;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int W = 12 << k;
-            int x0, x1;
-            float lx;
-            bil_src(xo, (float)W / (float)OW, W, x0, x1, lx);
-            if (x0 != xl[k]) {
-                if (x0 == xr[k]) colL[k] = colR[k]; else colL[k] = vload(k, x0);
-                xl[k] = x0;
-            }
-            if (x1 != xr[k]) {
-                if (x1 == xl[k]) colR[k] = colL[k]; else colR[k] = vload(k, x1);
-                xr[k] = x1;
-            }
-            const float w0 = 1.0f - lx;
-            acc.x += w0 * colL[k].x + lx * colR[k].x;
-            acc.y += w0 * colL[k].y + lx * colR[k].y;
-            acc.z += w0 * colL[k].z + lx * colR[k].z;
-            acc.w += w0 * colL[k].w + lx * colR[k].w;
-        }
-        orow[(size_t)dx * CV] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
-    }
+    MsWalk<0>::run(base, y0, y1, ly, xb, xl, colL, colR, orow);
 }
 
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {
