@@ -30,6 +30,20 @@ import torch  # noqa: E402
 CLIPS_PER_GPU = 8
 NFE = 10
 GFLOP_PER_CLIP_EVAL = 152.73          # torch flop counter on the reference graph (audio-visual)
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM-class launch, from the committed ncu capture
+    (profiles/r1_gemm_traffic_summary.txt); None if that file is missing."""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r1_gemm_traffic_summary.txt")):
+            if line.startswith("avg_dram_bytes_per_launch"):
+                return float(line.split()[1])
+    except Exception:
+        pass
+    return None
+
+
 WORKLOAD = ("audio_visual (cfgs/audio_visual.py shapes) batch 8 clips/GPU, DPM-solver multistep order 2, logSNR steps, "
             "10 NFE (steps=9 + denoise_to_zero), x0-parameterised SalUNet, random-init 'wide' weights")
 
@@ -259,9 +273,11 @@ def run_b200(args):
         tot_ms = sum(v[0] for v in acc.values()) / reps
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12
         step_tf = n_clips_total * NFE * GFLOP_PER_CLIP_EVAL * 1e9 * args.steps / (ms * 1e-3) / 1e12 / world
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/linear/attention launches)",
+        roof = {"bound": "tensor",
+                "kernel": "gemm_tc_kernel<0|1> + mlp_fused_kernel (tcgen05 implicit GEMM / fused GEMM chains: every conv, linear and attention launch)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"],
+                "traffic": ncu_traffic_per_launch(), "traffic_unit": "bytes per launch (ncu dram read+write, B=8)",
+                "peak_source": peaks["source"],
                 "launches_per_eval": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9,
                 "kernel_share_of_eval": gemm_ms / tot_ms,
