@@ -139,6 +139,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.ldo = op.ldo ? op.ldo : op.N;
     p.out_fmul = op.out_fmul ? op.out_fmul : 1;
     p.out_fadd = op.out_fadd;
+    p.out2_f32 = op.out2_f32; p.out2_fmul = op.out2_fmul ? op.out2_fmul : 1; p.out2_fadd = op.out2_fadd;
     p.head_w = op.head_w; p.head_b = op.head_b; p.out_head = op.out_head;
     p.b_rows_per_frame = op.b_rows_per_frame;
     p.out_softmax = op.out_softmax;

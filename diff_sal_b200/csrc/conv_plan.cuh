@@ -37,6 +37,8 @@ struct ConvOp {
     bf16* out_softmax;      // attention-score epilogue (N == 48)
     int f_group, f_used;    // frame remap: F counts USED frames; tile frame tf -> source (tf/f_used)*f_group + tf%f_used
     int out_remap;          // write outputs at the source frame index (else compact)
+    float* out2_f32;        // optional second fp32 output with its own frame mapping
+    int out2_fmul, out2_fadd;
     int two_cta;            // -1: never, 0: automatic (pairs when there are enough tiles), 1: force
 };
 

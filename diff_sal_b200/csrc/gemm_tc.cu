@@ -220,6 +220,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const int fo = p.out_remap ? fs : f;
             const size_t pix_in = ((size_t)fs * p.H + y) * p.W + x;
             const size_t pix_out = ((size_t)(fo * p.out_fmul + p.out_fadd) * p.H + y) * p.W + x;
+            const size_t pix_out2 = ((size_t)(fo * p.out2_fmul + p.out2_fadd) * p.H + y) * p.W + x;
             const int n0 = nt * p.bn;
 
             mbar_wait(&bars->tmem_full[acc], acc_phase);
@@ -340,6 +341,11 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
 #pragma unroll
                             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
+                        if (p.out2_f32) {
+                            float4* op = reinterpret_cast<float4*>(p.out2_f32 + pix_out2 * p.ldo + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
                         if (p.out_bf16) {
                             uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
                             op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -352,12 +358,13 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             } else {
                 // general epilogue: 32-column chunks are transposed through shared memory so that one warp
                 // instruction touches whole 128-byte rows (coalesced residual loads and output stores)
-                float* tile = epi_base + 128 * kPerQuad + (warp - 2) * (32 * 36 + 96);
-                int* rowtab = reinterpret_cast<int*>(tile + 32 * 36);      // [32][3]: pix_out, pix_in, frame (or -1)
+                float* tile = epi_base + 128 * kPerQuad + (warp - 2) * (32 * 36 + 128);
+                int* rowtab = reinterpret_cast<int*>(tile + 32 * 36);      // [32]: pix_out | pix_in | frame | pix_out2
                 __syncwarp();
                 rowtab[lane * 3 + 0] = valid ? (int)pix_out : -1;
                 rowtab[lane * 3 + 1] = (int)pix_in;
                 rowtab[lane * 3 + 2] = fs;
+                rowtab[96 + lane] = (int)pix_out2;
                 const int cq = (lane & 7) * 4;                             // this lane's 4 columns inside the chunk
                 const int rq = lane >> 3;                                  // row offset inside a group of 4 rows
                 for (int c = half * 32; c < p.bn; c += 32 * kPerQuad) {
@@ -396,6 +403,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                         }
                         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
+                        if (p.out2_f32) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)rowtab[96 + row] * p.ldo + n) = v;
                         if (p.out_bf16)
                             *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po * p.ldo + n) =
                                 make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -494,7 +502,7 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.two_cta && (p.b_rows_per_frame || p.out_softmax || (p.bn / 2) % 8)) return -20;
     if (p.ksub < 1 || (p.taps * p.cin_blocks) % p.ksub) return -21;
     const uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
-    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 96) : 0) + 128 * kPerQuad) * sizeof(float);
+    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;

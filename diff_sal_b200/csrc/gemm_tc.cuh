@@ -47,6 +47,8 @@ struct GemmParams {
     bf16* out_bf16;                 // [pix][ldo] or null
     int ldo;                        // output row pitch in elements
     int out_fmul, out_fadd;         // output frame = f * out_fmul + out_fadd
+    float* out2_f32;                // optional second fp32 copy of the output (own frame mapping), e.g. the noise slice
+    int out2_fmul, out2_fadd;       //   written both compactly and into frame slot 8 of the 9-frame stage tensor
     // fused 96->1 head (mt_proj + logits): out_head[pix] = sigmoid(sum_n v[n] * head_w[n] + head_b)
     const float* head_w;            // [N] or null
     float head_b;

@@ -156,26 +156,35 @@ int gn_stats_launch(const float* x, int F, int HW, int C, double* part, cudaStre
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int HW, int C, int S,
-                                                      const double* __restrict__ part, const float* __restrict__ gamma,
+                                                      const double* __restrict__ part_sums, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, bf16* __restrict__ out_act,
                                                       bf16* __restrict__ out_raw) {
     __shared__ float mean[32];
     __shared__ float rstd[32];
     const int f = blockIdx.y, tid = threadIdx.x;
     const int cg = C >> 5;
-    if (tid < 32) {
+    {
+        // 8 threads per group add the per-split partial sums (fixed order: deterministic), then combine by shuffle
+        const int grp = tid >> 3, part = tid & 7;
         double sm = 0.0, sq = 0.0;
-        for (int k = 0; k < S; ++k) {
-            const double* o = part + (((size_t)f * S + k) * 32 + tid) * 2;
+        for (int k = part; k < S; k += 8) {
+            const double* o = part_sums + (((size_t)f * S + k) * 32 + grp) * 2;
             sm += o[0];
             sq += o[1];
         }
-        const double n = (double)HW * cg;
-        const double m = sm / n;
-        double v = sq / n - m * m;
-        if (v < 0.0) v = 0.0;
-        mean[tid] = (float)m;
-        rstd[tid] = (float)(1.0 / sqrt(v + 1e-6));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (part == 0) {
+            const double n = (double)HW * cg;
+            const double m = sm / n;
+            double v = sq / n - m * m;
+            if (v < 0.0) v = 0.0;
+            mean[grp] = (float)m;
+            rstd[grp] = (float)(1.0 / sqrt(v + 1e-6));
+        }
     }
     __syncthreads();
     const int cv_n = C >> 2;

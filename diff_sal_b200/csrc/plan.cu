@@ -352,7 +352,11 @@ int build_program(dsb_handle* h) {
             tw.wp[i] = WF(r + "weight.T"); tw.bp[i] = W(h, r + "bias"); tw.cout[i] = cout[i];
         }
         float* tp[3] = {h->tp[0], h->tp[1], h->tp[2]};
+        // the timestep MLP only feeds the conv1 epilogues: it runs beside the stem / first GroupNorm on a side stream
+        b.depend(4, 0, 1);
+        b.cur = 1;
         b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); }, "temb");
+        b.cur = 0;
         const float *w5 = WF("stem.w5"), *b5 = WF("stem.b5");
         float* h0 = h->h0;
         b.add([h, w5, b5, h0, B](cudaStream_t s) { return stem_launch(h->cur_x, B, w5, b5, h0, s); }, "stem5x5", (double)B * (344064.0 + 2064384.0));
@@ -370,6 +374,7 @@ int build_program(dsb_handle* h) {
             float *c1 = h->enc_c1, *sc = h->enc_sc;
             b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); }, "gn_stats", (double)B * HW * Cin * 4.0);
             b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); }, "gn_apply", (double)B * HW * Cin * 8.0);
+            if (i == 0) b.depend(5, 1, 0);                  // timestep projections ready
             {   // conv1 + bias + temb projection
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
                 op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
@@ -389,18 +394,13 @@ int build_program(dsb_handle* h) {
             }
             const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
             float* d = h->enc_d[i];
-            {   // Downsample: pad (0,1,0,1) + 3x3 stride 2
+            {   // Downsample: pad (0,1,0,1) + 3x3 stride 2.  The result is the next block's input (compact copy) AND the
+                // noise slice = frame 8 of the stage input / skip tensor (sal_unet.py:311-317), written by the same epilogue
                 ConvOp op = make_op(CONV_3X3_S2, B, H / 2, Wd / 2, Cout, Cout, res, WP(dk + "weight"));
                 op.shift = W(h, dk + "bias"); op.out_f32 = d;
+                op.out2_f32 = h->back[2 - i]; op.out2_fmul = kT; op.out2_fadd = kTv;
                 b.conv(op, "res.down");
             }
-            // noise slice = frame 8 of the stage input / skip tensor (sal_unet.py:311-317)
-            const size_t fe = frame_elems(2 - i);
-            float* dst = h->back[2 - i] + (size_t)kTv * fe;
-            b.add([=](cudaStream_t s) {
-                return (int)cudaMemcpy2DAsync(dst, (size_t)kT * fe * sizeof(float), d, fe * sizeof(float),
-                                              fe * sizeof(float), B, cudaMemcpyDeviceToDevice, s);
-            }, "noise_slice_copy", (double)B * fe * 8.0);
             cur = d;
             Cin = Cout; H /= 2; Wd /= 2;
         }
