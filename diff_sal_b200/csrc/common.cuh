@@ -218,7 +218,7 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-erf GELU (nn.GELU default).  erf through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16
 // rounding of the value that is stored): 2 MUFU (rcp.approx, ex2.approx) + ~10 FMA-class instructions, against the
 // ~40-instruction branchy erff -- the GELU epilogues were instruction-bound.

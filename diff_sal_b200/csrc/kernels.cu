@@ -141,13 +141,44 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         double s = 0.0, q = 0.0;
         for (int l = 0; l < P; ++l)
             for (int k = 0; k < cg; ++k) { s += (double)ssum[l * C + tid * cg + k]; q += (double)ssq[l * C + tid * cg + k]; }
-        double* o = part + (((size_t)f * gridDim.x + blockIdx.x) * 32 + tid) * 2;
+        double* o = part + (size_t)f * 4096 + ((size_t)blockIdx.x * 32 + tid) * 2;
         o[0] = s;
         o[1] = q;
+        __threadfence();
     }
+    // the last block of a frame to arrive folds the splits (fixed order -> bitwise reproducible) into (mean, rstd)
+    __shared__ bool last;
+    unsigned* counter = reinterpret_cast<unsigned*>(part + (size_t)f * 4096 + 4064);
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int grp = tid >> 3, sl = tid & 7, S = gridDim.x;
+    double sm = 0.0, sq = 0.0;
+    for (int k = sl; k < S; k += 8) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(part + (size_t)f * 4096 + ((size_t)k * 32 + grp) * 2));
+        sm += v.x;
+        sq += v.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (sl == 0) {
+        const double n = (double)HW * (C >> 5);
+        const double m = sm / n;
+        double v = sq / n - m * m;
+        if (v < 0.0) v = 0.0;
+        float2* fin = reinterpret_cast<float2*>(part + (size_t)f * 4096 + 4032);
+        fin[grp] = make_float2((float)m, (float)(1.0 / sqrt(v + 1e-6)));
+    }
+    if (tid == 0) *counter = 0;
 }
 
-static int gn_splits(int HW) { int S = HW / 8; return S > 64 ? 64 : (S < 1 ? 1 : S); }
+// scratch layout, 4096 doubles per frame: partials [S <= 63][32][2] | (mean, rstd) float2 [32] | arrival counter
+static int gn_splits(int HW) { int S = HW / 8; return S > 63 ? 63 : (S < 1 ? 1 : S); }
 
 int gn_stats_launch(const float* x, int F, int HW, int C, double* part, cudaStream_t s) {
     if (C % 32 || C > 768 || C < 96) return -30;
@@ -163,54 +194,41 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     __shared__ float rstd[32];
     const int f = blockIdx.y, tid = threadIdx.x;
     const int cg = C >> 5;
-    {
-        // 8 threads per group add the per-split partial sums (fixed order: deterministic), then combine by shuffle
-        const int grp = tid >> 3, part = tid & 7;
-        double sm = 0.0, sq = 0.0;
-        for (int k = part; k < S; k += 8) {
-            const double* o = part_sums + (((size_t)f * S + k) * 32 + grp) * 2;
-            sm += o[0];
-            sq += o[1];
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            sm += __shfl_xor_sync(0xffffffffu, sm, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        }
-        if (part == 0) {
-            const double n = (double)HW * cg;
-            const double m = sm / n;
-            double v = sq / n - m * m;
-            if (v < 0.0) v = 0.0;
-            mean[grp] = (float)m;
-            rstd[grp] = (float)(1.0 / sqrt(v + 1e-6));
-        }
+    if (tid < 32) {
+        const float2 v = reinterpret_cast<const float2*>(part_sums + (size_t)f * 4096 + 4032)[tid];
+        mean[tid] = v.x;
+        rstd[tid] = v.y;
     }
     __syncthreads();
+    // gridDim.x * 256 is a multiple of C / 4 (launch picks gridDim.x % 3 == 0), so a thread keeps one 4-channel vector
+    // for its whole walk: the affine (x * a + b) of its channels is hoisted out of the loop
     const int cv_n = C >> 2;
-    const long total = (long)HW * cv_n;
-    const size_t fb = (size_t)f * HW * C;
-    for (long i = (long)blockIdx.x * 256 + tid; i < total; i += (long)gridDim.x * 256) {
-        const int cv = (int)(i % cv_n);
-        const float4 v = reinterpret_cast<const float4*>(x + fb)[i];
-        const float4 g = reinterpret_cast<const float4*>(gamma)[cv];
-        const float4 bt = reinterpret_cast<const float4*>(beta)[cv];
-        const int c = 4 * cv;
-        const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
-        const float a0 = swishf((v.x - mean[g0]) * rstd[g0] * g.x + bt.x);
-        const float a1 = swishf((v.y - mean[g1]) * rstd[g1] * g.y + bt.y);
-        const float a2 = swishf((v.z - mean[g2]) * rstd[g2] * g.z + bt.z);
-        const float a3 = swishf((v.w - mean[g3]) * rstd[g3] * g.w + bt.w);
-        reinterpret_cast<uint2*>(out_act + fb)[i] = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
-        if (out_raw) reinterpret_cast<uint2*>(out_raw + fb)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const int total = HW * cv_n;
+    const int i0 = blockIdx.x * 256 + tid, stride = gridDim.x * 256;
+    const int cv = i0 % cv_n, c = 4 * cv;
+    const float4 g = reinterpret_cast<const float4*>(gamma)[cv];
+    const float4 bt = reinterpret_cast<const float4*>(beta)[cv];
+    const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
+    const float ax = rstd[g0] * g.x, ay = rstd[g1] * g.y, az = rstd[g2] * g.z, aw = rstd[g3] * g.w;
+    const float bx = fmaf(-mean[g0], ax, bt.x), by = fmaf(-mean[g1], ay, bt.y), bz = fmaf(-mean[g2], az, bt.z),
+                bw = fmaf(-mean[g3], aw, bt.w);
+    const float4* xin = reinterpret_cast<const float4*>(x + (size_t)f * HW * C);
+    uint2* oa = reinterpret_cast<uint2*>(out_act + (size_t)f * HW * C);
+    uint2* orw = out_raw ? reinterpret_cast<uint2*>(out_raw + (size_t)f * HW * C) : nullptr;
+#pragma unroll 4
+    for (int i = i0; i < total; i += stride) {
+        const float4 v = xin[i];
+        oa[i] = make_uint2(pack_bf16x2(swishf(fmaf(v.x, ax, bx)), swishf(fmaf(v.y, ay, by))),
+                           pack_bf16x2(swishf(fmaf(v.z, az, bz)), swishf(fmaf(v.w, aw, bw))));
+        if (orw) orw[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
 
 int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, const float* gamma, const float* beta,
                     bf16* out_act, bf16* out_raw, cudaStream_t s) {
     long total = (long)HW * (C / 4);
-    int gx = (int)((total + 255) / 256);
-    if (gx > 296) gx = 296;
+    int gx = (int)((total + 767) / 768) * 3;             // multiple of 3: 768 threads cover whole C/4 periods
+    if (gx > 297) gx = 297;
     gn_apply_kernel<<<dim3(gx, F), 256, 0, s>>>(x, HW, C, gn_splits(HW), acc, gamma, beta, out_act, out_raw);
     DSB_LAUNCH_CHECK();
 }
@@ -300,78 +318,92 @@ int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cud
     DSB_LAUNCH_CHECK();
 }
 
-// ------------------------------------------------------------------------------------------ LayerNorm (warp / token)
-template <int NV>
-__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, long tokens, float2* stats, int hw,
-                                                      int T, int tmax) {
-    constexpr int C = NV * 32;
-    const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tok >= tokens) return;
-    if ((int)((tok / hw) % T) >= tmax) return;
-    const float* row = x + tok * C;
-    float v[NV];
-    float s = 0.0f;
+// ------------------------------------------------------------------------------------------ LayerNorm over channels
+// A token's C channels are read as float4 by LPT lanes (8 / 16 / 32 lanes for C = 96 / 192 / >= 384), so a warp covers
+// 4 / 2 / 1 tokens with 48-96 bytes in flight per lane; statistics are two-pass (mean, then centred squares) in fp32.
+template <int C>
+struct LnGeom {
+    static constexpr int V = C / 4;
+    static constexpr int LPT = (C == 96) ? 8 : ((C == 192) ? 16 : 32);
+    static constexpr int NVEC = V / LPT;
+    static constexpr int TPW = 32 / LPT;
+};
+
+template <int LPT>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { v[i] = row[lane + 32 * i]; s += v[i]; }
-    const float mean = warp_sum(s) * (1.0f / C);
-    float q = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float var = warp_sum(q) * (1.0f / C);
-    if (lane == 0) stats[tok] = make_float2(mean, rsqrtf(var + 1e-5f));
+    for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, int T, int tmax, cudaStream_t s) {
-    const int g = (int)((tokens + 7) / 8);
+template <int C, bool APPLY>
+__global__ void __launch_bounds__(256) ln_vec_kernel(const float* __restrict__ x, long tokens, float2* __restrict__ stats,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    bf16* __restrict__ out, int hw, int T, int tmax) {
+    using G = LnGeom<C>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / G::LPT, l = lane % G::LPT;
+    const long tok = ((long)blockIdx.x * 8 + warp) * G::TPW + sub;
+    const bool live = tok < tokens && (int)((tok / hw) % T) < tmax;
+    float4 v[G::NVEC];
+    const float4* row = reinterpret_cast<const float4*>(x + (live ? tok : 0) * C);
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < G::NVEC; ++i) {
+        v[i] = live ? row[l + G::LPT * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = group_sum<G::LPT>(s) * (1.0f / C);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < G::NVEC; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(group_sum<G::LPT>(q) * (1.0f / C) + 1e-5f);
+    if (!live) return;
+    if constexpr (APPLY) {
+        uint2* o = reinterpret_cast<uint2*>(out + tok * C);
+        const float4* g4 = reinterpret_cast<const float4*>(gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+        for (int i = 0; i < G::NVEC; ++i) {
+            const float4 g = g4[l + G::LPT * i], b = b4[l + G::LPT * i];
+            o[l + G::LPT * i] = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                                           pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+        }
+    } else {
+        if (l == 0) stats[tok] = make_float2(mean, rstd);
+    }
+}
+
+template <bool APPLY>
+static int ln_vec_launch(const float* x, long tokens, int C, float2* stats, const float* gamma, const float* beta, bf16* out,
+                         int hw, int T, int tmax, cudaStream_t s) {
+#define DSB_LN_CASE(CC)                                                                                              \
+    case CC: {                                                                                                       \
+        const int g = (int)((tokens + 8 * LnGeom<CC>::TPW - 1) / (8 * LnGeom<CC>::TPW));                              \
+        ln_vec_kernel<CC, APPLY><<<g, 256, 0, s>>>(x, tokens, stats, gamma, beta, out, hw, T, tmax);                  \
+        break;                                                                                                       \
+    }
     switch (C) {
-        case 96: ln_stats_kernel<3><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
-        case 192: ln_stats_kernel<6><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
-        case 384: ln_stats_kernel<12><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
-        case 768: ln_stats_kernel<24><<<g, 256, 0, s>>>(x, tokens, stats, hw, T, tmax); break;
+        DSB_LN_CASE(96)
+        DSB_LN_CASE(192)
+        DSB_LN_CASE(384)
+        DSB_LN_CASE(768)
         default: return -31;
     }
+#undef DSB_LN_CASE
     DSB_LAUNCH_CHECK();
 }
 
-template <int NV>
-__global__ void __launch_bounds__(256) ln_apply_kernel(const float* __restrict__ x, long tokens,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      bf16* __restrict__ out, int hw, int T, int tmax) {
-    constexpr int C = NV * 32;
-    const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tok >= tokens) return;
-    if ((int)((tok / hw) % T) >= tmax) return;
-    const float* row = x + tok * C;
-    float v[NV];
-    float s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { v[i] = row[lane + 32 * i]; s += v[i]; }
-    const float mean = warp_sum(s) * (1.0f / C);
-    float q = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
-    bf16* o = out + tok * C;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        o[c] = __float2bfloat16((v[i] - mean) * rstd * gamma[c] + beta[c]);
-    }
+int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, int T, int tmax, cudaStream_t s) {
+    return ln_vec_launch<false>(x, tokens, C, stats, nullptr, nullptr, nullptr, hw, T, tmax, s);
 }
 
 int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
                     int T, int tmax, cudaStream_t s) {
-    const int g = (int)((tokens + 7) / 8);
-    switch (C) {
-        case 96: ln_apply_kernel<3><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
-        case 192: ln_apply_kernel<6><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
-        case 384: ln_apply_kernel<12><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
-        case 768: ln_apply_kernel<24><<<g, 256, 0, s>>>(x, tokens, gamma, beta, out, hw, T, tmax); break;
-        default: return -31;
-    }
-    DSB_LAUNCH_CHECK();
+    return ln_vec_launch<true>(x, tokens, C, nullptr, gamma, beta, out, hw, T, tmax, s);
 }
 
 // ------------------------------------------------------------------------------------------ q = LN(dw3x3(LN(x)))
@@ -454,18 +486,22 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
     }
 }
 
-// Shared-memory tiled variant for the narrow, token-rich stages (C = 96, 192): a block stages the LayerNormed inputs
-// of 3 rows x (XT + 2) tokens once (normalisation applied while loading), then each warp produces tokens from shared
-// memory -- every input element is loaded from L2 ~3 times instead of 9 and normalised once instead of 9 times.
-template <int NV, int XT>
+// Shared-memory tiled variant for the narrow, token-rich stages (C = 96, 192).  A block owns XT tokens of one image row
+// and stages the LayerNormed inputs of the 3 x (XT + 2) neighbourhood once (normalised while loading; zero outside the
+// image = the conv's zero padding of LN(x)).  Both phases use the LnGeom layout: LPT lanes x 3 float4 cover a token,
+// so a warp works on 4 (C = 96) or 2 (C = 192) tokens at a time with 128-bit shared/global accesses and the channel
+// LayerNorm of the conv output is a shuffle reduction inside the LPT lanes.  (The scalar one-token-per-warp version was
+// issue-bound: ~150 warp instructions per token against ~50 here.)
+template <int C, int XT>
 __global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
                                                           int H, int W, const float* __restrict__ ng,
                                                           const float* __restrict__ nb, const float* __restrict__ wq,
                                                           const float* __restrict__ qg, const float* __restrict__ qb,
                                                           bf16* __restrict__ out, int T, int tmax) {
-    constexpr int C = NV * 32;
-    constexpr int TW = XT + 2;
-    extern __shared__ float tile[];                      // [3][TW][C]
+    using G = LnGeom<C>;
+    static_assert(G::NVEC == 3 && XT == 8 * G::TPW, "tile geometry");
+    constexpr int TW = XT + 2, CV = C / 4, NT = 3 * TW, PER = 8 * G::TPW, NPASS = (NT + PER - 1) / PER;
+    extern __shared__ float4 tile4[];                    // [3][TW][CV]
     const int nseg = W / XT;
     const int seg = blockIdx.x % nseg;
     const int y = (blockIdx.x / nseg) % H;
@@ -473,60 +509,82 @@ __global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restri
     if (f % T >= tmax) return;
     const int x0 = seg * XT;
     const size_t fbase = (size_t)f * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / G::LPT, l = lane % G::LPT;
+    const int slot = warp * G::TPW + sub;                // token slot of this lane group, 0 .. PER-1
+    const float4* x4 = reinterpret_cast<const float4*>(x);
     {
-        // one token per warp iteration: statistics loaded once, affine parameters in registers, coalesced row loads
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        float g[NV], b[NV];
+        float4 v[NPASS][3];
+        float2 st[NPASS];
+        bool ok[NPASS];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { g[i] = ng[lane + 32 * i]; b[i] = nb[lane + 32 * i]; }
-        for (int t = warp; t < 3 * TW; t += 8) {
-            const int col = t % TW, r = t / TW;
+        for (int p = 0; p < NPASS; ++p) {
+            const int t = slot + p * PER;
+            const int r = t / TW, col = t % TW;
             const int yy = y + r - 1, xx = x0 + col - 1;
-            float* dst = tile + t * C;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                const size_t tok = fbase + (size_t)yy * W + xx;
-                const float2 st = stats[tok];
-                const float* row = x + tok * C;
+            ok[p] = t < NT && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const size_t tok = ok[p] ? fbase + (size_t)yy * W + xx : fbase;
+            st[p] = stats[tok];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = (row[lane + 32 * i] - st.x) * st.y * g[i] + b[i];
-            } else {
+            for (int i = 0; i < 3; ++i) v[p][i] = x4[tok * CV + l + G::LPT * i];
+        }
+        float4 g[3], b[3];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) dst[lane + 32 * i] = 0.0f;
+        for (int i = 0; i < 3; ++i) {
+            g[i] = reinterpret_cast<const float4*>(ng)[l + G::LPT * i];
+            b[i] = reinterpret_cast<const float4*>(nb)[l + G::LPT * i];
+        }
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) {
+            const int t = slot + p * PER;
+            if (t < NT) {
+                const float m = st[p].x, rs = ok[p] ? st[p].y : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok[p])
+                        o = make_float4((v[p][i].x - m) * rs * g[i].x + b[i].x, (v[p][i].y - m) * rs * g[i].y + b[i].y,
+                                        (v[p][i].z - m) * rs * g[i].z + b[i].z, (v[p][i].w - m) * rs * g[i].w + b[i].w);
+                    tile4[t * CV + l + G::LPT * i] = o;
+                }
             }
         }
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float wt[9][NV], gq[NV], bq[NV];
+    const float4* w4 = reinterpret_cast<const float4*>(wq);
+    float4 q[3];
+    float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        gq[i] = qg[c]; bq[i] = qb[c];
+    for (int i = 0; i < 3; ++i) {
+        const int cvi = l + G::LPT * i;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wt[k][i] = wq[k * C + c];
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 tv = tile4[(r * TW + slot + k) * CV + cvi];
+                const float4 wv = __ldg(w4 + (r * 3 + k) * CV + cvi);
+                a.x = fmaf(wv.x, tv.x, a.x); a.y = fmaf(wv.y, tv.y, a.y);
+                a.z = fmaf(wv.z, tv.z, a.z); a.w = fmaf(wv.w, tv.w, a.w);
+            }
+        q[i] = a;
+        s += (a.x + a.y) + (a.z + a.w);
     }
-    for (int tk = warp; tk < XT; tk += 8) {
-        float q[NV];
-        float s = 0.0f;
+    const float mean = group_sum<G::LPT>(s) * (1.0f / C);
+    float v2 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            float a = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+        const float a = q[i].x - mean, b = q[i].y - mean, c = q[i].z - mean, d = q[i].w - mean;
+        v2 = fmaf(a, a, v2); v2 = fmaf(b, b, v2); v2 = fmaf(c, c, v2); v2 = fmaf(d, d, v2);
+    }
+    const float rstd = rsqrtf(group_sum<G::LPT>(v2) * (1.0f / C) + 1e-5f);
+    uint2* o = reinterpret_cast<uint2*>(out + (fbase + (size_t)y * W + x0 + slot) * C);
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) a = fmaf(wt[r * 3 + k][i], tile[(r * TW + tk + k) * C + c], a);
-            q[i] = a;
-            s += a;
-        }
-        const float mean = warp_sum(s) * (1.0f / C);
-        float v2 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) { const float d = q[i] - mean; v2 = fmaf(d, d, v2); }
-        const float rstd = rsqrtf(warp_sum(v2) * (1.0f / C) + 1e-5f);
-        bf16* o = out + (fbase + (size_t)y * W + x0 + tk) * C;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) o[lane + 32 * i] = __float2bfloat16((q[i] - mean) * rstd * gq[i] + bq[i]);
+    for (int i = 0; i < 3; ++i) {
+        const int cvi = l + G::LPT * i;
+        const float4 gq = __ldg(reinterpret_cast<const float4*>(qg) + cvi), bq = __ldg(reinterpret_cast<const float4*>(qb) + cvi);
+        o[cvi] = make_uint2(pack_bf16x2((q[i].x - mean) * rstd * gq.x + bq.x, (q[i].y - mean) * rstd * gq.y + bq.y),
+                            pack_bf16x2((q[i].z - mean) * rstd * gq.z + bq.z, (q[i].w - mean) * rstd * gq.w + bq.w));
     }
 }
 
@@ -535,11 +593,11 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
     const long tokens = (long)F * H * W;
     const int g = (int)((tokens + 7) / 8);
     if (C == 96 && W % 32 == 0) {
-        q_dwln_tiled_kernel<3, 32><<<F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        q_dwln_tiled_kernel<96, 32><<<F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
         DSB_LAUNCH_CHECK();
     }
     if (C == 192 && W % 16 == 0) {
-        q_dwln_tiled_kernel<6, 16><<<F * H * (W / 16), 256, 3 * 18 * 192 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        q_dwln_tiled_kernel<192, 16><<<F * H * (W / 16), 256, 3 * 18 * 192 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
         DSB_LAUNCH_CHECK();
     }
     switch (C) {
