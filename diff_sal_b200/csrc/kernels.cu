@@ -623,34 +623,16 @@ __device__ __forceinline__ void pooled_ln_store(const float* pre, int C, const f
     for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2bfloat16((pre[c] - mean) * rstd * g[c] + b[c]);
 }
 
-// Accumulates pre[c] = sum_p src(p, c) over the s*s window into sm[0..C).  Threads are laid out as
-// channels x pixel-groups when C <= blockDim (partials combined through smem), else channels are looped.
-template <class Src>
-__device__ __forceinline__ void pool_accumulate(const Src& src, int C, int npx, float* sm) {
-    const int nthr = blockDim.x, tid = threadIdx.x;
-    if (C <= nthr) {
-        const int G = nthr / C;
-        const int c = tid % C, gq = tid / C;
-        float acc = 0.0f;
-        if (gq < G) {
-            for (int p = gq; p < npx; p += G) acc += src(p, c);
-            sm[gq * C + c] = acc;
-        }
-        __syncthreads();
-        float a = 0.0f;
-        if (tid < C)
-            for (int k = 0; k < G; ++k) a += sm[k * C + tid];
-        __syncthreads();
-        if (tid < C) sm[tid] = a;
-        __syncthreads();
-    } else {
-        for (int c = tid; c < C; c += nthr) {
-            float acc = 0.0f;
-            for (int p = 0; p < npx; ++p) acc += src(p, c);
-            sm[c] = acc;
-        }
-        __syncthreads();
+// part[G][C] (one partial row per pixel group) -> pre[C] in part[0], groups added in index order
+__device__ __forceinline__ void pool_fold_groups(float* sm, int C, int G) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        float a = sm[c];
+        for (int k = 1; k < G; ++k) a += sm[k * C + c];
+        sm[c] = a;                                        // element c of row 0 is only touched by this thread
     }
+    __syncthreads();
 }
 
 // one block per pooled token (f, Y, X)
@@ -665,26 +647,43 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
     if (f % T >= tmax) return;
     const size_t fbase = (size_t)f * H * W;
     const int sl = 31 - __clz(s_);                       // s is a power of two (2, 4, 8, 16)
-    const float* xw = x + (fbase + (size_t)(Y * s_) * W + X * s_) * C;
+    const int CV = C >> 2, tid = threadIdx.x;
+    const int G = blockDim.x / CV;                       // pixel groups; thread = (4-channel vector, pixel group)
+    const int c4 = tid % CV, gq = tid / CV;
+    const float4* xw = reinterpret_cast<const float4*>(x + (fbase + (size_t)(Y * s_) * W + X * s_) * C) + c4;
     const float2* sw = stats + fbase + (size_t)(Y * s_) * W + X * s_;
-    auto src = [&](int p, int c) -> float {
-        const int dy = p >> sl, dx = p & (s_ - 1);
-        const int t = dy * W + dx;
-        const float2 st = sw[t];
-        return wv[p * C + c] * ((xw[(size_t)t * C + c] - st.x) * st.y * ng[c] + nb[c]);
-    };
-    pool_accumulate(src, C, s_ * s_, sm);
+    const float4* w4 = reinterpret_cast<const float4*>(wv) + c4;
+    if (gq < G) {
+        const float4 g = reinterpret_cast<const float4*>(ng)[c4], bb = reinterpret_cast<const float4*>(nb)[c4];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int npx = s_ * s_;
+#pragma unroll 4
+        for (int p = gq; p < npx; p += G) {
+            const int t = (p >> sl) * W + (p & (s_ - 1));
+            const float2 st = sw[t];
+            const float4 v = xw[(size_t)t * CV];
+            const float4 w = __ldg(w4 + p * CV);
+            acc.x = fmaf(w.x, (v.x - st.x) * st.y * g.x + bb.x, acc.x);
+            acc.y = fmaf(w.y, (v.y - st.x) * st.y * g.y + bb.y, acc.y);
+            acc.z = fmaf(w.z, (v.z - st.x) * st.y * g.z + bb.z, acc.z);
+            acc.w = fmaf(w.w, (v.w - st.x) * st.y * g.w + bb.w, acc.w);
+        }
+        reinterpret_cast<float4*>(sm)[gq * CV + c4] = acc;
+    }
+    pool_fold_groups(sm, C, G);
     pooled_ln_store(sm, C, vg, vb, out + (size_t)tokv * C, red);
 }
 
-static int pool_threads(int C) { return C <= 384 ? 768 : 768; }   // channels x pixel groups (G = 768 / C)
+// (C / 4) channel vectors x pixel groups; 256-thread blocks keep >= 5 blocks resident per SM (768-thread blocks were
+// register-limited to one per SM and ran ~9 serial waves of sync-heavy work)
+static int pool_threads(int C) { (void)C; return 256; }
 
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
                    const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, int T, int tmax,
                    cudaStream_t s) {
     const int nthr = pool_threads(C);
-    const int G = (C <= nthr) ? nthr / C : 1;
-    const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
+    if (C % 4 || C / 4 > nthr) return -34;
+    const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
     pool_ln_kernel<<<F * 18, nthr, smem, s>>>(x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax);
     DSB_LAUNCH_CHECK();
 }
@@ -692,25 +691,33 @@ int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int
 // ------------------------------------------------------------------------------------------ audio gate
 // one block per (y, b, 32-channel chunk): m[x][c] = mean_t a*x ; softmax over x ; g written as [b][c][y][x]
 __global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ x, const float* __restrict__ a_low,
-                                                     int T, int H, int W, int C, float* __restrict__ g) {
+                                                     int T, int H, int W, int C, int rshift, float* __restrict__ g) {
     __shared__ float m[96 * 33];           // [W][33]
     const int y = blockIdx.x, b = blockIdx.y, c0 = blockIdx.z * 32;
-    const int r = H / 7;
     const float invT = 1.0f / (float)T;
-    for (int e = threadIdx.x; e < W * 32; e += 256) {
-        const int c = e & 31, xx = e >> 5;
-        float acc = 0.0f;
-        const float* xp = x + ((((size_t)b * T) * H + y) * W + xx) * C + c0 + c;
-        const float* ap = a_low + ((((size_t)b * T) * 7 + y / r) * 12 + xx / r) * C + c0 + c;
-        const size_t xs = (size_t)H * W * C, as = (size_t)84 * C;
+    const int CV = C >> 2;
+    // thread = (pixel, 4-channel vector): 8 lanes cover the block's 32 channels with 128-bit loads
+    for (int e = threadIdx.x; e < W * 8; e += 256) {
+        const int c4 = e & 7, xx = e >> 3;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* xp = reinterpret_cast<const float4*>(x) + ((((size_t)b * T) * H + y) * W + xx) * CV + (c0 >> 2) + c4;
+        const float4* ap = reinterpret_cast<const float4*>(a_low) +
+                           ((((size_t)b * T) * 7 + (y >> rshift)) * 12 + (xx >> rshift)) * CV + (c0 >> 2) + c4;
+        const int xs = H * W * CV, as = 84 * CV;
         int t = 0;
         for (; t + 3 <= T; t += 3) {                       // 6 independent loads in flight
-            const float x0 = xp[(size_t)t * xs], x1 = xp[(size_t)(t + 1) * xs], x2 = xp[(size_t)(t + 2) * xs];
-            const float a0 = ap[(size_t)t * as], a1 = ap[(size_t)(t + 1) * as], a2 = ap[(size_t)(t + 2) * as];
-            acc = fmaf(a0, x0, acc); acc = fmaf(a1, x1, acc); acc = fmaf(a2, x2, acc);
+            const float4 x0 = xp[t * xs], x1 = xp[(t + 1) * xs], x2 = xp[(t + 2) * xs];
+            const float4 a0 = __ldg(ap + t * as), a1 = __ldg(ap + (t + 1) * as), a2 = __ldg(ap + (t + 2) * as);
+            acc.x = fmaf(a0.x, x0.x, acc.x); acc.y = fmaf(a0.y, x0.y, acc.y); acc.z = fmaf(a0.z, x0.z, acc.z); acc.w = fmaf(a0.w, x0.w, acc.w);
+            acc.x = fmaf(a1.x, x1.x, acc.x); acc.y = fmaf(a1.y, x1.y, acc.y); acc.z = fmaf(a1.z, x1.z, acc.z); acc.w = fmaf(a1.w, x1.w, acc.w);
+            acc.x = fmaf(a2.x, x2.x, acc.x); acc.y = fmaf(a2.y, x2.y, acc.y); acc.z = fmaf(a2.z, x2.z, acc.z); acc.w = fmaf(a2.w, x2.w, acc.w);
         }
-        for (; t < T; ++t) acc = fmaf(ap[(size_t)t * as], xp[(size_t)t * xs], acc);
-        m[xx * 33 + c] = acc * invT;
+        for (; t < T; ++t) {
+            const float4 x0 = xp[t * xs], a0 = __ldg(ap + t * as);
+            acc.x = fmaf(a0.x, x0.x, acc.x); acc.y = fmaf(a0.y, x0.y, acc.y); acc.z = fmaf(a0.z, x0.z, acc.z); acc.w = fmaf(a0.w, x0.w, acc.w);
+        }
+        float* mp = m + xx * 33 + 4 * c4;
+        mp[0] = acc.x * invT; mp[1] = acc.y * invT; mp[2] = acc.z * invT; mp[3] = acc.w * invT;
     }
     __syncthreads();
     {   // softmax over x: 8 threads per channel, shuffle-reduced
@@ -720,116 +727,98 @@ __global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ 
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float sum = 0.0f;
-        for (int xx = part; xx < W; xx += 8) { const float e = expf(m[xx * 33 + c] - mx); m[xx * 33 + c] = e; sum += e; }
+        for (int xx = part; xx < W; xx += 8) { const float e = __expf(m[xx * 33 + c] - mx); m[xx * 33 + c] = e; sum += e; }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float inv = 1.0f / sum;
         for (int xx = part; xx < W; xx += 8) m[xx * 33 + c] *= inv;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < W * 32; e += 256) {
-        const int xx = e % W, c = e / W;
-        g[(((size_t)b * C + c0 + c) * H + y) * W + xx] = m[xx * 33 + c];
+    const int WQ = W >> 2;                 // W is 12, 24, 48 or 96
+    for (int e = threadIdx.x; e < WQ * 32; e += 256) {
+        const int q = e % WQ, c = e / WQ;
+        const float* mp = m + (4 * q) * 33 + c;
+        reinterpret_cast<float4*>(g + (((size_t)b * C + c0 + c) * H + y) * W)[q] = make_float4(mp[0], mp[33], mp[66], mp[99]);
     }
 }
 
 int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s) {
-    if (W > 96 || C % 32) return -33;
-    av_gate_kernel<<<dim3(H, B, C / 32), 256, 0, s>>>(x, a_low, T, H, W, C, g);
+    if (W > 96 || C % 32 || W % 4) return -33;
+    const int r = H / 7;
+    int rshift = 0;
+    while ((1 << rshift) < r) ++rshift;
+    if ((1 << rshift) != r || H != 7 * r || W != 12 * r) return -33;
+    av_gate_kernel<<<dim3(H, B, C / 32), 256, 0, s>>>(x, a_low, T, H, W, C, rshift, g);
     DSB_LAUNCH_CHECK();
 }
 
 // K source = raw reinterpretation of the contiguous [B][C][T][H][W] buffer (a*g) as [(B T)][H W][C]
 // (transformer.py:146) followed by 'b (h w) c -> b c h w' (attention.py:89): element (bt, pix', c') is the flat
 // element j = (bt % T)*HW*C + pix'*C + c' of clip b = bt / T, and flat j decodes to (c, t, pix) = [C][T][HW].
-template <int C, int H, int W, int S_>
-__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int T, int tmax,
+template <int C, int H, int W, int S_, int T_>
+__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int tmax,
                                 const float* __restrict__ wk, const float* __restrict__ kg,
                                 const float* __restrict__ kb, bf16* __restrict__ out) {
     extern __shared__ float sm[];
     __shared__ float red[32];
-    constexpr int HW = H * W;
-    constexpr int R = H / 7;
+    constexpr int HW = H * W, R = H / 7, CV = C / 4, THW = T_ * HW, NPX = S_ * S_;
+    static_assert(HW % 4 == 0 && W % 4 == 0 && C % 4 == 0, "4 consecutive flat indices stay inside one source row");
     const int tokv = blockIdx.x;                 // bt*18 + Y*6 + X
     const int bt = tokv / 18, Y = (tokv % 18) / 6, X = tokv % 6;
-    const int b = bt / T, tt = bt % T;
+    const int b = bt / T_, tt = bt % T_;
     if (tt >= tmax) return;
     const int clip_base = tt * HW * C;           // < 9 * 516096, fits int
-    const int THW = T * HW;
-    const int nthr = blockDim.x, tid = threadIdx.x;
-    // Thread (c, gq) walks window rows dy = gq, gq+G, ... and, inside a row, the S_ pixels dx.  The flat index of the
-    // scrambled source advances by C per dx, so (channel, frame, y, x) of the source are stepped with adds and carries
-    // (where C < HW: at most one carry per step) instead of being re-derived with divisions for every element.
-    constexpr int G_MAX = 4;
-    const int G = (C <= nthr) ? nthr / C : 1;
-    const float* a_b = a_low + (size_t)b * T * 84 * C;
+    const int tid = threadIdx.x;
+    // Thread (4-channel vector c4, pixel group gq).  Token (tt, pixel p') channel c of the reference's raw .view of the
+    // gated [C, T, H, W] clip is flat element j = (tt*HW + p')*C + c; 4 consecutive channels are 4 consecutive source
+    // pixels of one row (all extents are multiples of 4), so gate values come as one float4 and the audio map (nearest
+    // upsample by R) as 1, 2 or 4 scalars.  All divisors are compile-time.
+    const int G = blockDim.x / CV;
+    const int c4 = tid % CV, gq = tid / CV;
+    const float* a_b = a_low + (size_t)b * T_ * 84 * C;
     const float* g_b = g + (size_t)b * C * HW;
-    for (int c = (C <= nthr ? tid % C : tid), pass = 0; c < C && (C > nthr || pass == 0); c += nthr, ++pass) {
-        const int gq = (C <= nthr) ? tid / C : 0;
-        float acc = 0.0f;
-        if (gq < G) {
-            for (int dy = gq; dy < S_; dy += G) {
-                const int pixp = (Y * S_ + dy) * W + X * S_;
-                int j = clip_base + pixp * C + c;
-                int cs = j / THW;
-                int rem = j - cs * THW;
-                int ts = rem / HW;
-                int pix = rem - ts * HW;
-                int ys = pix / W, xs = pix - ys * W;
-                const float* wrow = wk + (dy * S_) * C + c;
-#pragma unroll 4
-                for (int dx = 0; dx < S_; ++dx) {
-                    const float av = a_b[(((size_t)ts * 7 + (ys / R)) * 12 + (xs / R)) * C + cs];
-                    const float gv = g_b[(size_t)cs * HW + pix];
-                    acc = fmaf(wrow[dx * C], av * gv, acc);
-                    if constexpr (C < HW) {
-                        // advance the flat source index by C with adds and carries
-                        pix += C;
-                        xs += C % W;
-                        ys += C / W;
-                        if (xs >= W) { xs -= W; ++ys; }
-                        if (pix >= HW) {
-                            pix -= HW; ys -= H;
-                            if (++ts == T) { ts = 0; ++cs; }
-                        }
-                    } else {
-                        // wide, small stages (C >= HW): several wraps per step, re-derive
-                        j += C;
-                        cs = j / THW;
-                        rem = j - cs * THW;
-                        ts = rem / HW;
-                        pix = rem - ts * HW;
-                        ys = pix / W;
-                        xs = pix - ys * W;
-                    }
-                }
+    if (gq < G) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int p = gq; p < NPX; p += G) {
+            const int dy = p / S_, dx = p % S_;
+            const int j = clip_base + ((Y * S_ + dy) * W + X * S_ + dx) * C + 4 * c4;
+            const int cs = j / THW, rem = j % THW;
+            const int ts = rem / HW, pix = rem % HW;
+            const int ys = pix / W, xs = pix % W;
+            const float4 gv = *reinterpret_cast<const float4*>(g_b + (size_t)cs * HW + pix);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wk) + p * CV + c4);
+            const float* ar = a_b + (((size_t)ts * 7 + (ys / R)) * 12) * C + cs;
+            float a0, a1, a2, a3;
+            if constexpr (R >= 4) {
+                a0 = a1 = a2 = a3 = ar[(xs / R) * C];
+            } else if constexpr (R == 2) {
+                a0 = a1 = ar[(xs / 2) * C];
+                a2 = a3 = ar[(xs / 2 + 1) * C];
+            } else {
+                a0 = ar[xs * C]; a1 = ar[(xs + 1) * C]; a2 = ar[(xs + 2) * C]; a3 = ar[(xs + 3) * C];
             }
-            if (C <= nthr) sm[gq * C + c] = acc; else sm[c] = acc;
+            acc.x = fmaf(w.x, a0 * gv.x, acc.x);
+            acc.y = fmaf(w.y, a1 * gv.y, acc.y);
+            acc.z = fmaf(w.z, a2 * gv.z, acc.z);
+            acc.w = fmaf(w.w, a3 * gv.w, acc.w);
         }
+        reinterpret_cast<float4*>(sm)[gq * CV + c4] = acc;
     }
-    (void)G_MAX;
-    __syncthreads();
-    if (C <= nthr && G > 1) {
-        float a = 0.0f;
-        if (tid < C)
-            for (int k = 0; k < G; ++k) a += sm[k * C + tid];
-        __syncthreads();
-        if (tid < C) sm[tid] = a;
-        __syncthreads();
-    }
+    pool_fold_groups(sm, C, G);
     pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
 }
 
 int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_, const float* wk,
                     const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s) {
     const int nthr = pool_threads(C);
-    const int G = (C <= nthr) ? nthr / C : 1;
-    const size_t smem = (size_t)(G > 1 ? G : 1) * C * sizeof(float);
+    if (T != 9 || C / 4 > nthr) return -34;
+    const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
     const int grid = B * T * 18;
-    if (C == 768 && H == 7 && W == 12 && s_ == 2) kpool_av_kernel<768, 7, 12, 2><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
-    else if (C == 384 && H == 14 && W == 24 && s_ == 4) kpool_av_kernel<384, 14, 24, 4><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
-    else if (C == 192 && H == 28 && W == 48 && s_ == 8) kpool_av_kernel<192, 28, 48, 8><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
-    else if (C == 96 && H == 56 && W == 96 && s_ == 16) kpool_av_kernel<96, 56, 96, 16><<<grid, nthr, smem, s>>>(g, a_low, T, tmax, wk, kg, kb, out);
+    if (C == 768 && H == 7 && W == 12 && s_ == 2) kpool_av_kernel<768, 7, 12, 2, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 384 && H == 14 && W == 24 && s_ == 4) kpool_av_kernel<384, 14, 24, 4, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 192 && H == 28 && W == 48 && s_ == 8) kpool_av_kernel<192, 28, 48, 8, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 96 && H == 56 && W == 96 && s_ == 16) kpool_av_kernel<96, 56, 96, 16, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
     else return -34;
     DSB_LAUNCH_CHECK();
 }
