@@ -390,6 +390,7 @@ static int ln_vec_launch(const float* x, long tokens, int C, float2* stats, cons
         DSB_LN_CASE(96)
         DSB_LN_CASE(192)
         DSB_LN_CASE(384)
+        DSB_LN_CASE(512)
         DSB_LN_CASE(768)
         default: return -31;
     }
@@ -1136,6 +1137,134 @@ int to_bf16_launch(const float* x, long n, bf16* out, cudaStream_t s) {
     if (g > 148 * 8) g = 148 * 8;
     if (g < 1) g = 1;
     to_bf16_kernel<<<(int)g, 256, 0, s>>>(x, n, out);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ audio transformer glue
+// (models/audio_attention.py:55-69) qkv [tokens][3 * 128] -> per-head operands of the two attention GEMMs:
+//   Qh [2][B][n][64] (pre-scaled by 64^-0.5 = 0.125, exact in bf16), Kh [2][B][npad][64], Vt [2][B][64][npad]
+// rows / columns n..npad-1 are never written (zeroed once at allocation).
+__global__ void __launch_bounds__(256) qkv_split_kernel(const bf16* __restrict__ qkv, int B, int n, int npad,
+                                                       bf16* __restrict__ Qh, bf16* __restrict__ Kh,
+                                                       bf16* __restrict__ Vt) {
+    __shared__ bf16 vt[32][130];
+    const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x;
+    const __nv_bfloat162 eighth = __floats2bfloat162_rn(0.125f, 0.125f);
+    // q, k: 32 tokens x 2 x 16 uint4 ; v: 32 tokens x 16 uint4 staged for the transpose
+    for (int e = tid; e < 32 * 48; e += 256) {
+        const int tk = e / 48, u = e % 48, tok = t0 + tk;
+        if (tok >= n) continue;
+        uint4 v = reinterpret_cast<const uint4*>(qkv + ((size_t)b * n + tok) * 384)[u];
+        const int part = u >> 4, hh = (u >> 3) & 1, d8 = u & 7;     // part: 0 q, 1 k, 2 v ; 8 uint4 per head
+        if (part == 0) {
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h2[i] = __hmul2(h2[i], eighth);
+            reinterpret_cast<uint4*>(Qh + (((size_t)hh * B + b) * n + tok) * 64)[d8] = v;
+        } else if (part == 1) {
+            reinterpret_cast<uint4*>(Kh + (((size_t)hh * B + b) * npad + tok) * 64)[d8] = v;
+        } else {
+            const bf16* e8 = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vt[tk][hh * 64 + d8 * 8 + i] = e8[i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 128 * 32; e += 256) {
+        const int tk = e & 31, r = e >> 5, tok = t0 + tk;          // r = head * 64 + d
+        if (tok < n) Vt[(((size_t)(r >> 6) * B + b) * 64 + (r & 63)) * npad + tok] = vt[tk][r];
+    }
+}
+
+int qkv_split_launch(const bf16* qkv, int B, int n, int npad, bf16* Qh, bf16* Kh, bf16* Vt, cudaStream_t s) {
+    qkv_split_kernel<<<dim3((n + 31) / 32, B), 256, 0, s>>>(qkv, B, n, npad, Qh, Kh, Vt);
+    DSB_LAUNCH_CHECK();
+}
+
+// softmax over the first `valid` of `ld` (= 768) columns of each fp32 row -> bf16 probabilities (padding columns 0)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long rows, int valid,
+                                                          bf16* __restrict__ P) {
+    constexpr int LD = 768, NV = LD / 128;               // 6 float4 per lane
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(S + row * LD);
+    float4 v[NV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = src[lane + 32 * i];
+        const int c = 4 * (lane + 32 * i);
+        if (c + 0 >= valid) v[i].x = -INFINITY;
+        if (c + 1 >= valid) v[i].y = -INFINITY;
+        if (c + 2 >= valid) v[i].z = -INFINITY;
+        if (c + 3 >= valid) v[i].w = -INFINITY;
+        mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i].x = __expf(v[i].x - mx); v[i].y = __expf(v[i].y - mx);
+        v[i].z = __expf(v[i].z - mx); v[i].w = __expf(v[i].w - mx);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    uint2* dst = reinterpret_cast<uint2*>(P + row * LD);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        dst[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x * inv, v[i].y * inv), pack_bf16x2(v[i].z * inv, v[i].w * inv));
+}
+
+int softmax_rows_launch(const float* S, long rows, int valid, int ld, bf16* P, cudaStream_t s) {
+    if (ld != 768 || valid < 1 || valid > ld) return -37;
+    softmax_rows_kernel<<<(int)((rows + 7) / 8), 256, 0, s>>>(S, rows, valid, P);
+    DSB_LAUNCH_CHECK();
+}
+
+// final LayerNorm of the audio transformer, written back channels-first: x [B][n][512] -> out [B][512][n]
+// (audio_attention.py:90,141: 'b (t h w) c -> b c t h w').  16 tokens per block through a padded smem tile.
+__global__ void __launch_bounds__(256) ln_nct_kernel(const float* __restrict__ x, int n, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ out) {
+    constexpr int C = 512;
+    __shared__ float tile[16][C + 1];
+    const int b = blockIdx.y, t0 = blockIdx.x * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int tk = warp; tk < 16; tk += 8) {
+        const int tok = t0 + tk;
+        if (tok >= n) continue;
+        const float4* row = reinterpret_cast<const float4*>(x + ((size_t)b * n + tok) * C);
+        float4 v[4];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = row[lane + 32 * i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        const float mean = warp_sum(s) * (1.0f / C);
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q = fmaf(a, a, q); q = fmaf(bb, bb, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c4 = lane + 32 * i;
+            const float4 g = reinterpret_cast<const float4*>(gamma)[c4], be = reinterpret_cast<const float4*>(beta)[c4];
+            float* d = &tile[tk][4 * c4];
+            d[0] = (v[i].x - mean) * rstd * g.x + be.x; d[1] = (v[i].y - mean) * rstd * g.y + be.y;
+            d[2] = (v[i].z - mean) * rstd * g.z + be.z; d[3] = (v[i].w - mean) * rstd * g.w + be.w;
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C * 16; e += 256) {
+        const int tk = e & 15, c = e >> 4, tok = t0 + tk;
+        if (tok < n) out[((size_t)b * C + c) * n + tok] = tile[tk][c];
+    }
+}
+
+int ln_nct_launch(const float* x, int B, int n, int C, const float* gamma, const float* beta, float* out, cudaStream_t s) {
+    if (C != 512) return -38;
+    ln_nct_kernel<<<dim3((n + 15) / 16, B), 256, 0, s>>>(x, n, gamma, beta, out);
     DSB_LAUNCH_CHECK();
 }
 

@@ -81,4 +81,10 @@ int audio_tokens_launch(const float* audio, int B, int T, bf16* out, cudaStream_
 // fp32 -> bf16 elementwise
 int to_bf16_launch(const float* x, long n, bf16* out, cudaStream_t s);
 
+// audio transformer glue (models/audio_attention.py:55-90): head split of the bias-free qkv projection, row softmax
+// over 756 of 768 columns, final LayerNorm written channels-first
+int qkv_split_launch(const bf16* qkv, int B, int n, int npad, bf16* Qh, bf16* Kh, bf16* Vt, cudaStream_t s);
+int softmax_rows_launch(const float* S, long rows, int valid, int ld, bf16* P, cudaStream_t s);
+int ln_nct_launch(const float* x, int B, int n, int C, const float* gamma, const float* beta, float* out, cudaStream_t s);
+
 }  // namespace dsb

@@ -67,6 +67,20 @@ def _bind(lib):
     lib.dsb_profile_denoise.restype = ci
     lib.dsb_profile_name.argtypes = [vp, ci]
     lib.dsb_profile_name.restype = ctypes.c_char_p
+    lib.dsb_audio_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.dsb_audio_create.restype = ci
+    lib.dsb_audio_destroy.argtypes = [vp]
+    lib.dsb_audio_destroy.restype = None
+    lib.dsb_audio_last_error.argtypes = [vp]
+    lib.dsb_audio_last_error.restype = ctypes.c_char_p
+    lib.dsb_audio_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.dsb_audio_load_weight.restype = ci
+    lib.dsb_audio_finalize.argtypes = [vp]
+    lib.dsb_audio_finalize.restype = ci
+    lib.dsb_audio_forward.argtypes = [vp, vp, vp, ci, vp]
+    lib.dsb_audio_forward.restype = ci
+    lib.dsb_audio_last_launch_count.argtypes = [vp]
+    lib.dsb_audio_last_launch_count.restype = ci
     lib._dsb_bound = True
     return lib
 
@@ -226,3 +240,67 @@ class Engine:
         with torch.cuda.device(self.device):
             n = self._check(self.lib.dsb_debug_read(self._h, name.encode(), _lib.ptr(buf), numel, _stream()), "debug")
         return buf[:n]
+
+
+class AudioEngine:
+    """Handle of the once-per-clip audio transformer (dsb_audio_*; models/audio_attention.py:93-143)."""
+
+    def __init__(self, max_batch=8, device=None):
+        if not torch.cuda.is_available():
+            raise DsbError("diff_sal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _bind(_lib.lib())
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_batch = int(max_batch)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.dsb_audio_create(self.max_batch, ctypes.byref(self._h))
+        if rc != 0:
+            raise DsbError("dsb_audio_create failed with %d (needs an sm_100 GPU)" % rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dsb_audio_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.dsb_audio_last_error(self._h)
+            raise DsbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def load_state_dict(self, state_dict, prefix=""):
+        """Loads an ``AudioAttnNet.state_dict()`` (optional container prefix such as 'module.spatiotemp_net.')."""
+        with torch.cuda.device(self.device):
+            for key, val in state_dict.items():
+                if prefix:
+                    if not key.startswith(prefix):
+                        continue
+                    key = key[len(prefix):]
+                t = val.detach().to(dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                self._check(self.lib.dsb_audio_load_weight(self._h, key.encode(), ctypes.c_void_p(t.data_ptr()), shape,
+                                                           t.dim()), "dsb_audio_load_weight(%s)" % key)
+            self._check(self.lib.dsb_audio_finalize(self._h), "dsb_audio_finalize")
+
+    def forward(self, audio):
+        """audio [B, 512, 9, 7, 12] -> same shape, fp32 on this engine's device."""
+        if audio.dim() != 5 or tuple(audio.shape[1:]) != (512, 9, 7, 12):
+            raise DsbError("audio features must be [B, 512, 9, 7, 12], got %s" % (tuple(audio.shape),))
+        B = audio.shape[0]
+        if B < 1 or B > self.max_batch:
+            raise DsbError("batch %d outside [1, %d]" % (B, self.max_batch))
+        a = audio.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(a)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_audio_forward(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                   B, _stream()), "dsb_audio_forward")
+        return out
+
+    @property
+    def last_launch_count(self):
+        return int(self.lib.dsb_audio_last_launch_count(self._h))

@@ -134,6 +134,44 @@ def make_state_dict(kind="wide", seed=0):
     return sd
 
 
+def audio_attn_state_dict_spec(depth=1):
+    """(key, shape) of ``AudioAttnNet(depth, heads=2, dim=512, mlp_dim=256, patch_dim=512, dim_head=64)`` in the
+    reference's registration order (models/audio_attention.py:96-130, cfgs/audio_visual.py:34-48)."""
+    spec = [("pos_embedding", (1, 1, 9, 1, 1)),
+            ("to_patch_embedding.0.weight", (512,)), ("to_patch_embedding.0.bias", (512,)),
+            ("to_patch_embedding.1.weight", (512, 512)), ("to_patch_embedding.1.bias", (512,)),
+            ("to_patch_embedding.2.weight", (512,)), ("to_patch_embedding.2.bias", (512,)),
+            ("transformer.norm.weight", (512,)), ("transformer.norm.bias", (512,))]
+    for i in range(depth):
+        a, f = "transformer.layers.%d.0." % i, "transformer.layers.%d.1." % i
+        spec += [(a + "norm.weight", (512,)), (a + "norm.bias", (512,)), (a + "to_qkv.weight", (384, 512)),
+                 (a + "to_out.0.weight", (512, 128)), (a + "to_out.0.bias", (512,)),
+                 (f + "net.0.weight", (512,)), (f + "net.0.bias", (512,)), (f + "net.1.weight", (256, 512)),
+                 (f + "net.1.bias", (256,)), (f + "net.4.weight", (512, 256)), (f + "net.4.bias", (512,))]
+    return spec
+
+
+def make_audio_attn_state_dict(seed=0, depth=1):
+    """'wide' random weights for the audio transformer: fan-in scaled linears, non-zero biases, randomised LayerNorm
+    affines (so that every term of every formula influences the output)."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    sd = {}
+    for key, shape in audio_attn_state_dict_spec(depth):
+        leaf = key.rsplit(".", 1)[-1]
+        is_norm = len(shape) == 1 and ("norm" in key or key.endswith("net.0.weight") or key.endswith("net.0.bias")
+                                       or "to_patch_embedding.0" in key or "to_patch_embedding.2" in key)
+        if key == "pos_embedding":
+            v = torch.randn(shape, generator=g)
+        elif is_norm:
+            v = (1.0 + 0.2 * torch.randn(shape, generator=g)) if leaf == "weight" else 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "bias":
+            v = 0.05 * torch.randn(shape, generator=g)
+        else:
+            v = torch.randn(shape, generator=g) * (1.0 / math.sqrt(shape[1]))
+        sd[key] = v.float().contiguous()
+    return sd
+
+
 def make_inputs(batch, audio=True, seed=1234):
     """Seeded synthetic clip batch: x_T, the four MViT-shaped feature tensors and the
     audio feature tensor.  Clip ``i`` uses generator seed ``seed + i`` so that a clip's

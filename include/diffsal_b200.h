@@ -23,6 +23,10 @@
  *   dsb_sample
  *        the whole loop: DiffusionTrainer.sample_ddim (diffusion_trainer.py:439-480) /
  *        DPM_Solver.sample(method="multistep") (sampler.py:1048-1247) as a program of EVAL / AXPY ops
+ *   dsb_audio_create / dsb_audio_load_weight / dsb_audio_finalize / dsb_audio_forward
+ *        AudioAttnNet.__init__ + load_state_dict + forward (models/audio_attention.py:93-143), the once-per-clip
+ *        audio transformer whose output VideoSaliencyModel.forward_vggish hands to the decoder
+ *        (models/diff_model.py:70-81,97-113) -- SURVEY.md 8f row N1
  */
 #ifndef DIFFSAL_B200_H
 #define DIFFSAL_B200_H
@@ -121,6 +125,21 @@ const char* dsb_profile_name(const dsb_handle* h, int i);
 /* copies an internal fp32 buffer to `dst` (device); names: "noise0".."noise2" ([B,hw,C] frame-8 slices),
  * "x0".."x3" (stage outputs [B*9,hw,C]), "r0".."r3" ([B,hw,768]), "p" ([B,112,192]).  Returns element count. */
 int64_t dsb_debug_read(dsb_handle* h, const char* name, float* dst, int64_t max_elems, void* stream);
+
+/* ---- once-per-clip audio transformer (models/audio_attention.py:93-143; cfgs/audio_visual.py:34-48) -------------
+ * Own opaque handle (weights + workspace for up to max_batch clips).  Weight keys are AudioAttnNet.state_dict()'s
+ * ("transformer.layers.0.0.to_qkv.weight", ...); to_patch_embedding.* / pos_embedding may be loaded but are unused,
+ * exactly as in the reference, whose forward discards the patch embedding (audio_attention.py:134-141).  Only the
+ * shipped geometry is accepted: dim 512, 2 heads x 64, mlp_dim 256, 9 x 7 x 12 tokens; depth is taken from the keys.
+ * audio / out: [B, 512, 9, 7, 12] fp32 device tensors (out may not alias audio). */
+typedef struct dsb_audio dsb_audio;
+int dsb_audio_create(int max_batch, dsb_audio** out);
+void dsb_audio_destroy(dsb_audio* h);
+const char* dsb_audio_last_error(const dsb_audio* h);
+int dsb_audio_load_weight(dsb_audio* h, const char* ref_key, const void* data, const int64_t* shape, int ndim);
+int dsb_audio_finalize(dsb_audio* h);
+int dsb_audio_forward(dsb_audio* h, const float* audio, float* out, int B, void* stream);
+int dsb_audio_last_launch_count(const dsb_audio* h);
 
 /* ---- single-kernel test entry (tests/test_kernels_gpu.py) ------------------------------------------------- */
 int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt, const void* A,

@@ -69,3 +69,21 @@ def test_visual_only_is_noise_invariant():
     a = salunet.forward(sd, x, torch.tensor([500]), feats, None)
     b = salunet.forward(sd, torch.randn_like(x), torch.tensor([3]), feats, None)
     assert torch.equal(a, b)
+
+
+def test_audio_attention():
+    """the once-per-clip audio transformer (models/audio_attention.py) against the reference fixture."""
+    from oracle import audio_attention
+    sd = synth.make_audio_attn_state_dict()
+    _, _, aud = synth.make_inputs(1, audio=True)
+    y = audio_attention.forward(sd, aud)
+    assert (y - gold("audio_attn_wide_b1")).abs().max().item() < 2e-5        # values reach +-6
+
+
+def test_audio_attention_feeds_decoder():
+    """diff_model.py:70-113: decoder conditioned on the transformer output, one evaluation at t = 500."""
+    from oracle import audio_attention
+    x, feats, aud = synth.make_inputs(1, audio=True)
+    emb = audio_attention.forward(synth.make_audio_attn_state_dict(), aud)
+    y = salunet.forward(synth.make_state_dict("wide"), x, torch.tensor([500]), feats, emb)
+    assert (y - gold("step_wide_av_attn_t500")).abs().max().item() < TOL

@@ -104,3 +104,30 @@ def test_metrics_match_reference():
         assert abs(rm.NSS(pred, fix) - metrics.nss(pred, fix)) < 1e-12
         assert abs(rm.CC(pred, dens) - metrics.cc(pred, dens)) < 1e-12
         assert abs(rm.SIM(pred, dens) - metrics.sim(pred, dens)) < 1e-12
+
+
+def _ref_audio_attn(depth=1):
+    ref_loader.load()
+    from models.audio_attention import AudioAttnNet
+    return AudioAttnNet(depth=depth, heads=2, dim=512, mlp_dim=256, patch_dim=512, num_patches=16, height=7, width=12,
+                        pool="cls", dim_head=64, dropout=0.0, emb_dropout=0.0).eval()
+
+
+def test_audio_attn_spec_matches_reference():
+    ref = _ref_audio_attn().state_dict()
+    spec = synth.audio_attn_state_dict_spec()
+    assert [k for k, _ in spec] == list(ref.keys())
+    for k, s in spec:
+        assert tuple(ref[k].shape) == tuple(s), k
+
+
+@pytest.mark.parametrize("depth,batch", [(1, 2), (2, 1)])
+def test_audio_attention_matches_reference(depth, batch):
+    from oracle import audio_attention
+    net = _ref_audio_attn(depth)
+    sd = synth.make_audio_attn_state_dict(seed=3, depth=depth)
+    net.load_state_dict(sd, strict=True)
+    _, _, aud = synth.make_inputs(batch, audio=True, seed=77)
+    with torch.no_grad():
+        ref = net(aud.clone())
+    assert (audio_attention.forward(sd, aud) - ref).abs().max().item() < 2e-5
