@@ -1268,4 +1268,87 @@ int ln_nct_launch(const float* x, int B, int n, int C, const float* gamma, const
     DSB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------ sampler correctors
+__global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ x, long n4, float lo, float hi) {
+    float4* x4 = reinterpret_cast<float4*>(x);
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+        float4 v = x4[i];
+        v.x = fminf(fmaxf(v.x, lo), hi); v.y = fminf(fmaxf(v.y, lo), hi);
+        v.z = fminf(fmaxf(v.z, lo), hi); v.w = fminf(fmaxf(v.w, lo), hi);
+        x4[i] = v;
+    }
+}
+
+int clamp_launch(float* x, long n, float lo, float hi, cudaStream_t s) {
+    if (n & 3) return -39;
+    long g = (n / 4 + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    clamp_kernel<<<(int)g, 256, 0, s>>>(x, n / 4, lo, hi);
+    DSB_LAUNCH_CHECK();
+}
+
+// DPM_Solver.dynamic_thresholding_fn (models/dpm_solver/sampler.py:417-426): per clip s = max(quantile(|x0|, p),
+// max_val); x0 = clamp(x0, -s, s) / s.  torch.quantile's 'linear' rule: rank = p * (n - 1) in fp32, value =
+// lerp(sorted[floor(rank)], sorted[ceil(rank)], frac(rank)); the host passes k = floor(rank) and w = frac(rank).
+// One block per clip: exact order statistics by a 4-pass radix select on the bit patterns of |x| (monotone for
+// non-negative floats), no sort.
+__global__ void __launch_bounds__(1024) dyn_threshold_kernel(float* __restrict__ x, int n, int k, float w, float max_val) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sh_prefix, sh_rank, sh_eq, sh_next;
+    float* xb = x + (size_t)blockIdx.x * n;
+    const int tid = threadIdx.x;
+    unsigned prefix = 0, mask = 0, rank = (unsigned)k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) {
+            const unsigned key = __float_as_uint(fabsf(xb[i]));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0;
+            int d = 0;
+            for (; d < 255; ++d) {
+                if (cum + hist[d] > rank) break;
+                cum += hist[d];
+            }
+            sh_prefix = prefix | ((unsigned)d << shift);
+            sh_rank = rank - cum;
+            sh_eq = hist[d];
+            sh_next = 0xffffffffu;
+        }
+        __syncthreads();
+        prefix = sh_prefix;
+        rank = sh_rank;
+        mask |= 255u << shift;
+    }
+    // prefix = bits of the k-th smallest |x|; rank = its index among the sh_eq elements equal to it
+    unsigned above = prefix;
+    if (w != 0.0f && rank + 1 >= sh_eq) {
+        unsigned mn = 0xffffffffu;
+        for (int i = tid; i < n; i += 1024) {
+            const unsigned key = __float_as_uint(fabsf(xb[i]));
+            if (key > prefix) mn = min(mn, key);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if ((tid & 31) == 0) atomicMin(&sh_next, mn);
+        __syncthreads();
+        above = sh_next == 0xffffffffu ? prefix : sh_next;
+    }
+    const float a = __uint_as_float(prefix), b = __uint_as_float(above);
+    // at::lerp: a + w * (b - a) for |w| < 0.5, else b - (b - a) * (1 - w)
+    const float diff = __fsub_rn(b, a);
+    const float q = (fabsf(w) < 0.5f) ? __fadd_rn(a, __fmul_rn(w, diff)) : __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, w)));
+    const float sc = fmaxf(q, max_val);
+    for (int i = tid; i < n; i += 1024) xb[i] = __fdiv_rn(fminf(fmaxf(xb[i], -sc), sc), sc);
+}
+
+int dyn_threshold_launch(float* x, int B, int n, int k, float w, float max_val, cudaStream_t s) {
+    if (k < 0 || k >= n || !(w >= 0.0f && w < 1.0f) || (w != 0.0f && k + 1 >= n)) return -40;
+    dyn_threshold_kernel<<<B, 1024, 0, s>>>(x, n, k, w, max_val);
+    DSB_LAUNCH_CHECK();
+}
+
 }  // namespace dsb

@@ -87,4 +87,8 @@ int qkv_split_launch(const bf16* qkv, int B, int n, int npad, bf16* Qh, bf16* Kh
 int softmax_rows_launch(const float* S, long rows, int valid, int ld, bf16* P, cudaStream_t s);
 int ln_nct_launch(const float* x, int B, int n, int C, const float* gamma, const float* beta, float* out, cudaStream_t s);
 
+// sampler correctors: in-place clamp (util/denoising.py:54) and DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426)
+int clamp_launch(float* x, long n, float lo, float hi, cudaStream_t s);
+int dyn_threshold_launch(float* x, int B, int n, int k, float w, float max_val, cudaStream_t s);
+
 }  // namespace dsb

@@ -845,6 +845,16 @@ extern "C" int dsb_sampler_update(dsb_handle* h, const float* coef, const float*
     return DSB_OK;
 }
 
+extern "C" int dsb_sampler_clamp(float* x, int64_t n, float lo, float hi, void* stream) {
+    if (!x || n < 4 || (n & 3) || !(lo <= hi)) return DSB_ERR_ARG;
+    return clamp_launch(x, (long)n, lo, hi, (cudaStream_t)stream) ? DSB_ERR_CUDA : DSB_OK;
+}
+
+extern "C" int dsb_sampler_dynamic_threshold(float* x, int B, int64_t n, int k, float w, float max_val, void* stream) {
+    if (!x || B < 1 || n < 2 || n > (1 << 30)) return DSB_ERR_ARG;
+    return dyn_threshold_launch(x, B, (int)n, k, w, max_val, (cudaStream_t)stream) ? DSB_ERR_ARG : DSB_OK;
+}
+
 static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cudaStream_t s) {
     const long n = (long)B * kMapElems;
     int eval_idx = 0;
@@ -868,6 +878,15 @@ static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cuda
             const float* nz = (op.noise_index >= 0 && d->noise) ? d->noise + (size_t)op.noise_index * n : nullptr;
             int r = axpy_launch(op.nin, ins, cs, nz, op.noise_coef, h->sbuf[op.dst], n, s);
             if (r) return fail(h, DSB_ERR_CUDA, "axpy launch failed (%d)", r);
+            h->last_launches += 1;
+        } else if (op.kind == DSB_OP_CLAMP) {
+            if (op.dst < 0 || op.dst > 7) return fail(h, DSB_ERR_ARG, "sampler op %d malformed", i);
+            if (int r = clamp_launch(h->sbuf[op.dst], n, op.coef[0], op.coef[1], s)) return fail(h, DSB_ERR_CUDA, "clamp launch failed (%d)", r);
+            h->last_launches += 1;
+        } else if (op.kind == DSB_OP_DYNTHRESH) {
+            if (op.dst < 0 || op.dst > 7) return fail(h, DSB_ERR_ARG, "sampler op %d malformed", i);
+            if (int r = dyn_threshold_launch(h->sbuf[op.dst], B, kMapElems, op.noise_index, op.coef[0], op.coef[1], s))
+                return fail(h, DSB_ERR_ARG, "dynamic thresholding launch failed (%d)", r);
             h->last_launches += 1;
         } else {
             return fail(h, DSB_ERR_ARG, "sampler op %d: unknown kind %d", i, op.kind);

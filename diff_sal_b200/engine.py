@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-OP_EVAL, OP_AXPY = 0, 1
+OP_EVAL, OP_AXPY, OP_CLAMP, OP_DYNTHRESH = 0, 1, 2, 3
 
 
 class DsbConfig(ctypes.Structure):
@@ -67,6 +67,10 @@ def _bind(lib):
     lib.dsb_profile_denoise.restype = ci
     lib.dsb_profile_name.argtypes = [vp, ci]
     lib.dsb_profile_name.restype = ctypes.c_char_p
+    lib.dsb_sampler_clamp.argtypes = [vp, ctypes.c_int64, cf, cf, vp]
+    lib.dsb_sampler_clamp.restype = ci
+    lib.dsb_sampler_dynamic_threshold.argtypes = [vp, ci, ctypes.c_int64, ci, cf, cf, vp]
+    lib.dsb_sampler_dynamic_threshold.restype = ci
     lib.dsb_audio_create.argtypes = [ci, ctypes.POINTER(vp)]
     lib.dsb_audio_create.restype = ci
     lib.dsb_audio_destroy.argtypes = [vp]
@@ -193,12 +197,18 @@ class Engine:
     # ------------------------------------------------------------------ whole loop
     def sample(self, ops, x, noise=None, use_graph=True):
         """Runs a sampler program (list of ('eval', t) / ('axpy', dst, [(src, coef), ...], noise_coef,
-        noise_index)) in place on x [B,1,224,384]."""
+        noise_index) / ('clamp', buf, lo, hi) / ('thresh', buf, k, w, max_val)) in place on x [B,1,224,384]."""
         arr = (DsbSamplerOp * len(ops))()
         for i, op in enumerate(ops):
             o = arr[i]
             if op[0] == "eval":
                 o.kind, o.t, o.noise_index = OP_EVAL, float(op[1]), -1
+            elif op[0] == "clamp":                      # ('clamp', buf, lo, hi)
+                o.kind, o.dst, o.noise_index = OP_CLAMP, int(op[1]), -1
+                o.coef[0], o.coef[1] = float(op[2]), float(op[3])
+            elif op[0] == "thresh":                     # ('thresh', buf, k, w, max_val)
+                o.kind, o.dst, o.noise_index = OP_DYNTHRESH, int(op[1]), int(op[2])
+                o.coef[0], o.coef[1] = float(op[3]), float(op[4])
             else:
                 _, dst, terms, ncoef, nidx = op
                 o.kind, o.dst, o.nin = OP_AXPY, int(dst), len(terms)

@@ -68,6 +68,12 @@ class DdimTables:
         self.sqrt_alphas_hat = torch.sqrt(ah).double().numpy()
         self.sqrt_recip_alphas_hat = torch.sqrt(1.0 / ah).double().numpy()
         self.sqrt_recipm1_alphas_hat = torch.sqrt(1.0 / ah - 1).double().numpy()
+        # posterior q(x_{t-1} | x_t, x_0) terms exactly as written at diffusion_trainer.py:55,66-74 (fp32 torch math)
+        prev = torch.cat([torch.ones(1), ah[:-1]], dim=0)
+        pv = b * (1.0 - prev) / (1.0 - ah)
+        self.posterior_log_variance_clipped = torch.log(torch.maximum(pv, torch.tensor(1e-20))).double().numpy()
+        self.posterior_mean_coef1 = (b * torch.sqrt(ah) / (1.0 - ah)).double().numpy()
+        self.posterior_mean_coef2 = ((1.0 - prev) * torch.sqrt(1.0 - b) / (1.0 - ah)).double().numpy()
 
 
 def _scalar(t):
@@ -299,9 +305,19 @@ def multistep_update_coefs(ns, algorithm_type, t_prev, t, order, solver_type="dp
 _X, _RAW, _HIST = 0, 1, 2
 
 
+def quantile_rank(ratio, n):
+    """torch.quantile's 'linear' rule: rank = fp32(ratio) * (n - 1) evaluated in fp32 -> (floor(rank), frac(rank))."""
+    rank = np.float32(np.float32(ratio) * np.float32(n - 1))
+    k = int(np.floor(rank))
+    return k, float(np.float32(rank - np.float32(k)))
+
+
 def build_dpm_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type="x_start", skip_type="logSNR",
-                      lower_order_final=False, denoise_to_zero=True, solver_type="dpmsolver", t_start=None, t_end=None):
-    """DPM_Solver.sample(method='multistep') (sampler.py:1171-1247) as EVAL/AXPY ops; returns (ops, model_times)."""
+                      lower_order_final=False, denoise_to_zero=True, solver_type="dpmsolver", t_start=None, t_end=None,
+                      thresholding=None, map_elems=224 * 384):
+    """DPM_Solver.sample(method='multistep') (sampler.py:1171-1247) as EVAL/AXPY ops; returns (ops, model_times).
+    ``thresholding=(ratio, max_val)`` appends DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426) to every data
+    prediction, as ``correcting_x0_fn="dynamic_thresholding"`` does (sampler.py:410-411,441-442)."""
     assert steps >= order
     t_0 = 1.0 / ns.total_N if t_end is None else t_end
     t_T = ns.T if t_start is None else t_start
@@ -323,6 +339,8 @@ def build_dpm_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type
                 cx, cr = 0.0, 1.0                            # the two conversions cancel exactly
         terms = [(_RAW, cr)] if cx == 0.0 else [(_X, cx), (_RAW, cr)]
         ops.append(("axpy", slot, terms, 0.0, -1))
+        if pp and thresholding is not None:
+            ops.append(("thresh", slot) + quantile_rank(thresholding[0], map_elems) + (float(thresholding[1]),))
 
     hist = []                                                # [(t, slot)], oldest first
     free = [_HIST + k for k in range(order)]
@@ -361,6 +379,8 @@ def build_dpm_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type
             cx, cr = 0.0, 1.0
         terms = [(_RAW, cr)] if cx == 0.0 else [(_X, cx), (_RAW, cr)]
         ops.append(("axpy", _X, terms, 0.0, -1))
+        if thresholding is not None:                         # denoise_to_zero_fn = data_prediction_fn (sampler.py:542-546)
+            ops.append(("thresh", _X) + quantile_rank(thresholding[0], map_elems) + (float(thresholding[1]),))
     return ops, times
 
 
@@ -398,6 +418,49 @@ def build_ddim_program(tables, timesteps, eta=0.0, training_target="x0"):
     return ops, n_noise
 
 
+def build_ddpm_program(tables, timesteps, training_target="x0"):
+    """DiffusionTrainer.sample_ddpm / p_sample (diffusion_trainer.py:488-540) as EVAL/AXPY ops: per step
+    x <- coef1[t] * x_recon + coef2[t] * x + exp(0.5 * logvar[t]) * z  (z only for t > 0; the reference's
+    ``x_recon.clamp(-1, 1)`` at :507 is not in-place and has no effect).  Returns (ops, n_noise_slabs)."""
+    skip = tables.num_timesteps // timesteps
+    ops, n_noise = [], 0
+    for time in reversed(range(0, tables.num_timesteps, skip)):
+        ops.append(("eval", float(time)))
+        c1, c2 = tables.posterior_mean_coef1[time], tables.posterior_mean_coef2[time]
+        if training_target == "x0":
+            xr_x, xr_r = 0.0, 1.0
+        else:
+            xr_x, xr_r = tables.sqrt_recip_alphas_hat[time], -tables.sqrt_recipm1_alphas_hat[time]
+        terms = [(_X, c2 + c1 * xr_x), (_RAW, c1 * xr_r)]
+        if time > 0:
+            ops.append(("axpy", _X, terms, math.exp(0.5 * tables.posterior_log_variance_clipped[time]), n_noise))
+            n_noise += 1
+        else:
+            ops.append(("axpy", _X, terms, 0.0, -1))
+    return ops, n_noise
+
+
+def _correct(kind, buf, args):
+    """'clamp' / 'thresh' program ops outside dsb_sample (generic denoiser path): same CUDA kernels, one-op program."""
+    import ctypes
+    from . import _lib
+    from .engine import _bind, _stream
+    if not buf.is_cuda:
+        raise RuntimeError("diff_sal_b200 sampler correctors run on the GPU only")
+    lib = _bind(_lib.lib())
+    buf = buf.to(dtype=torch.float32).contiguous()
+    B = buf.shape[0]
+    with torch.cuda.device(buf.device):
+        if kind == "clamp":
+            rc = lib.dsb_sampler_clamp(_lib.ptr(buf), buf.numel(), float(args[0]), float(args[1]), _stream())
+        else:
+            rc = lib.dsb_sampler_dynamic_threshold(_lib.ptr(buf), B, buf.numel() // B, int(args[0]), float(args[1]),
+                                                   float(args[2]), _stream())
+    if rc != 0:
+        raise RuntimeError("sampler corrector %r failed (%d)" % (kind, rc))
+    return buf
+
+
 def run_program_generic(ops, x, model, noise=None):
     """Executes a sampler program with an arbitrary denoiser callable ``model(x, t[B]) -> tensor`` (one fused
     update launch per AXPY).  The SalUNetB200 fast path runs the same ops inside dsb_sample instead."""
@@ -406,6 +469,8 @@ def run_program_generic(ops, x, model, noise=None):
         if op[0] == "eval":
             t = torch.full((x.shape[0],), op[1], dtype=torch.float32, device=x.device)
             bufs[_RAW] = model(bufs[_X], t)
+        elif op[0] in ("clamp", "thresh"):
+            bufs[op[1]] = _correct(op[0], bufs[op[1]], op[2:])
         else:
             _, dst, terms, ncoef, nidx = op
             nz = noise[nidx] if (nidx >= 0 and noise is not None) else None
@@ -422,9 +487,11 @@ class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
                  correcting_xt_fn=None, thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
         assert algorithm_type in ["dpmsolver", "dpmsolver++"]
-        if correcting_x0_fn is not None or correcting_xt_fn is not None:
-            raise NotImplementedError("correcting_x0_fn / correcting_xt_fn (dynamic thresholding) are not on the hot path "
-                                      "(cfgs/diffusion.yml: thresholding false)")
+        if correcting_xt_fn is not None or correcting_x0_fn not in (None, "dynamic_thresholding"):
+            raise NotImplementedError("only correcting_x0_fn in (None, 'dynamic_thresholding') runs in the fused loop; "
+                                      "Python callables per step are outside the hot path")
+        self.thresholding = (float(dynamic_thresholding_ratio), float(thresholding_max_val)) \
+            if correcting_x0_fn == "dynamic_thresholding" else None
         if not isinstance(model_fn, _WrappedModel):
             raise TypeError("model_fn must come from diff_sal_b200.sampler.model_wrapper")
         self.wrapped = model_fn
@@ -441,7 +508,8 @@ class DPM_Solver:
             raise NotImplementedError("return_intermediate is not supported by the fused loop")
         ns = self.noise_schedule
         ops, _ = build_dpm_program(ns, steps, order, self.algorithm_type, self.wrapped.model_type, skip_type,
-                                   lower_order_final, denoise_to_zero, solver_type, t_start, t_end)
+                                   lower_order_final, denoise_to_zero, solver_type, t_start, t_end,
+                                   thresholding=self.thresholding, map_elems=x[0].numel())
         model = self.wrapped.model
         kwargs = self.wrapped.model_kwargs
         fused = getattr(model, "_dsb_fused_sample", None)
@@ -481,17 +549,31 @@ class DiffusionSampler:
                                                   use_graph=use_graph)
 
     @torch.no_grad()
+    def sample_ddpm(self, x, img=None, audio_cond=None, use_graph=True, noise=None):
+        """Ancestral sampling (diffusion_trainer.py:522-540).  The reference's own method re-runs the encoders and feeds
+        an undefined feature list (:529-531); here ``img`` / ``audio_cond`` are the decoder's conditioning as in
+        ``sample_ddim``.  ``noise`` [n_steps-1, B, 1, H, W] may be given for reproducibility (default: randn)."""
+        ops, n_noise = build_ddpm_program(self.tables, self.config.sampling.timesteps, self.training_target)
+        if noise is None and n_noise:
+            noise = torch.randn((n_noise,) + tuple(x.shape), device=x.device)
+        return self.decoder_net._dsb_fused_sample(ops, x, img, {"audio_feat_list": audio_cond}, noise=noise,
+                                                  use_graph=use_graph)
+
+    @torch.no_grad()
     def sample_image(self, x, img=None, audio=None, base_samples=None, use_graph=True):
         st = self.config.sampling.sample_type
         if st == "ddim":
             return self.sample_ddim(x, img, audio, use_graph=use_graph)
+        if st == "ddpm":
+            return self.sample_ddpm(x, img, audio, use_graph=use_graph)
         if st in ["dpmsolver", "dpmsolver++"]:
             ns = NoiseScheduleVP(schedule="discrete", betas=self.betas)
             mtype = "x_start" if self.training_target == "x0" else "noise"
             mf = model_wrapper(self.decoder_net, ns, model_type=mtype, model_kwargs={"audio_feat_list": audio},
                                guidance_type="uncond")
-            solver = DPM_Solver(mf, ns, algorithm_type=st)
             s = self.config.sampling
+            solver = DPM_Solver(mf, ns, algorithm_type=st,
+                                correcting_x0_fn="dynamic_thresholding" if getattr(s, "thresholding", False) else None)
             return solver.sample(x, img, steps=(s.timesteps - 1 if s.denoise else s.timesteps), order=s.dpm_solver_order,
                                  skip_type=s.skip_type, method=s.dpm_solver_method, lower_order_final=s.lower_order_final,
                                  denoise_to_zero=s.denoise, solver_type=s.dpm_solver_type, atol=s.dpm_solver_atol,
@@ -568,4 +650,33 @@ def generalized_steps(x, seq, model, b, img=None, **kwargs):
             c2 = math.sqrt((1 - at_next) - c1 ** 2)
             nz = torch.randn_like(x) if c1 != 0.0 else None
             xs.append(_axpy([math.sqrt(at_next), c2], [x0_t, et], nz, c1))
+    return xs, x0_preds
+
+
+def ddpm_steps(x, seq, model, b, **kwargs):
+    """util/denoising.py:39-67 (DDIM-repo ancestral loop, eps-parameterised ``model(x, t_float)``): per step
+    x0 = clamp(sqrt(1/a_t) x - sqrt(1/a_t - 1) e, -1, 1); mean = (sqrt(a_{t-1}) beta_t x0 + sqrt(1 - beta_t)
+    (1 - a_{t-1}) x) / (1 - a_t); x <- mean + [t != 0] * sqrt(beta_t) * z.  As in generalized_steps the reference's
+    per-step host round trips are not reproduced.  ``noise`` (list of tensors, one per step) may be passed for
+    reproducibility."""
+    with torch.no_grad():
+        n = x.size(0)
+        seq = list(seq)
+        seq_next = [-1] + seq[:-1]
+        bcpu = _as_fp32_cpu(b)
+        ah = torch.cat([torch.ones(1), (1 - bcpu).cumprod(dim=0)]).double().numpy()   # index t+1
+        noise = kwargs.get("noise")
+        xs, x0_preds = [x], []
+        for step, (i, j) in enumerate(zip(reversed(seq), reversed(seq_next))):
+            t = (torch.ones(n) * i).to(x.device)
+            at, atm1 = float(ah[i + 1]), float(ah[j + 1])
+            beta_t = 1 - at / atm1
+            xt = xs[-1]
+            e = model(xt, t.float())
+            x0 = _correct("clamp", _axpy([math.sqrt(1.0 / at), -math.sqrt(1.0 / at - 1)], [xt, e]), (-1.0, 1.0))
+            x0_preds.append(x0)
+            z = noise[step] if noise is not None else torch.randn_like(x)
+            mask = 0.0 if i == 0 else 1.0
+            xs.append(_axpy([math.sqrt(atm1) * beta_t / (1.0 - at), math.sqrt(1 - beta_t) * (1 - atm1) / (1.0 - at)],
+                            [x0, xt], z, mask * math.sqrt(beta_t)))
     return xs, x0_preds

@@ -82,6 +82,10 @@ int dsb_sampler_update(dsb_handle* h, const float* coef, const float* const* in,
  */
 #define DSB_OP_EVAL 0
 #define DSB_OP_AXPY 1
+#define DSB_OP_CLAMP 2     /* buf[dst] = clamp(buf[dst], coef[0], coef[1])            (util/denoising.py:54)         */
+#define DSB_OP_DYNTHRESH 3 /* DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426) on buf[dst], per clip:
+                            * s = max(lerp(|x|_(k), |x|_(k+1), coef[0]), coef[1]) with k = noise_index the floor of
+                            * torch.quantile's fp32 rank p * (n - 1); buf = clamp(buf, -s, s) / s                     */
 typedef struct dsb_sampler_op {
     int kind;
     float t;
@@ -101,6 +105,12 @@ typedef struct dsb_sampler_desc {
 } dsb_sampler_desc;
 
 int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int B, void* stream);
+
+/* the two corrector ops as stand-alone calls (no handle state), for loops driven around an arbitrary denoiser:
+ * in-place clamp (util/denoising.py:54 `torch.clamp(x0_from_e, -1, 1)`) and DPM_Solver.dynamic_thresholding_fn
+ * (models/dpm_solver/sampler.py:417-426; x: [B][n], k / w = floor / frac of torch.quantile's fp32 rank p*(n-1)) */
+int dsb_sampler_clamp(float* x, int64_t n, float lo, float hi, void* stream);
+int dsb_sampler_dynamic_threshold(float* x, int B, int64_t n, int k, float w, float max_val, void* stream);
 
 /* output side of the loop: clamp(x,0,1) = inverse_data_transform (datasets/__init__.py:26-35, cfgs/diffusion.yml data.*)
  * and the per-map min-max -> uint8 of normalize_data (util/utils.py:11-16).  x: device fp32 [B][pixels_per_map];

@@ -48,6 +48,13 @@ class DdimTables:
         self.sqrt_recip_alphas_hat = torch.sqrt(1.0 / self.alphas_hat)
         self.sqrt_recipm1_alphas_hat = torch.sqrt(1.0 / self.alphas_hat - 1)
         self.num_timesteps = betas.shape[0]
+        # posterior q(x_{t-1} | x_t, x_0) terms (diffusion_trainer.py:55,66-74)
+        alphas = 1.0 - betas
+        prev = torch.cat([torch.ones(1), self.alphas_hat[:-1]], dim=0)
+        self.posterior_variance = betas * (1.0 - prev) / (1.0 - self.alphas_hat)
+        self.posterior_log_variance_clipped = torch.log(torch.maximum(self.posterior_variance, torch.tensor(1e-20)))
+        self.posterior_mean_coef1 = betas * torch.sqrt(self.alphas_hat) / (1.0 - self.alphas_hat)
+        self.posterior_mean_coef2 = (1.0 - prev) * torch.sqrt(alphas) / (1.0 - self.alphas_hat)
 
 
 def sample_ddim(model, x, timesteps, eta=0.0, training_target="x0", tables=None, noise_fn=None):
@@ -76,6 +83,67 @@ def sample_ddim(model, x, timesteps, eta=0.0, training_target="x0", tables=None,
         z = torch.randn_like(x) if noise_fn is None else noise_fn(x)
         x = tb.sqrt_alphas_hat[time_next] * x_start + c1 * z + c2 * pred_noise
     return x
+
+
+def sample_ddpm(model, x, timesteps, training_target="x0", tables=None, noise_fn=None):
+    """DiffusionTrainer.sample_ddpm / p_sample / p_mean_variance / q_posterior (diffusion_trainer.py:488-540) around
+    ``model(x, t_int64[B])``.  The reference's ``x_recon.clamp(-1.0, 1.0)`` (:507) is not in-place and therefore has
+    no effect; ``posterior_mean_coef1`` is ``betas * sqrt(alphas_hat) / (1 - alphas_hat)`` exactly as written at :71
+    (not the textbook sqrt(alphas_hat_prev)).  ``noise_fn(x)`` supplies the ancestral noise (default randn_like,
+    drawn only for t > 0 as in :518-520)."""
+    tb = DdimTables() if tables is None else tables
+    skip = tb.num_timesteps // timesteps
+    n = x.shape[0]
+    for time in reversed(range(0, tb.num_timesteps, skip)):
+        t = torch.full((n,), time, dtype=torch.int64)
+        if training_target == "x0":
+            x_recon = model(x, t)
+        else:
+            x_recon = tb.sqrt_recip_alphas_hat[time] * x - tb.sqrt_recipm1_alphas_hat[time] * model(x, t)
+        mean = tb.posterior_mean_coef1[time] * x_recon + tb.posterior_mean_coef2[time] * x
+        if time > 0:
+            z = torch.randn_like(x) if noise_fn is None else noise_fn(x)
+        else:
+            z = torch.zeros_like(x)
+        x = mean + z * (0.5 * tb.posterior_log_variance_clipped[time]).exp()
+    return x
+
+
+def ddpm_steps(x, seq, model, b, noise_fn=None):
+    """util/denoising.py:39-67 (``model(x, t_float[B])`` predicts eps).  The reference's ``.to('cuda')`` /
+    ``.to('cpu')`` hops are device plumbing and are dropped; arithmetic and call order are the reference's."""
+    n = x.size(0)
+    seq = list(seq)
+    seq_next = [-1] + seq[:-1]
+    xs, x0_preds = [x], []
+
+    def compute_alpha(beta, t):                                     # util/denoising.py:3-6
+        beta = torch.cat([torch.zeros(1), beta], dim=0)
+        return (1 - beta).cumprod(dim=0).index_select(0, t + 1).view(-1, 1, 1, 1)
+
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = torch.ones(n) * i
+        next_t = torch.ones(n) * j
+        at = compute_alpha(b, t.long())
+        atm1 = compute_alpha(b, next_t.long())
+        beta_t = 1 - at / atm1
+        x = xs[-1]
+        e = model(x, t.float())
+        x0_from_e = (1.0 / at).sqrt() * x - (1.0 / at - 1).sqrt() * e
+        x0_from_e = torch.clamp(x0_from_e, -1, 1)
+        x0_preds.append(x0_from_e)
+        mean = ((atm1.sqrt() * beta_t) * x0_from_e + ((1 - beta_t).sqrt() * (1 - atm1)) * x) / (1.0 - at)
+        noise = torch.randn_like(x) if noise_fn is None else noise_fn(x)
+        mask = (1 - (t == 0).float()).view(-1, 1, 1, 1)
+        xs.append(mean + mask * torch.exp(0.5 * beta_t.log()) * noise)
+    return xs, x0_preds
+
+
+def dynamic_thresholding(x0, ratio=0.995, max_val=1.0):
+    """DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426)."""
+    s = torch.quantile(torch.abs(x0).reshape((x0.shape[0], -1)), ratio, dim=1)
+    s = torch.maximum(s, max_val * torch.ones_like(s)).reshape((-1,) + (1,) * (x0.dim() - 1))
+    return torch.clamp(x0, -s, s) / s
 
 
 # ----------------------------------------------------------------------------- DPM-solver
@@ -144,7 +212,8 @@ def dpm_time_steps(ns, steps, skip_type="logSNR"):
 
 def sample_dpm(model, x, betas=None, steps=9, order=2, algorithm_type="dpmsolver",
                model_type="x_start", skip_type="logSNR", lower_order_final=False,
-               denoise_to_zero=True, solver_type="dpmsolver", return_model_times=False):
+               denoise_to_zero=True, solver_type="dpmsolver", return_model_times=False,
+               correcting_x0_fn=None, thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
     """DPM_Solver.sample(method='multistep') driven through model_wrapper(uncond).
     ``model(x, t_float[B])`` is the raw network; model_type says what it predicts."""
     betas = betas_fp32() if betas is None else betas
@@ -164,7 +233,12 @@ def sample_dpm(model, x, betas=None, steps=9, order=2, algorithm_type="dpmsolver
 
     def data_pred(x, t):
         noise = noise_pred(x, t)
-        return (x - ns.sigma(t) * noise) / ns.alpha(t)
+        x0 = (x - ns.sigma(t) * noise) / ns.alpha(t)
+        if correcting_x0_fn == "dynamic_thresholding":       # sampler.py:410-411,434-443
+            x0 = dynamic_thresholding(x0, dynamic_thresholding_ratio, thresholding_max_val)
+        elif correcting_x0_fn is not None:
+            x0 = correcting_x0_fn(x0, t)
+        return x0
 
     def model_fn(x, t):
         return data_pred(x, t) if algorithm_type == "dpmsolver++" else noise_pred(x, t)

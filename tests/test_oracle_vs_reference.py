@@ -131,3 +131,89 @@ def test_audio_attention_matches_reference(depth, batch):
     with torch.no_grad():
         ref = net(aud.clone())
     assert (audio_attention.forward(sd, aud) - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("target", ["x0", "noise"])
+@pytest.mark.parametrize("S", [1, 4, 10])
+def test_ddpm_bit_exact_on_toy_net(target, S):
+    """Ancestral sampling: the reference's p_sample / p_mean_variance / q_posterior (diffusion_trainer.py:488-520)
+    driven over the same reversed(range(0, T, T // S)) sequence as sample_ddpm (:533-538), whose own encoder calls
+    (:529-531) reference modules the decoder-only harness does not have."""
+    ref_loader.load()
+    import diffusion_trainer as dt
+
+    class Dec(torch.nn.Module):
+        def forward(self, x, t, img, audio=None):
+            return _toy(x, t)
+
+    tb = samplers.DdimTables()
+    tr = dt.DiffusionTrainer.__new__(dt.DiffusionTrainer)
+    tr.device = torch.device("cpu")
+    tr.num_timesteps = 1000
+    tr.training_target = target
+    for k in ("sqrt_recip_alphas_hat", "sqrt_recipm1_alphas_hat", "posterior_mean_coef1", "posterior_mean_coef2",
+              "posterior_variance", "posterior_log_variance_clipped"):
+        setattr(tr, k, getattr(tb, k))
+    tr.model = types.SimpleNamespace(module=types.SimpleNamespace(decoder_net=Dec()))
+    x = torch.randn(2, 1, 8, 8, generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(5)
+    ref = x
+    for t in reversed(range(0, 1000, 1000 // S)):
+        ref = tr.p_sample(ref, t, [torch.zeros(1)])
+    torch.manual_seed(5)
+    mine = samplers.sample_ddpm(_toy, x, S, training_target=target)
+    assert torch.equal(ref, mine)
+
+
+def test_posterior_tables_match_reference_formulas():
+    """diffusion_trainer.py:47-74 evaluated literally on the oracle's betas."""
+    tb = samplers.DdimTables()
+    betas = tb.betas
+    alphas = 1.0 - betas
+    ah = alphas.cumprod(dim=0)
+    prev = torch.cat([torch.ones(1), ah[:-1]], dim=0)
+    pv = betas * (1.0 - prev) / (1.0 - ah)
+    assert torch.equal(tb.posterior_log_variance_clipped, torch.log(torch.maximum(pv, torch.tensor(1e-20))))
+    assert torch.equal(tb.posterior_mean_coef1, betas * torch.sqrt(ah) / (1.0 - ah))
+    assert torch.equal(tb.posterior_mean_coef2, (1.0 - prev) * torch.sqrt(alphas) / (1.0 - ah))
+
+
+@pytest.mark.parametrize("algo", ["dpmsolver", "dpmsolver++"])
+def test_dynamic_thresholding_bit_exact_on_toy_net(algo):
+    ns = ref_loader.load()
+    betas = samplers.betas_fp32()
+    x = 2.5 * torch.randn(1, 1, 16, 24, generator=torch.Generator().manual_seed(1))
+    net = lambda x_, t_: 1.7 * _toy(x_, t_)
+    nsv = ns.NoiseScheduleVP(schedule="discrete", betas=betas)
+    mf = ns.model_wrapper(lambda x_, t_, img, **kw: net(x_, t_), nsv, model_type="x_start", model_kwargs={},
+                          guidance_type="uncond")
+    ref = ns.DPM_Solver(mf, nsv, algorithm_type=algo, correcting_x0_fn="dynamic_thresholding").sample(
+        x, None, steps=5, order=2, skip_type="logSNR", method="multistep", lower_order_final=False, denoise_to_zero=True)
+    mine = samplers.sample_dpm(net, x, betas, steps=5, order=2, algorithm_type=algo, model_type="x_start",
+                               correcting_x0_fn="dynamic_thresholding")
+    assert torch.equal(ref, mine)
+
+
+def test_ddpm_steps_bit_exact_on_toy_net(monkeypatch):
+    """util/denoising.py:39-67.  The reference hard-codes .to('cuda') / .to('cpu') hops (:48,55,64); they are made
+    no-ops for this CPU run (device plumbing only, no arithmetic)."""
+    ref_loader.load()
+    import util.denoising as den
+    orig_to = torch.Tensor.to
+
+    def to(self, *args, **kwargs):
+        if args and args[0] in ("cuda", "cpu"):
+            return self
+        return orig_to(self, *args, **kwargs)
+
+    monkeypatch.setattr(torch.Tensor, "to", to)
+    betas = samplers.betas_fp32()
+    x = torch.randn(2, 1, 8, 8, generator=torch.Generator().manual_seed(4))
+    seq = range(0, 1000, 250)
+    torch.manual_seed(9)
+    rxs, rx0 = den.ddpm_steps(x, seq, lambda x_, t_: _toy(x_, t_), betas)
+    torch.manual_seed(9)
+    mxs, mx0 = samplers.ddpm_steps(x, seq, lambda x_, t_: _toy(x_, t_), betas)
+    assert len(rxs) == len(mxs) == 5 and len(rx0) == len(mx0) == 4
+    for a, b in zip(rxs + rx0, mxs + mx0):
+        assert torch.equal(a, b)

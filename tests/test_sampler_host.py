@@ -25,6 +25,16 @@ def interpret(ops, x, net, noise=None):
         if op[0] == "eval":
             t = torch.full((x.shape[0],), op[1], dtype=torch.float32)
             bufs[1] = net(bufs[0].float(), t).double()
+        elif op[0] == "clamp":
+            bufs[op[1]] = bufs[op[1]].clamp(op[2], op[3])
+        elif op[0] == "thresh":
+            _, dst, k, w, mx = op
+            v = bufs[dst].float()
+            srt = v.abs().reshape(v.shape[0], -1).sort(dim=1).values
+            a, b = srt[:, k], srt[:, min(k + 1, srt.shape[1] - 1)]
+            q = torch.lerp(a, b, torch.tensor(w))
+            sc = torch.maximum(q, torch.tensor(mx)).reshape((-1,) + (1,) * (v.dim() - 1))
+            bufs[dst] = (torch.clamp(v, -sc, sc) / sc).double()
         else:
             _, dst, terms, ncoef, nidx = op
             acc = sum(c * bufs[s] for s, c in terms)
@@ -136,3 +146,47 @@ def test_product_fails_loudly_without_gpu():
     from diff_sal_b200.engine import DsbError, Engine
     with pytest.raises(DsbError):
         Engine(max_batch=1)
+
+
+@pytest.mark.parametrize("target", ["x0", "noise"])
+@pytest.mark.parametrize("Sn", [1, 4, 10])
+def test_ddpm_program_matches_oracle(target, Sn):
+    """Ancestral sampling (diffusion_trainer.py:488-540) as a program vs the oracle loop, same noise."""
+    betas = O.betas_fp32()
+    tables = S.DdimTables(betas)
+    ops, n_noise = S.build_ddpm_program(tables, Sn, target)
+    assert n_noise == Sn - 1
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 1, 8, 12, generator=g)
+    noise = torch.randn(max(n_noise, 1), 2, 1, 8, 12, generator=g)
+    it = iter(noise)
+    ref = O.sample_ddpm(lambda x_, t_: _toy(x_, t_), x, Sn, target, noise_fn=lambda x_: next(it))
+    got = interpret(ops, x, lambda x_, t_: _toy(x_, t_), noise)
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("algo", ["dpmsolver++", "dpmsolver"])
+def test_dynamic_thresholding_program_matches_oracle(algo):
+    """correcting_x0_fn='dynamic_thresholding' (sampler.py:410-426,441-442): program ops vs the oracle loop."""
+    betas = O.betas_fp32()
+    ns = S.NoiseScheduleVP("discrete", betas=betas)
+    g = torch.Generator().manual_seed(5)
+    x = 2.5 * torch.randn(2, 1, 16, 24, generator=g)
+    net = lambda x_, t_: 1.7 * _toy(x_, t_)
+    ops, _ = S.build_dpm_program(ns, 5, 2, algo, "x_start", "logSNR", False, True, thresholding=(0.995, 1.0),
+                                 map_elems=16 * 24)
+    assert sum(op[0] == "thresh" for op in ops) == (6 if algo == "dpmsolver++" else 1)
+    ref = O.sample_dpm(net, x, betas, steps=5, order=2, algorithm_type=algo, model_type="x_start",
+                       correcting_x0_fn="dynamic_thresholding")
+    got = interpret(ops, x, net)
+    assert (got - ref).abs().max().item() < 5e-5
+
+
+def test_quantile_rank_is_torch_rule():
+    for n, p in [(86016, 0.995), (384, 0.995), (1000, 0.5), (11, 0.9)]:
+        k, w = S.quantile_rank(p, n)
+        v = torch.randn(3, n, generator=torch.Generator().manual_seed(n)).abs()
+        srt = v.sort(dim=1).values
+        want = torch.quantile(v, p, dim=1)
+        got = torch.lerp(srt[:, k], srt[:, min(k + 1, n - 1)], torch.tensor(w))
+        assert torch.equal(got, want), (n, p)

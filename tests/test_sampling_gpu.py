@@ -176,3 +176,74 @@ def test_output_postprocessing_matches_reference_formulas():
         ref = np.clip((d - d.min()) * (255.0 / (d.max() - d.min())), 0, 255).astype(np.uint8)
         diff = np.abs(u8[i].astype(np.int32) - ref.astype(np.int32))
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8f row N4
+def test_ddpm_ancestral_matches_oracle(nets):
+    """DiffusionTrainer.sample_ddpm / p_sample (diffusion_trainer.py:488-540) with fixed ancestral noise."""
+    from diff_sal_b200.sampler import DiffusionSampler
+    from oracle import salunet, samplers as O
+    x, feats, aud = inputs(1, True)
+    # timesteps 3 -> seq = range(0, 1000, 333) = [0, 333, 666, 999]: 4 evaluations, noise on the 3 with t > 0
+    noise = torch.randn(3, 1, 1, 224, 384, generator=torch.Generator().manual_seed(11))
+    smp = DiffusionSampler(nets("wide", True), config("ddpm", 3))
+    y = smp.sample_ddpm(x, feats, aud, noise=noise.cuda()).cpu()
+    sd = synth.make_state_dict("wide")
+    xc, fc, ac = synth.make_inputs(1, audio=True)
+    it = iter(noise)
+    ref = O.sample_ddpm(lambda x_, t_: salunet.forward(sd, x_, t_, fc, ac), xc, 3, "x0", noise_fn=lambda x_: next(it))
+    assert (minmax(y) - minmax(ref)).abs().max().item() <= TOL
+    # sample_image dispatch (sample_type 'ddpm') draws its own noise: same shape, finite, graph == eager is covered above
+    y2 = smp.sample_image(x, feats, aud)
+    assert y2.shape == x.shape and torch.isfinite(y2).all()
+
+
+def test_dynamic_thresholding_kernel_is_torch_quantile():
+    """dsb_sampler_dynamic_threshold vs DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426) on random maps."""
+    from diff_sal_b200 import sampler as S
+    from oracle import samplers as O
+    g = torch.Generator().manual_seed(3)
+    for n, scale, mx in [(224 * 384, 3.0, 1.0), (224 * 384, 0.2, 1.0), (4096, 5.0, 0.5)]:
+        x = scale * torch.randn(3, 1, n // 64, 64, generator=g)
+        x[1, 0, 0, :8] = x[1, 0, 1, :8]                       # a few exact ties
+        k, w = S.quantile_rank(0.995, n)
+        got = S._correct("thresh", x.cuda().clone(), (k, w, mx)).cpu()
+        ref = O.dynamic_thresholding(x, 0.995, mx)
+        assert (got - ref).abs().max().item() <= 1e-6
+
+
+def test_dpm_solver_pp_dynamic_thresholding(nets):
+    """correcting_x0_fn='dynamic_thresholding' in the fused loop vs the oracle loop (max_val 0.2 so that the
+    99.5 % quantile of the saliency map, not the floor, sets the scale)."""
+    from diff_sal_b200 import sampler as S
+    from oracle import salunet, samplers as O
+    net = nets("wide", True)
+    x, feats, aud = inputs(1, True)
+    ns = S.NoiseScheduleVP("discrete", betas=O.betas_fp32())
+    mf = S.model_wrapper(net, ns, model_type="x_start", model_kwargs={"audio_feat_list": aud}, guidance_type="uncond")
+    y = S.DPM_Solver(mf, ns, algorithm_type="dpmsolver++", correcting_x0_fn="dynamic_thresholding",
+                     thresholding_max_val=0.2).sample(x, feats, steps=2, order=2, skip_type="logSNR", method="multistep",
+                                                      lower_order_final=False, denoise_to_zero=True).cpu()
+    sd = synth.make_state_dict("wide")
+    xc, fc, ac = synth.make_inputs(1, audio=True)
+    ref = O.sample_dpm(lambda x_, t_: salunet.forward(sd, x_, t_, fc, ac), xc, steps=2, order=2, algorithm_type="dpmsolver++",
+                       model_type="x_start", correcting_x0_fn="dynamic_thresholding", thresholding_max_val=0.2)
+    assert ref.max().item() > 0.99                                  # the scale was active
+    assert (minmax(y) - minmax(ref)).abs().max().item() <= TOL
+
+
+def test_ddpm_steps_api():
+    """util/denoising.py:39-67 around an arbitrary eps-model (toy network on the GPU), fixed noise."""
+    from diff_sal_b200 import sampler as S
+    from oracle import samplers as O
+    toy = lambda x_, t_: torch.tanh(0.7 * x_ + 0.001 * t_.float()[:, None, None, None]) * 0.5 + 0.1 * torch.roll(x_, 1, -1)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 1, 16, 16, generator=g)
+    noise = [torch.randn(2, 1, 16, 16, generator=g) for _ in range(4)]
+    b = O.betas_fp32()
+    it = iter(noise)
+    rxs, rx0 = O.ddpm_steps(x, range(0, 1000, 250), toy, b, noise_fn=lambda x_: next(it))
+    xs, x0s = S.ddpm_steps(x.cuda(), range(0, 1000, 250), toy, b, noise=[z.cuda() for z in noise])
+    assert len(xs) == 5 and len(x0s) == 4
+    for a, r in zip(xs + x0s, rxs + rx0):
+        assert (a.cpu() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item())
