@@ -148,11 +148,88 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.epi_transposed = (op.out_f32 && !op.out_bf16 && !op.residual && !op.head_w && !op.out_softmax && bn % 32 == 0 &&
                         (long)p.taps * C >= 480) ? 1 : 0;
     p.f_group = op.f_group; p.f_used = op.f_used; p.out_remap = op.out_remap;
+
+    // ---- split-K: few tiles x long K (the encoder's deep convs, ReduceTemp of the small stages at small batch)
+    if (op.split_ws && !p.two_cta && !op.b_rows_per_frame && !op.out_softmax && !op.head_w && !op.f_group) {
+        const int bf_ = 128 >> (p.bw_log2 + p.bh_log2);
+        const int f_nom = op.split_frames_nominal > 0 ? op.split_frames_nominal : op.F;
+        const long tiles = (long)p.tiles_x * p.tiles_y * ((f_nom + bf_ - 1) / bf_) * (op.N / bn);   // at the nominal batch
+        const int nk = p.taps * p.cin_blocks / p.ksub;
+        const long rows = (long)op.F * op.H * op.W;
+        int S = 1;
+        for (int cand = 2; cand <= 16; ++cand) {
+            if (nk % cand) continue;
+            if (tiles * cand > 148) break;
+            if (nk / cand < 3) break;                       // keep at least 3 pipeline stages of work per slice
+            S = cand;
+        }
+        if (rows * op.N * S > op.split_ws_elems) S = 1;
+        if (S > 1) {
+            SplitReduce& r = out->split;
+            r.ws = op.split_ws; r.S = S; r.slab = rows * op.N;
+            r.rows = (int)rows; r.N = op.N; r.HW = op.H * op.W;
+            r.scale = p.scale; r.shift = p.shift; r.rowbias = p.rowbias; r.residual = p.residual; r.act = p.act;
+            r.out_f32 = p.out_f32; r.out_bf16 = p.out_bf16; r.out2_f32 = p.out2_f32;
+            r.ldo = p.ldo; r.out_fmul = p.out_fmul; r.out_fadd = p.out_fadd; r.out2_fmul = p.out2_fmul; r.out2_fadd = p.out2_fadd;
+            // the GEMM pass writes raw partials, compact rows, plain direct epilogue
+            p.scale = p.shift = p.rowbias = p.residual = nullptr;
+            p.act = ACT_NONE;
+            p.out_f32 = op.split_ws; p.out_bf16 = nullptr; p.out2_f32 = nullptr;
+            p.ldo = op.N; p.out_fmul = 1; p.out_fadd = 0; p.out2_fmul = 1; p.out2_fadd = 0;
+            p.epi_transposed = 0;
+            p.ksplit = S;
+            p.split_stride = r.slab;
+        }
+    }
     return 0;
 }
 
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitReduce r) {
+    const int nv = r.N >> 2;
+    const long total = (long)r.rows * nv;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const int row = (int)(i / nv), n = (int)(i % nv) * 4;
+        const int f = row / r.HW, pix = row - f * r.HW;
+        const float4* src = reinterpret_cast<const float4*>(r.ws + (size_t)row * r.N + n);
+        float4 v = src[0];
+        for (int s = 1; s < r.S; ++s) {                      // fixed order: bitwise reproducible
+            const float4 t = *reinterpret_cast<const float4*>(r.ws + (size_t)s * r.slab + (size_t)row * r.N + n);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (r.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(r.scale + n)); v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w; }
+        if (r.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(r.shift + n)); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (r.rowbias) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(r.rowbias + (size_t)f * r.N + n));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (r.act == ACT_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        } else if (r.act == ACT_GELU) {
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        }
+        if (r.residual) {
+            const float4 t = *reinterpret_cast<const float4*>(r.residual + (size_t)row * r.N + n);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        const size_t po = ((size_t)(f * r.out_fmul + r.out_fadd) * r.HW + pix) * r.ldo + n;
+        if (r.out_f32) *reinterpret_cast<float4*>(r.out_f32 + po) = v;
+        if (r.out_bf16) *reinterpret_cast<uint2*>(r.out_bf16 + po) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        if (r.out2_f32) {
+            const size_t p2 = ((size_t)(f * r.out2_fmul + r.out2_fadd) * r.HW + pix) * r.ldo + n;
+            *reinterpret_cast<float4*>(r.out2_f32 + p2) = v;
+        }
+    }
+}
+
 int conv_run(const ConvLaunch& l, int num_sms, cudaStream_t stream) {
-    return gemm_launch(l.p, l.tmA, l.tmB, num_sms, stream);
+    if (int r = gemm_launch(l.p, l.tmA, l.tmB, num_sms, stream)) return r;
+    if (l.split.S > 1) {
+        long g = ((long)l.split.rows * (l.split.N >> 2) + 255) / 256;
+        if (g > 148 * 8) g = 148 * 8;
+        splitk_reduce_kernel<<<(int)g, 256, 0, stream>>>(l.split);
+        return (int)cudaGetLastError();
+    }
+    return 0;
 }
 
 }  // namespace dsb

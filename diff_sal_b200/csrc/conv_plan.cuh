@@ -40,11 +40,32 @@ struct ConvOp {
     float* out2_f32;        // optional second fp32 output with its own frame mapping
     int out2_fmul, out2_fadd;
     int two_cta;            // -1: never, 0: automatic (pairs when there are enough tiles), 1: force
+    // split-K (opt-in): fp32 scratch for the per-slice partial sums.  Used when the GEMM has too few tiles to fill
+    // the machine and a long K loop; the slices are added in a fixed order by splitk_reduce (bitwise reproducible).
+    float* split_ws;
+    long split_ws_elems;
+    int split_frames_nominal;   // > 0: choose the slice count as if F were this (keeps the K partition, and with it the
+                                // rounding, independent of the batch size); 0: use F
+};
+
+// second pass of a split-K op: out = epilogue(sum over slices of ws[s][row][n]) with the op's own epilogue
+struct SplitReduce {
+    const float* ws;
+    int S;                  // 0: not split
+    long slab;              // elements per slice
+    int rows, N, HW;
+    const float *scale, *shift, *rowbias, *residual;
+    int act;
+    float* out_f32;
+    bf16* out_bf16;
+    float* out2_f32;
+    int ldo, out_fmul, out_fadd, out2_fmul, out2_fadd;
 };
 
 struct ConvLaunch {
     GemmParams p;
     CUtensorMap tmA, tmB;
+    SplitReduce split;
 };
 
 // Lowers `op`; returns 0 or a negative error.

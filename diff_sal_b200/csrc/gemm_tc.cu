@@ -79,7 +79,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     const int total_tiles = two ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
     const int unit0 = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int unit_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int nk = p.taps * p.cin_blocks / p.ksub;          // pipeline stages per tile
+    const int ksplit = p.ksplit > 1 ? p.ksplit : 1;         // K slices per tile (split-K for tile-poor, K-long GEMMs)
+    const int total_units = total_tiles * ksplit;
+    const int nk = p.taps * p.cin_blocks / p.ksub / ksplit; // pipeline stages per work unit
     const int bh_log2 = p.bh_log2, bw_log2 = p.bw_log2;
 
     if (warp == 0) {
@@ -87,7 +89,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         // (whole warp convergent, one elected lane issues: keeps coordinates in uniform registers)
         int s = 0;
         uint32_t phase = 0;
-        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        for (int unit = unit0; unit < total_units; unit += unit_step) {
+            const int tile = unit / ksplit, ks = unit - tile * ksplit;
             const int nt = tile % n_tiles;
             const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;   // may be one past the end
             const int tx = mt % p.tiles_x;
@@ -101,7 +104,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const int y3 = (p.ydim == 3) ? y0 : 0;
             // per-frame B operand is indexed by the SOURCE frame; a pair splits the B rows between its CTAs
             const int brow = nt * p.bn + (two ? (int)(rank * bn_local) : f0 * p.b_rows_per_frame);
-            int tap = 0, cb = 0;
+            const int sub0 = ks * nk * p.ksub;                 // first K sub-block of this slice
+            int tap = sub0 / p.cin_blocks, cb = sub0 % p.cin_blocks;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&bars->empty[s], phase ^ 1u);
                 if (elect_one()) {
@@ -153,7 +157,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            for (int unit = unit0; unit < total_units; unit += unit_step) {
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
@@ -206,7 +210,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         const int rf = r >> (bw_log2 + bh_log2);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        for (int unit = unit0; unit < total_units; unit += unit_step) {
+            const int tile = unit / ksplit, ks = unit - tile * ksplit;
             const int nt = tile % n_tiles;
             const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;
             const int tx = mt % p.tiles_x;
@@ -337,7 +342,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             }
                         }
                         if (p.out_f32) {
-                            float4* op = reinterpret_cast<float4*>(p.out_f32 + pix_out * p.ldo + n);
+                            float4* op = reinterpret_cast<float4*>(p.out_f32 + (size_t)ks * p.split_stride + pix_out * p.ldo + n);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
@@ -501,6 +506,12 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.f_group && (p.f_used < 1 || p.f_used > p.f_group)) return -19;
     if (p.two_cta && (p.b_rows_per_frame || p.out_softmax || (p.bn / 2) % 8)) return -20;
     if (p.ksub < 1 || (p.taps * p.cin_blocks) % p.ksub) return -21;
+    if (p.ksplit > 1) {
+        if (p.two_cta || p.epi_transposed || p.head_w || p.out_softmax || p.out_bf16 || p.out2_f32 || p.scale || p.shift ||
+            p.rowbias || p.residual || p.act != ACT_NONE || !p.out_f32 || p.f_group)
+            return -22;
+        if ((p.taps * p.cin_blocks / p.ksub) % p.ksplit) return -22;
+    }
     const uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
     const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;
@@ -511,7 +522,7 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (int e = gemm_init()) return e;
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
     if (!p.two_cta) {
-        const int total = m_tiles * (p.N / p.bn);
+        const int total = m_tiles * (p.N / p.bn) * (p.ksplit > 1 ? p.ksplit : 1);
         int grid = total < num_sms ? total : num_sms;
         if (grid < 1) return -16;
         gemm_tc_kernel<false><<<grid, kGemmThreads, smem, stream>>>(p, tmA, tmB, stages);

@@ -43,6 +43,8 @@ struct GemmParams {
     const float* residual;          // fp32 [pix][N] or null
     int act;
     int epi_transposed;             // 1: stage 32-column chunks through smem for row-coalesced global access
+    int ksplit;                     // > 1: split-K -- work unit = (tile, K slice); slice ks writes its raw fp32 partial to
+    long split_stride;              //      out_f32 + ks * split_stride (plain epilogue; splitk_reduce finishes the op)
     float* out_f32;                 // [pix][ldo] or null
     bf16* out_bf16;                 // [pix][ldo] or null
     int ldo;                        // output row pitch in elements

@@ -33,6 +33,7 @@ constexpr int kReduce = 5;       // ReduceTemp kernel == stride (cfgs/audio_visu
 constexpr size_t frame_elems(int i) { return (size_t)64512 << i; }   // C_i * h_i * w_i of decoder stage i
 constexpr size_t kMaxFrame = (size_t)64512 << 3;
 constexpr long kMapElems = 224L * 384L;
+constexpr long kSplitWsPerClip = 336L * 768L * 8L;      // largest rows x N x slices of a split-K layer, per clip
 
 struct Weight {
     float* p = nullptr;
@@ -85,6 +86,7 @@ struct dsb_handle {
     bf16* S = nullptr;
     float* p = nullptr;
     float* sbuf[8] = {};                          // sampler buffers
+    float* splitws = nullptr;                     // split-K partial sums (main-stream GEMMs only, so one buffer suffices)
     float* t_all = nullptr;                       // [max evals][B]
     int t_all_cap = 0;
 
@@ -257,6 +259,7 @@ int alloc_workspace(dsb_handle* h) {
     if (int r = dev_alloc(h, &h->p, B * 112 * 192)) return r;
     for (int i = 0; i < 8; ++i)
         if (int r = dev_alloc(h, &h->sbuf[i], B * kMapElems)) return r;
+    if (int r = dev_alloc(h, &h->splitws, (size_t)kSplitWsPerClip * B)) return r;
     h->t_all_cap = 1024;
     if (int r = dev_alloc(h, &h->t_all, (size_t)h->t_all_cap * B)) return r;
     h->ws_ready = true;
@@ -305,6 +308,7 @@ struct Builder {
         if (r) { err = fail(h, DSB_ERR_CUDA, "conv_lower failed (%d) for %s (%dx%d, %d->%d)", r, name, op.H, op.W, op.Cin, op.N); return; }
         const int sms = h->num_sms;
         out->push_back([cl, sms](cudaStream_t s) { return conv_run(cl, sms, s); });
+        if (cl.split.S > 1) h->prog_launches++;              // split-K ops launch the GEMM and the slice reduction
         h->prog_name.push_back(std::string("gemm:") + name);
         const double m = (double)op.F * op.H * op.W;
         h->prog_flops.push_back(algo_flops >= 0 ? algo_flops : 2.0 * m * op.N * (double)cl.p.taps * op.Cin);
@@ -378,6 +382,7 @@ int build_program(dsb_handle* h) {
             {   // conv1 + bias + temb projection
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
                 op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
+                op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
                 b.conv(op, "res.conv1");
             }
             {   // 1x1 shortcut on the raw block input
@@ -390,6 +395,7 @@ int build_program(dsb_handle* h) {
             {   // conv2 + bias + shortcut -> block output (only ever a GEMM operand: bf16)
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
                 op.shift = W(h, rk + "conv2.bias"); op.residual = sc; op.out_bf16 = res;
+                op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
                 b.conv(op, "res.conv2");
             }
             const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
@@ -399,6 +405,7 @@ int build_program(dsb_handle* h) {
                 ConvOp op = make_op(CONV_3X3_S2, B, H / 2, Wd / 2, Cout, Cout, res, WP(dk + "weight"));
                 op.shift = W(h, dk + "bias"); op.out_f32 = d;
                 op.out2_f32 = h->back[2 - i]; op.out2_fmul = kT; op.out2_fadd = kTv;
+                op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
                 b.conv(op, "res.down");
             }
             cur = d;
@@ -583,7 +590,8 @@ int build_program(dsb_handle* h) {
             ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
                                 WP("invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight"));
             op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i];
-            b.conv(op, "reduce_temp");
+            op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
+                b.conv(op, "reduce_temp");
         }
     }
 

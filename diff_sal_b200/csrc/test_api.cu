@@ -17,6 +17,13 @@ static int g_test_two_cta = 0;
 // -1: never use CTA pairs, 0: automatic, 1: always (for the per-kernel tests)
 extern "C" void dsb_test_set_two_cta(int mode) { g_test_two_cta = mode; }
 
+static float* g_test_split_ws = nullptr;
+static long g_test_split_elems = 0;
+// split-K scratch for dsb_test_conv (NULL: never split); returns the slice count the LAST lowered op used
+static int g_test_last_ksplit = 0;
+extern "C" void dsb_test_set_split_ws(float* ws, long elems) { g_test_split_ws = ws; g_test_split_elems = elems; }
+extern "C" int dsb_test_last_ksplit(void) { return g_test_last_ksplit; }
+
 extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt,
                              const void* A, const void* Wt, const float* scale, const float* shift,
                              const float* rowbias, const float* residual, int act, float* out_f32, void* out_bf16,
@@ -30,9 +37,11 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     op.out_f32 = out_f32; op.out_bf16 = (bf16*)out_bf16; op.out_fmul = out_fmul; op.out_fadd = out_fadd;
     op.head_w = head_w; op.head_b = head_b; op.out_head = out_head;
     op.two_cta = g_test_two_cta;
+    op.split_ws = g_test_split_ws; op.split_ws_elems = g_test_split_elems;
     ConvLaunch l;
     int r = conv_lower(op, &l);
     if (r) return r;
+    g_test_last_ksplit = l.split.S;
     return conv_run(l, num_sms_cached(), (cudaStream_t)stream);
 }
 

@@ -184,6 +184,9 @@ int dsb_test_mlp_fused(int C, int HW, int F, int f_group, int f_used, const void
 
 /* CTA-pair (cta_group::2) policy of dsb_test_conv: -1 never, 0 automatic, 1 always */
 void dsb_test_set_two_cta(int mode);
+/* split-K scratch of dsb_test_conv (NULL: never split) and the slice count its last call used (0: not split) */
+void dsb_test_set_split_ws(float* ws, long elems);
+int dsb_test_last_ksplit(void);
 
 #ifdef __cplusplus
 }

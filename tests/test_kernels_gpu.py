@@ -172,3 +172,53 @@ def test_fused_mlp(L, C, HW, F_, fg, fu):
     close(out[live], ref[live], 3e-3)
     if dead:
         assert (out[dead] == 7.0).all()
+
+
+@pytest.fixture
+def split_ws(L):
+    lib = L.lib()
+    ws = torch.zeros(148 * 128 * 256, device="cuda")
+    lib.dsb_test_set_split_ws.argtypes = [ctypes.c_void_p, ctypes.c_long]
+    lib.dsb_test_set_split_ws(L.ptr(ws), ws.numel())
+    yield lib
+    lib.dsb_test_set_split_ws(None, 0)
+
+
+@pytest.mark.parametrize("Fr,H,W,C,N", [(8, 7, 12, 768, 768), (8, 14, 24, 384, 384), (2, 14, 24, 384, 768)])
+def test_splitk_conv_matches_unsplit(L, split_ws, Fr, H, W, C, N):
+    """Tile-poor, K-long convs (the deep encoder layers at small batch) take the split-K path; same epilogue
+    semantics (bias + row bias + residual, second output slot) and bitwise repeatable."""
+    x = _rand(Fr, C, H, W, seed=30).to(torch.bfloat16)
+    w = _rand(N, C, 3, 3, seed=31, scale=(9 * C) ** -0.5).to(torch.bfloat16)
+    b, rb, res = _rand(N, seed=32), _rand(Fr, N, seed=33), _rand(Fr, H, W, N, seed=34)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, C, shift=b, rowbias=rb, residual=res, want="f32")
+    assert split_ws.dsb_test_last_ksplit() > 1
+    out2 = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, C, shift=b, rowbias=rb, residual=res, want="f32")
+    assert torch.equal(out, out2)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1) + rb[:, :, None, None] + res.permute(0, 3, 1, 2)
+    close(out.permute(0, 3, 1, 2), ref, 2e-3)
+
+
+def test_splitk_temporal_reduce_and_stride2(L, split_ws):
+    B, H, W, C = 8, 7, 12, 768
+    x = _rand(B, C, 9, H, W, seed=35).to(torch.bfloat16)
+    w = _rand(768, C, 5, 1, 1, seed=36, scale=(5 * C) ** -0.5).to(torch.bfloat16)
+    a = x.permute(0, 2, 3, 4, 1).contiguous()
+    wt = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(768, 5 * C).contiguous()
+    out = run_conv(L, CONV_TEMPORAL, a, wt, 768, B, H, W, C, T=9, kt=5, act=ACT_RELU, want="f32")
+    assert split_ws.dsb_test_last_ksplit() > 1
+    ref = F.relu(F.conv3d(x.float(), w.float(), None, stride=(5, 1, 1))).squeeze(2)
+    close(out.permute(0, 3, 1, 2), ref, 2e-3)
+    # stride-2 down conv writing frame slot 8 of 9
+    Fr, H, W, C = 8, 7, 12, 768
+    x = _rand(Fr, C, 2 * H, 2 * W, seed=37).to(torch.bfloat16)
+    w = _rand(C, C, 3, 3, seed=38, scale=(9 * C) ** -0.5).to(torch.bfloat16)
+    b = _rand(C, seed=39)
+    out = run_conv(L, CONV_3X3_S2, x.permute(0, 2, 3, 1).contiguous(), pack_w(w), C, Fr, H, W, C, shift=b, want="f32",
+                   out_frames=Fr * 9, out_fmul=9, out_fadd=8)
+    assert split_ws.dsb_test_last_ksplit() > 1
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), b, stride=2)
+    out = out.reshape(Fr, 9, H, W, C)
+    close(out[:, 8].permute(0, 3, 1, 2), ref, 2e-3)
+    assert out[:, :8].abs().max().item() == 0.0
