@@ -379,19 +379,24 @@ int build_program(dsb_handle* h) {
             b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); }, "gn_stats", (double)B * HW * Cin * 4.0);
             b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); }, "gn_apply", (double)B * HW * Cin * 8.0);
             if (i == 0) b.depend(5, 1, 0);                  // timestep projections ready
+            {   // 1x1 shortcut on the raw block input: only conv2's epilogue needs it, so it runs beside
+                // conv1 / GroupNorm 2 on the side stream
+                b.depend(6, 0, 1);
+                b.cur = 1;
+                ConvOp op = make_op(CONV_1X1, B, H, Wd, Cin, Cout, raw, WP(rk + "nin_shortcut.weight"));
+                op.shift = W(h, rk + "nin_shortcut.bias"); op.out_f32 = sc;
+                b.conv(op, "res.shortcut");
+                b.cur = 0;
+            }
             {   // conv1 + bias + temb projection
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
                 op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
                 op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
                 b.conv(op, "res.conv1");
             }
-            {   // 1x1 shortcut on the raw block input
-                ConvOp op = make_op(CONV_1X1, B, H, Wd, Cin, Cout, raw, WP(rk + "nin_shortcut.weight"));
-                op.shift = W(h, rk + "nin_shortcut.bias"); op.out_f32 = sc;
-                b.conv(op, "res.shortcut");
-            }
             b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); }, "gn_stats", (double)B * HW * Cout * 4.0);
             b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); }, "gn_apply", (double)B * HW * Cout * 6.0);
+            b.depend(7, 1, 0);                              // shortcut ready
             {   // conv2 + bias + shortcut -> block output (only ever a GEMM operand: bf16)
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
                 op.shift = W(h, rk + "conv2.bias"); op.residual = sc; op.out_bf16 = res;
