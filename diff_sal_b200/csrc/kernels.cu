@@ -826,36 +826,48 @@ int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int
 
 // ------------------------------------------------------------------------------------------ attention operands
 __global__ void __launch_bounds__(256) attn_operands_kernel(const float* __restrict__ kp, const float* __restrict__ vp,
-                                                           int F, int C, float scale, bf16* __restrict__ KB,
+                                                           int C, float scale, bf16* __restrict__ KB,
                                                            bf16* __restrict__ VB) {
-    const long nK = (long)F * 48 * C, nV = (long)F * C * 64;
-    const int d = C >> 1;
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nK + nV; i += (long)gridDim.x * 256) {
-        if (i < nK) {
-            const int c = (int)(i % C);
-            const int row = (int)((i / C) % 48);
-            const long f = i / ((long)C * 48);
-            float v = 0.0f;
-            if (row < 36 && (c / d) == (row / 18)) v = kp[(f * 18 + row % 18) * C + c] * scale;
-            KB[i] = __float2bfloat16(v);
-        } else {
-            const long k = i - nK;
-            const int col = (int)(k % 64);
-            const int c = (int)((k / 64) % C);
-            const long f = k / ((long)C * 64);
-            float v = 0.0f;
-            if (col < 36 && (c / d) == (col / 18)) v = vp[(f * 18 + col % 18) * C + c];
-            VB[k] = __float2bfloat16(v);
+    // blockIdx.y = frame.  Items 0 .. 48*C/8-1: one uint4 (8 channels) of KB[f][row][c]; then one 128-byte row
+    // VB[f][c][0..63] per item.  A head owns a contiguous half of the channels (d = C/2, a multiple of 8).
+    const int f = blockIdx.y, d = C >> 1, c8n = C >> 3, nK = 48 * c8n;
+    const int item = blockIdx.x * 256 + threadIdx.x;
+    if (item < nK) {
+        const int row = item / c8n, c = (item - row * c8n) * 8;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (row < 36 && (c / d) == (row / 18)) {
+            const float4* src = reinterpret_cast<const float4*>(kp + ((size_t)f * 18 + row % 18) * C + c);
+            const float4 a = src[0], b = src[1];
+            o = make_uint4(pack_bf16x2(a.x * scale, a.y * scale), pack_bf16x2(a.z * scale, a.w * scale),
+                           pack_bf16x2(b.x * scale, b.y * scale), pack_bf16x2(b.z * scale, b.w * scale));
         }
+        reinterpret_cast<uint4*>(KB + ((size_t)f * 48 + row) * C + c)[0] = o;
+    } else if (item < nK + C) {
+        const int c = item - nK, h = c / d;
+        float v[18];
+#pragma unroll
+        for (int j = 0; j < 18; ++j) v[j] = vp[((size_t)f * 18 + j) * C + c];
+        uint32_t w[32];                                       // 64 bf16 columns: head h owns columns 18h .. 18h+17
+#pragma unroll
+        for (int k = 0; k < 32; ++k) w[k] = 0u;
+        if (h == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[9 + k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(VB + ((size_t)f * C + c) * 64);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
 }
 
 int attn_operands_launch(const float* kp, const float* vp, int F, int C, float scale, bf16* KB, bf16* VB,
                          cudaStream_t s) {
-    const long n = (long)F * 48 * C + (long)F * C * 64;
-    long g = (n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
-    attn_operands_kernel<<<(int)g, 256, 0, s>>>(kp, vp, F, C, scale, KB, VB);
+    if (C % 16) return -36;
+    const int items = 48 * (C / 8) + C;
+    attn_operands_kernel<<<dim3((items + 255) / 256, F), 256, 0, s>>>(kp, vp, C, scale, KB, VB);
     DSB_LAUNCH_CHECK();
 }
 
@@ -863,45 +875,56 @@ int attn_operands_launch(const float* kp, const float* vp, int F, int C, float s
 //   K1[f][hj][c]   = scale * sum_{d in head h} K[f,j,d] * Wq[d][c]      (bf16 [F][64][C], rows 36..63 zero)
 //   sb[f][hj]      = scale * sum_{d in head h} K[f,j,d] * bq[d]         (fp32 [F][64])
 //   V2[f][c][hj]   = sum_{d in head h} Wp[c][d] * V[f,j,d]              (bf16 [F][C][64], columns 36..63 zero)
-// one block per (hj, f), one thread per channel c
-__global__ void attn_fold_kernel(const float* __restrict__ kp, const float* __restrict__ vp, const float* __restrict__ wq,
-                                 const float* __restrict__ bq, const float* __restrict__ wpT, int C, float scale, int T,
-                                 int tmax, bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
-    __shared__ float sk[384];
-    __shared__ float sv[384];
-    const int hj = blockIdx.x, f = blockIdx.y, c = threadIdx.x;
+// one block per (head, group of 3 keys, frame), one thread per output channel c: a weight element read from L2 feeds
+// 3 keys / 3 values (the first version, one block per key, moved 36 x both weight matrices per frame through L2)
+__global__ void __launch_bounds__(384) attn_fold_kernel(const float* __restrict__ kp, const float* __restrict__ vp,
+                                                       const float* __restrict__ wq, const float* __restrict__ bq,
+                                                       const float* __restrict__ wpT, int C, float scale, int T, int tmax,
+                                                       bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
+    constexpr int KPB = 3;
+    __shared__ float sk[KPB][192];
+    __shared__ float sv[KPB][192];
+    const int h = blockIdx.x / 6, j0 = (blockIdx.x % 6) * KPB, f = blockIdx.y, c = threadIdx.x;
     if (f % T >= tmax) return;
-    if (hj >= 36) {
-        K1[((size_t)f * 64 + hj) * C + c] = __float2bfloat16(0.0f);
-        V2[((size_t)f * C + c) * 64 + hj] = __float2bfloat16(0.0f);
-        if (c == 0) sb[(size_t)f * 64 + hj] = 0.0f;
-        return;
-    }
-    const int h = hj / 18, j = hj % 18, d = C >> 1, d0 = h * d;
-    for (int i = c; i < d; i += blockDim.x) {
-        sk[i] = kp[((size_t)f * 18 + j) * C + d0 + i];
-        sv[i] = vp[((size_t)f * 18 + j) * C + d0 + i];
+    const int d = C >> 1, d0 = h * d;
+    for (int e = c; e < KPB * d; e += blockDim.x) {
+        const int j = e / d, i = e - j * d;
+        sk[j][i] = kp[((size_t)f * 18 + j0 + j) * C + d0 + i];
+        sv[j][i] = vp[((size_t)f * 18 + j0 + j) * C + d0 + i];
     }
     __syncthreads();
-    float ak = 0.0f, av = 0.0f;
+    float ak[KPB], av[KPB];
+#pragma unroll
+    for (int j = 0; j < KPB; ++j) { ak[j] = 0.0f; av[j] = 0.0f; }
 #pragma unroll 4
     for (int i = 0; i < d; ++i) {
-        ak = fmaf(sk[i], wq[(size_t)(d0 + i) * C + c], ak);
-        av = fmaf(sv[i], wpT[(size_t)(d0 + i) * C + c], av);
+        const float w = wq[(size_t)(d0 + i) * C + c], wp = wpT[(size_t)(d0 + i) * C + c];
+#pragma unroll
+        for (int j = 0; j < KPB; ++j) { ak[j] = fmaf(sk[j][i], w, ak[j]); av[j] = fmaf(sv[j][i], wp, av[j]); }
     }
-    K1[((size_t)f * 64 + hj) * C + c] = __float2bfloat16(ak * scale);
-    V2[((size_t)f * C + c) * 64 + hj] = __float2bfloat16(av);
-    if (c == 0) {
+    bf16* v2row = V2 + ((size_t)f * C + c) * 64;
+#pragma unroll
+    for (int j = 0; j < KPB; ++j) {
+        K1[((size_t)f * 64 + h * 18 + j0 + j) * C + c] = __float2bfloat16(ak[j] * scale);
+        v2row[h * 18 + j0 + j] = __float2bfloat16(av[j]);
+    }
+    if (blockIdx.x == 0) {                                   // zero padding: key rows / value columns 36..63
+        for (int r = 36; r < 64; ++r) K1[((size_t)f * 64 + r) * C + c] = __float2bfloat16(0.0f);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) reinterpret_cast<uint2*>(v2row + 36)[k] = make_uint2(0u, 0u);
+        if (c < 28) sb[(size_t)f * 64 + 36 + c] = 0.0f;
+    }
+    if (c < KPB) {
         float b = 0.0f;
-        for (int i = 0; i < d; ++i) b = fmaf(sk[i], bq[d0 + i], b);
-        sb[(size_t)f * 64 + hj] = b * scale;
+        for (int i = 0; i < d; ++i) b = fmaf(sk[c][i], bq[d0 + i], b);
+        sb[(size_t)f * 64 + h * 18 + j0 + c] = b * scale;
     }
 }
 
 int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
                      float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s) {
-    if (C > 384) return -36;
-    attn_fold_kernel<<<dim3(64, F), C, 0, s>>>(kp, vp, wq, bq, wpT, C, scale, T, tmax, K1, sb, V2);
+    if (C > 384 || C < 32) return -36;
+    attn_fold_kernel<<<dim3(12, F), C, 0, s>>>(kp, vp, wq, bq, wpT, C, scale, T, tmax, K1, sb, V2);
     DSB_LAUNCH_CHECK();
 }
 
