@@ -979,7 +979,7 @@ struct MsWalk {
     }
 };
 
-__global__ void __launch_bounds__(256) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
+__global__ void __launch_bounds__(256, 4) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
     constexpr int C = 768, CV = C / 4, OH = 112, OW = 192, XT = 32;
     const int cv = blockIdx.z % 12 * 16 + (threadIdx.x & 15);
     const int b = blockIdx.z / 12;
