@@ -145,8 +145,8 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.out_softmax = op.out_softmax;
     // fp32-only outputs of compute-heavy GEMMs go through the smem-transposed (row-coalesced) epilogue; measured
     // better there, worse for bf16 / residual epilogues of the short-K token GEMMs (profiles/)
-    p.epi_transposed = (op.out_f32 && !op.out_bf16 && !op.residual && !op.head_w && !op.out_softmax && bn % 32 == 0 &&
-                        (long)p.taps * C >= 480) ? 1 : 0;
+    p.epi_transposed = (op.out_f32 && !op.out_bf16 && !op.head_w && !op.out_softmax && bn % 32 == 0 &&
+                        ((long)p.taps * C >= 480 || op.residual)) ? 1 : 0;
     p.f_group = op.f_group; p.f_used = op.f_used; p.out_remap = op.out_remap;
 
     // ---- split-K: few tiles x long K (the encoder's deep convs, ReduceTemp of the small stages at small batch)

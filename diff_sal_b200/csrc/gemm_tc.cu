@@ -370,9 +370,22 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 rowtab[lane * 3 + 1] = (int)pix_in;
                 rowtab[lane * 3 + 2] = fs;
                 rowtab[96 + lane] = (int)pix_out2;
+                __syncwarp();
                 const int cq = (lane & 7) * 4;                             // this lane's 4 columns inside the chunk
                 const int rq = lane >> 3;                                  // row offset inside a group of 4 rows
                 for (int c = half * 32; c < p.bn; c += 32 * kPerQuad) {
+                    // the chunk's residual rows (coalesced: 4 rows x 128 B per instruction) are requested before the
+                    // TMEM load so that their DRAM latency overlaps the tcgen05.ld + smem transpose
+                    float4 resv[8];
+                    if (p.residual) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int row = it * 4 + rq;
+                            resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rowtab[row * 3 + 0] >= 0)
+                                resv[it] = *reinterpret_cast<const float4*>(p.residual + (size_t)rowtab[row * 3 + 1] * p.N + n0 + c + cq);
+                        }
+                    }
                     uint32_t raw[32];
                     tmem_ld32(t_addr + c, raw);
                     tmem_ld_wait();
@@ -404,7 +417,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
                         }
                         if (p.residual) {
-                            const float4 t = *reinterpret_cast<const float4*>(p.residual + (size_t)rowtab[row * 3 + 1] * p.N + n);
+                            const float4 t = resv[it];
                             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                         }
                         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
