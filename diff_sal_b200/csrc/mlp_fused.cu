@@ -287,26 +287,31 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
         }
     } else if (warp < 14) {
         // ------------------------------------------------------------------ output stage (warps 10..13)
-        // out = acc2 + b2 + residual, overlapped with the GELU stage of the next tile (acc2 is double-buffered);
-        // the residual of chunk c+1 is requested before chunk c is processed
+        // out = acc2 + b2 + residual, overlapped with the GELU stage of the next tile (acc2 is double-buffered).
+        // Each 32-row x 32-column chunk is transposed through a padded smem tile so that one warp instruction touches
+        // whole 128-byte rows (4 rows per instruction): residual loads and output stores are fully coalesced.  The
+        // residual of chunk c + 1 is requested before chunk c is processed.
         const int q = warp & 3;
-        const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int nch = C / 32;
+        float* tile = reinterpret_cast<float*>(bars + 1) + 1024 + (warp - 10) * (32 * 36);   // behind the 4 KB softmax exchange
+        const int cq = (lane & 7) * 4;                      // this lane's 4 columns inside a chunk
+        const int rq = lane >> 3;                           // row offset inside a group of 4 rows
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int f = tile / tiles_per_frame;
-            const int x = ((tile % tiles_per_frame) << 7) + row;
+        for (int tile_i = blockIdx.x; tile_i < total_tiles; tile_i += gridDim.x, ++it) {
+            const int f = tile_i / tiles_per_frame;
+            const int x0 = ((tile_i % tiles_per_frame) << 7) + q * 32;      // first token (in the frame) of this warp's rows
             const int fs = p.f_group ? (f / p.f_used) * p.f_group + f % p.f_used : f;
-            const bool valid = x < p.HW;
-            const size_t tok = (size_t)fs * p.HW + x;
+            const int nvalid = min(32, p.HW - x0);                        // <= 0: no valid row
+            const size_t tok0 = (size_t)fs * p.HW + x0;
             const uint32_t ab = it & 1u;
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + tok * C);
-            float4* op = reinterpret_cast<float4*>(p.out + tok * C);
+            const float* rbase = p.residual + tok0 * C + cq;
+            float* obase = p.out + tok0 * C + cq;
             float4 res[2][8];
-            if (valid) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) res[0][j] = rp[j];
+            for (int k = 0; k < 8; ++k) {
+                const int row = k * 4 + rq;
+                res[0][k] = row < nvalid ? *reinterpret_cast<const float4*>(rbase + (size_t)row * C) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             mbar_wait(&bars->acc2_full[ab], (it >> 1) & 1u);
             tc_fence_after();
@@ -316,21 +321,31 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                 for (int u = 0; u < 2; ++u) {
                     const int c = cc + u;
                     if (c >= nch) break;
-                    if (valid && c + 1 < nch) {
+                    if (c + 1 < nch) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) res[(u + 1) & 1][j] = rp[(c + 1) * 8 + j];
+                        for (int k = 0; k < 8; ++k) {
+                            const int row = k * 4 + rq;
+                            res[(u + 1) & 1][k] = row < nvalid ? *reinterpret_cast<const float4*>(rbase + (size_t)row * C + (c + 1) * 32)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                     uint32_t raw[32];
                     tmem_ld32(tmem_base + lane_addr + kAcc2Col + ab * (uint32_t)C + c * 32, raw);
                     tmem_ld_wait();
-                    if (valid) {
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + j);
-                            op[c * 8 + j] = make_float4(__uint_as_float(raw[4 * j]) + b.x + res[u][j].x,
-                                                        __uint_as_float(raw[4 * j + 1]) + b.y + res[u][j].y,
-                                                        __uint_as_float(raw[4 * j + 2]) + b.z + res[u][j].z,
-                                                        __uint_as_float(raw[4 * j + 3]) + b.w + res[u][j].w);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(tile + lane * 36 + 4 * j) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+                    __syncwarp();
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32 + cq));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int row = k * 4 + rq;
+                        if (row < nvalid) {
+                            const float4 v = *reinterpret_cast<const float4*>(tile + row * 36 + cq);
+                            const float4 r = res[u][k];
+                            *reinterpret_cast<float4*>(obase + (size_t)row * C + c * 32) =
+                                make_float4(v.x + b.x + r.x, v.y + b.y + r.y, v.z + b.z + r.z, v.w + b.w + r.w);
                         }
                     }
                 }
@@ -389,7 +404,7 @@ int mlp_fused_run(const MlpLaunch& l, int num_sms, cudaStream_t stream) {
     const int ksub = p.C / p.bk;
     const size_t a_bytes = (size_t)128 * p.bk * 2 * ksub;
     const size_t w_stage = (size_t)kHC * p.bk * 2 * ksub + (size_t)p.C * kHC * 2;
-    const size_t fixed = a_bytes + 2 * (128 * kHC * 2) + sizeof(MlpBarriers) + 4096 + 1024;
+    const size_t fixed = a_bytes + 2 * (128 * kHC * 2) + sizeof(MlpBarriers) + 4096 + 4 * 32 * 36 * 4 + 1024;   // + softmax exchange + output transpose tiles
     int NS = (int)((230000 - fixed) / w_stage);
     if (NS > 4) NS = 4;
     if (NS < 2) return -42;
