@@ -20,12 +20,28 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
 // ------------------------------------------------------------------------------------------ timestep embedding
 // All weights are pre-transposed to [in][out] so that thread j reads column j with coalesced loads.
 // grid (B, 4): every block recomputes the 2-layer MLP (cheap) and produces a quarter of the 1344 projection outputs.
+// Three dependent matrix-vector products per clip: latency bound, so every layer is split 4 ways along k (thread =
+// 4 consecutive outputs x one k slice, float4 weight loads, 8 loads in flight) and folded through shared memory.
+__device__ __forceinline__ float4 temb_slice(const float* __restrict__ wt, int ld, int col, const float* __restrict__ v,
+                                             int k0, int k1) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(wt + (size_t)k * ld + col);
+        const float x = v[k];
+        acc.x = fmaf(w.x, x, acc.x); acc.y = fmaf(w.y, x, acc.y); acc.z = fmaf(w.z, x, acc.z); acc.w = fmaf(w.w, x, acc.w);
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, TembWeights w, float* tp0, float* tp1,
                                                   float* tp2) {
     __shared__ float emb[96];
     __shared__ float h1[384];
     __shared__ float h2[384];
+    __shared__ float4 part[4][96];
     const int b = blockIdx.x, tid = threadIdx.x;
+    const int og = tid % 96, ks = tid / 96;                  // output group (4 outputs), k slice
     const float tv = t[b];
     if (tid < 48) {
         const float fr = expf((float)tid * -0.19596468876545072f);   // exp(-k * ln(1e4) / 47)
@@ -34,41 +50,38 @@ __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, 
         emb[48 + tid] = cosf(a);
     }
     __syncthreads();
-    {
-        float acc = w.b0[tid];
-#pragma unroll 8
-        for (int k = 0; k < 96; ++k) acc = fmaf(w.w0[k * 384 + tid], emb[k], acc);
-        h1[tid] = swishf(acc);
-    }
+    part[ks][og] = temb_slice(w.w0, 384, 4 * og, emb, ks * 24, ks * 24 + 24);
     __syncthreads();
     {
-        float a0 = w.b1[tid], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;   // 4 independent chains: loads stay in flight
-#pragma unroll 4
-        for (int k = 0; k < 384; k += 4) {
-            a0 = fmaf(w.w1[k * 384 + tid], h1[k], a0);
-            a1 = fmaf(w.w1[(k + 1) * 384 + tid], h1[k + 1], a1);
-            a2 = fmaf(w.w1[(k + 2) * 384 + tid], h1[k + 2], a2);
-            a3 = fmaf(w.w1[(k + 3) * 384 + tid], h1[k + 3], a3);
-        }
-        h2[tid] = swishf((a0 + a1) + (a2 + a3));             // only swish(temb) is consumed (sal_unet.py:129)
+        const float* pf = reinterpret_cast<const float*>(part);
+        h1[tid] = swishf(w.b0[tid] + ((pf[tid] + pf[384 + tid]) + (pf[768 + tid] + pf[1152 + tid])));
     }
     __syncthreads();
-    const int o = blockIdx.y * 336 + tid;                    // 1344 = 192 + 384 + 768 outputs, 336 per block
-    if (tid < 336) {
-        int i, r;
+    part[ks][og] = temb_slice(w.w1, 384, 4 * og, h1, ks * 96, ks * 96 + 96);
+    __syncthreads();
+    {
+        const float* pf = reinterpret_cast<const float*>(part);
+        // only swish(temb) is consumed (sal_unet.py:129)
+        h2[tid] = swishf(w.b1[tid] + ((pf[tid] + pf[384 + tid]) + (pf[768 + tid] + pf[1152 + tid])));
+    }
+    __syncthreads();
+    // 1344 = 192 + 384 + 768 projection outputs, 336 per block = 84 groups of 4 (group boundaries never straddle a layer)
+    const int pg = tid % 84, pks = tid / 84;
+    int i = 0, r = 0, co = 0;
+    if (pks < 4) {
+        const int o = blockIdx.y * 336 + 4 * pg;
         if (o < 192) { i = 0; r = o; } else if (o < 576) { i = 1; r = o - 192; } else { i = 2; r = o - 576; }
-        const int co = w.cout[i];
-        const float* wt = w.wp[i];
-        float a0 = w.bp[i][r], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < 384; k += 4) {
-            a0 = fmaf(wt[k * co + r], h2[k], a0);
-            a1 = fmaf(wt[(k + 1) * co + r], h2[k + 1], a1);
-            a2 = fmaf(wt[(k + 2) * co + r], h2[k + 2], a2);
-            a3 = fmaf(wt[(k + 3) * co + r], h2[k + 3], a3);
-        }
+        co = w.cout[i];
+        part[pks][pg] = temb_slice(w.wp[i], co, r, h2, pks * 96, pks * 96 + 96);
+    }
+    __syncthreads();
+    if (tid < 84) {
+        const float4 p0 = part[0][tid], p1 = part[1][tid], p2 = part[2][tid], p3 = part[3][tid];
+        const float4 bb = *reinterpret_cast<const float4*>(w.bp[i] + r);
         float* out = i == 0 ? tp0 : (i == 1 ? tp1 : tp2);
-        out[(size_t)b * co + r] = (a0 + a1) + (a2 + a3);
+        *reinterpret_cast<float4*>(out + (size_t)b * co + r) =
+            make_float4(bb.x + ((p0.x + p1.x) + (p2.x + p3.x)), bb.y + ((p0.y + p1.y) + (p2.y + p3.y)),
+                        bb.z + ((p0.z + p1.z) + (p2.z + p3.z)), bb.w + ((p0.w + p1.w) + (p2.w + p3.w)));
     }
 }
 
