@@ -118,6 +118,14 @@ int dsb_sampler_dynamic_threshold(float* x, int B, int64_t n, int k, float w, fl
 int dsb_postprocess(const float* x, int B, int64_t pixels_per_map, float* clamped_or_null, uint8_t* u8_or_null,
                     void* stream);
 
+/* saliency metrics on the device: CC, SIM (against a density map), NSS, AUC-Judd (against a binary
+ * fixation map, at most 1024 fixations per clip) of metrics/metrics.py:7-64,178-252 with metrics/utils.py:11-52
+ * normalisation, fp64 accumulation.  pred / density / fixations: device fp32 [B][pixels_per_map]; jitter: device fp64
+ * [B][pixels_per_map] holding the reference's `rand * 1e-7` AUC-J jitter (metrics.py:44-45) or NULL;
+ * out4: device fp64 [B][4] = CC, SIM, NSS, AUC_J. */
+int dsb_metrics(const float* pred, const float* density, const float* fixations, const double* jitter_or_null, int B,
+                int64_t pixels_per_map, double* out4, void* stream);
+
 /* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
 int64_t dsb_last_launch_count(const dsb_handle* h);
 
