@@ -421,13 +421,17 @@ int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, cons
 }
 
 // ------------------------------------------------------------------------------------------ q = LN(dw3x3(LN(x)))
-template <int NV>
+// Wide stages (C = 384, 768; few tokens): one warp per token, a lane owns NVEC float4 channel vectors (LnGeom layout).
+// The 9 neighbour rows are read straight from L1/L2 with 128-bit loads; both LayerNorms are warp reductions.
+template <int C>
 __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
                                                     long tokens, int H, int W, const float* __restrict__ ng,
                                                     const float* __restrict__ nb, const float* __restrict__ wq,
                                                     const float* __restrict__ qg, const float* __restrict__ qb,
                                                     bf16* __restrict__ out, int T, int tmax) {
-    constexpr int C = NV * 32;
+    using G = LnGeom<C>;
+    static_assert(G::LPT == 32, "one token per warp");
+    constexpr int NV = G::NVEC, CV = C / 4;
     const long tok = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tok >= tokens) return;
@@ -436,67 +440,52 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
     if ((int)(f % T) >= tmax) return;
     const int pix = (int)(tok % hw);
     const int y = pix / W, xx = pix % W;
-    float g[NV], b[NV], q[NV];
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* w4 = reinterpret_cast<const float4*>(wq);
+    float4 q[NV], wsum[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { g[i] = ng[lane + 32 * i]; b[i] = nb[lane + 32 * i]; q[i] = 0.0f; }
-    if constexpr (NV >= 12) {
-    // wide rows (few tokens): issue the 9 statistics loads first, then the row loads of all in-image taps
-    float2 st[9];
-    bool ok[9];
+    for (int i = 0; i < NV; ++i) { q[i] = make_float4(0.f, 0.f, 0.f, 0.f); wsum[i] = q[i]; }
+    // conv(LN(x)) = g * sum_k w_k * n_k + b * sum_{k in image} w_k  with  n_k = (x_k - mean_k) * rstd_k
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const int yy = y + k / 3 - 1, xn = xx + k % 3 - 1;
-        ok[k] = (yy >= 0) && (yy < H) && (xn >= 0) && (xn < W);
-        st[k] = ok[k] ? stats[f * hw + (long)yy * W + xn] : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        if (!ok[k]) continue;
-        const int yy = y + k / 3 - 1, xn = xx + k % 3 - 1;
-        const float* row = x + (f * hw + (long)yy * W + xn) * C;
-        const float* wr = wq + k * C;
+        if (yy < 0 || yy >= H || xn < 0 || xn >= W) continue;          // warp-uniform
+        const long nt = f * hw + (long)yy * W + xn;
+        const float2 st = stats[nt];
+        const float a = st.y, c0 = -st.x * st.y;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            const float xv = (row[c] - st[k].x) * st[k].y * g[i] + b[i];
-            q[i] = fmaf(wr[c], xv, q[i]);
-        }
-    }
-    } else {
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xn = xx + dx;
-                if (xn < 0 || xn >= W) continue;
-                const long nt = f * hw + (long)yy * W + xn;
-                const float2 st = stats[nt];
-                const float* row = x + nt * C;
-                const float* wr = wq + ((dy + 1) * 3 + (dx + 1)) * C;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const int c = lane + 32 * i;
-                    const float xv = (row[c] - st.x) * st.y * g[i] + b[i];
-                    q[i] = fmaf(wr[c], xv, q[i]);
-                }
-            }
+            const float4 v = x4[nt * CV + lane + 32 * i];
+            const float4 w = __ldg(w4 + k * CV + lane + 32 * i);
+            q[i].x = fmaf(w.x, fmaf(v.x, a, c0), q[i].x); q[i].y = fmaf(w.y, fmaf(v.y, a, c0), q[i].y);
+            q[i].z = fmaf(w.z, fmaf(v.z, a, c0), q[i].z); q[i].w = fmaf(w.w, fmaf(v.w, a, c0), q[i].w);
+            wsum[i].x += w.x; wsum[i].y += w.y; wsum[i].z += w.z; wsum[i].w += w.w;
         }
     }
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += q[i];
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(ng) + lane + 32 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(nb) + lane + 32 * i);
+        q[i].x = fmaf(g.x, q[i].x, b.x * wsum[i].x); q[i].y = fmaf(g.y, q[i].y, b.y * wsum[i].y);
+        q[i].z = fmaf(g.z, q[i].z, b.z * wsum[i].z); q[i].w = fmaf(g.w, q[i].w, b.w * wsum[i].w);
+        s += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+    }
     const float mean = warp_sum(s) * (1.0f / C);
     float v2 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { const float d = q[i] - mean; v2 = fmaf(d, d, v2); }
+    for (int i = 0; i < NV; ++i) {
+        const float a = q[i].x - mean, b = q[i].y - mean, c = q[i].z - mean, d = q[i].w - mean;
+        v2 = fmaf(a, a, v2); v2 = fmaf(b, b, v2); v2 = fmaf(c, c, v2); v2 = fmaf(d, d, v2);
+    }
     const float rstd = rsqrtf(warp_sum(v2) * (1.0f / C) + 1e-5f);
-    bf16* o = out + tok * C;
+    uint2* o = reinterpret_cast<uint2*>(out + tok * C);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        o[c] = __float2bfloat16((q[i] - mean) * rstd * qg[c] + qb[c]);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(qg) + lane + 32 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(qb) + lane + 32 * i);
+        o[lane + 32 * i] = make_uint2(pack_bf16x2((q[i].x - mean) * rstd * g.x + b.x, (q[i].y - mean) * rstd * g.y + b.y),
+                                      pack_bf16x2((q[i].z - mean) * rstd * g.z + b.z, (q[i].w - mean) * rstd * g.w + b.w));
     }
 }
 
@@ -615,11 +604,9 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
         DSB_LAUNCH_CHECK();
     }
     switch (C) {
-        case 96: q_dwln_kernel<3><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        case 192: q_dwln_kernel<6><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        case 384: q_dwln_kernel<12><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        case 768: q_dwln_kernel<24><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        default: return -31;
+        case 384: q_dwln_kernel<384><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 768: q_dwln_kernel<768><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        default: return -31;     // C = 96 / 192 need W % 32 / W % 16 == 0 (tiled kernel above)
     }
     DSB_LAUNCH_CHECK();
 }
