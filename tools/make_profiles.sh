@@ -1,10 +1,10 @@
 #!/bin/bash
-# Runs on the GPU box (one gpurun call): ncu evidence for profiles/ (B=8 audio-visual, scratch/ncu_one_eval.py =
+# Runs on the GPU box (one gpurun call): ncu evidence for profiles/ (B=8 audio-visual, tools/ncu_one_eval.py =
 # weight prep + conditioning + 2 denoiser evaluations).  Outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
-PY="python scratch/ncu_one_eval.py"
+PY="python tools/ncu_one_eval.py"
 # (1) launch list of the whole run
 $NCU --metrics gpu__time_duration.sum -c 800 --csv --log-file gpurun_out/r1_launches.csv $PY > /dev/null 2>&1
 # (2) DRAM traffic + duration of every GEMM-class launch

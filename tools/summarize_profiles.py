@@ -1,4 +1,4 @@
-"""Builds the tracked summaries under profiles/ from the raw ncu outputs in gpurun_out/ (scratch/make_profiles.sh)."""
+"""Builds the tracked summaries under profiles/ from the raw ncu outputs in gpurun_out/ (tools/make_profiles.sh)."""
 import csv, io, os, re, subprocess, sys, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
@@ -29,7 +29,7 @@ for r in rows:
     us = float(r["Metric Value"]) / 1e3
     a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0]); a[0] += 1; a[1] += us; tot += us
 with open(os.path.join(P, "r1_launches_summary.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv python scratch/ncu_one_eval.py\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv python tools/ncu_one_eval.py\n")
     f.write("# B=8 audio-visual: weight prep + conditioning + 2 denoiser evaluations; per-launch times are cold-cache and\n")
     f.write("# serialised -> compare SHARES with bench.py's CUDA-event numbers, not absolutes\n")
     f.write("launches %d total us %.1f\n" % (len(rows), tot))
@@ -66,7 +66,7 @@ dram = sum(by_id[i].get("dram__bytes_read.sum", 0) + by_id[i].get("dram__bytes_w
 dur = sum(by_id[i]["gpu__time_duration.sum"] for i in sel)
 with open(os.path.join(P, "r1_gemm_traffic_summary.txt"), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-            "-k regex:'gemm_tc|mlp_fused|splitk_reduce' python scratch/ncu_one_eval.py (B=8)\n# second (warm) evaluation only\n")
+            "-k regex:'gemm_tc|mlp_fused|splitk_reduce' python tools/ncu_one_eval.py (B=8)\n# second (warm) evaluation only\n")
     f.write("launches %d\ndram_bytes_total %d\nduration_us_total %.1f\navg_dram_bytes_per_launch %d\n" % (per_eval_tc, dram, dur, dram / per_eval_tc))
 print("traffic: %d tensor-core launches / evaluation, %.1f MB DRAM per launch" % (per_eval_tc, dram / per_eval_tc / 1e6))
 
@@ -80,7 +80,7 @@ want = [("gpu__time_duration.sum", "us"), ("sm__throughput.avg.pct_of_peak_susta
         ("sm__inst_executed_pipe_tensor.sum", "tc_inst")]
 with open(os.path.join(P, "r1_gemm_sol.txt"), "w") as f:
     f.write("# ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy "
-            "--clock-control none -k regex:'gemm_tc|mlp_fused' --launch-skip 51 --launch-count 47 python scratch/ncu_one_eval.py\n")
+            "--clock-control none -k regex:'gemm_tc|mlp_fused' --launch-skip 51 --launch-count 47 python tools/ncu_one_eval.py\n")
     f.write("# every tensor-core launch of the second (warm) B=8 evaluation, in program order\n")
     f.write("%3s %-22s %9s %6s %6s %9s %9s %5s %3s\n" % ("#", "kernel", "us", "sm%", "dram%", "dram GB/s", "warps%", "grid", "clu"))
     ki = h.index("Kernel Name")
@@ -105,7 +105,7 @@ for rep, outn, what in [("r1_gemm_mtproj", "r1_gemm_mtproj_ncu.txt", "mt_proj 3x
     r = list(csv.reader(io.StringIO(out)))
     hh, units, row = r[0], r[1], r[2]
     with open(os.path.join(P, outn), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:gemm_tc ... python scratch/ncu_one_eval.py (B=8)\n# %s\n" % what)
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:gemm_tc ... python tools/ncu_one_eval.py (B=8)\n# %s\n" % what)
         for k in keys:
             if k in hh:
                 i = hh.index(k)
