@@ -85,6 +85,20 @@ def _bind(lib):
     lib.dsb_audio_forward.restype = ci
     lib.dsb_audio_last_launch_count.argtypes = [vp]
     lib.dsb_audio_last_launch_count.restype = ci
+    lib.dsb_vggish_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.dsb_vggish_create.restype = ci
+    lib.dsb_vggish_destroy.argtypes = [vp]
+    lib.dsb_vggish_destroy.restype = None
+    lib.dsb_vggish_last_error.argtypes = [vp]
+    lib.dsb_vggish_last_error.restype = ctypes.c_char_p
+    lib.dsb_vggish_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.dsb_vggish_load_weight.restype = ci
+    lib.dsb_vggish_finalize.argtypes = [vp]
+    lib.dsb_vggish_finalize.restype = ci
+    lib.dsb_vggish_forward_feat.argtypes = [vp, vp, vp, ci, vp]
+    lib.dsb_vggish_forward_feat.restype = ci
+    lib.dsb_vggish_last_launch_count.argtypes = [vp]
+    lib.dsb_vggish_last_launch_count.restype = ci
     lib._dsb_bound = True
     return lib
 
@@ -314,3 +328,68 @@ class AudioEngine:
     @property
     def last_launch_count(self):
         return int(self.lib.dsb_audio_last_launch_count(self._h))
+
+
+class VggishEngine:
+    """Handle of the VGGish feature stack (dsb_vggish_*; models/vggish.py:87-103)."""
+
+    def __init__(self, max_frames=72, device=None):
+        if not torch.cuda.is_available():
+            raise DsbError("diff_sal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _bind(_lib.lib())
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_frames = int(max_frames)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.dsb_vggish_create(self.max_frames, ctypes.byref(self._h))
+        if rc != 0:
+            raise DsbError("dsb_vggish_create failed with %d (needs an sm_100 GPU)" % rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dsb_vggish_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.dsb_vggish_last_error(self._h)
+            raise DsbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def load_state_dict(self, state_dict, prefix=""):
+        with torch.cuda.device(self.device):
+            for key, val in state_dict.items():
+                if prefix:
+                    if not key.startswith(prefix):
+                        continue
+                    key = key[len(prefix):]
+                if not key.startswith("features."):
+                    continue                                  # embeddings.*: not on forward_feat's path
+                t = val.detach().to(dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                self._check(self.lib.dsb_vggish_load_weight(self._h, key.encode(), ctypes.c_void_p(t.data_ptr()), shape,
+                                                            t.dim()), "dsb_vggish_load_weight(%s)" % key)
+            self._check(self.lib.dsb_vggish_finalize(self._h), "dsb_vggish_finalize")
+
+    def forward_feat(self, x):
+        """x [frames, 1, 112, 192] -> [frames, 512, 7, 12] fp32 on this engine's device."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 112, 192):
+            raise DsbError("audio patches must be [frames, 1, 112, 192], got %s" % (tuple(x.shape),))
+        F_ = x.shape[0]
+        if F_ < 1 or F_ > self.max_frames:
+            raise DsbError("%d frames outside [1, %d]" % (F_, self.max_frames))
+        a = x.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty((F_, 512, 7, 12), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_vggish_forward_feat(self._h, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                         F_, _stream()), "dsb_vggish_forward_feat")
+        return out
+
+    @property
+    def last_launch_count(self):
+        return int(self.lib.dsb_vggish_last_launch_count(self._h))

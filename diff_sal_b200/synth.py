@@ -172,6 +172,46 @@ def make_audio_attn_state_dict(seed=0, depth=1):
     return sd
 
 
+def vggish_state_dict_spec():
+    """(key, shape) of the reference ``VGGish`` (models/vggish.py:66-124) in registration order."""
+    spec, cin = [], 1
+    for idx, cout in zip((0, 3, 6, 8, 11, 13), (64, 128, 256, 256, 512, 512)):
+        spec += [("features.%d.weight" % idx, (cout, cin, 3, 3)), ("features.%d.bias" % idx, (cout,))]
+        cin = cout
+    for idx, (o, i) in zip((0, 2, 4), ((4096, 512 * 4 * 6), (4096, 4096), (128, 4096))):
+        spec += [("embeddings.%d.weight" % idx, (o, i)), ("embeddings.%d.bias" % idx, (o,))]
+    return spec
+
+
+def make_vggish_state_dict(seed=0, with_embeddings=False):
+    """He-scaled conv weights + small biases (ReLU stack keeps O(1) activations).  The ``embeddings`` MLP (113 M
+    parameters, unused by forward_feat) is only materialised on request."""
+    g = torch.Generator().manual_seed(seed + 4241)
+    sd = {}
+    for key, shape in vggish_state_dict_spec():
+        if key.startswith("embeddings") and not with_embeddings:
+            continue
+        if key.endswith("bias"):
+            v = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            v = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        sd[key] = v.float().contiguous()
+    return sd
+
+
+def make_audio_input(batch, seed=4321, frames=9, hw=(112, 192)):
+    """Log-mel-like audio patches as the loader hands them to forward_vggish (datasets/saliency_db.py:303-305,457):
+    [B, 1, 9, 112, 192], values ~ N(-2, 1.5)."""
+    out = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed + i)
+        out.append(torch.randn((1, 1, frames) + tuple(hw), generator=g) * 1.5 - 2.0)
+    return torch.cat(out, 0)
+
+
 def make_inputs(batch, audio=True, seed=1234):
     """Seeded synthetic clip batch: x_T, the four MViT-shaped feature tensors and the
     audio feature tensor.  Clip ``i`` uses generator seed ``seed + i`` so that a clip's

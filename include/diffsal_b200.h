@@ -27,6 +27,10 @@
  *        AudioAttnNet.__init__ + load_state_dict + forward (models/audio_attention.py:93-143), the once-per-clip
  *        audio transformer whose output VideoSaliencyModel.forward_vggish hands to the decoder
  *        (models/diff_model.py:70-81,97-113) -- SURVEY.md 8f row N1
+ *   dsb_vggish_create / dsb_vggish_load_weight / dsb_vggish_finalize / dsb_vggish_forward_feat
+ *        VGGish.__init__ + load_state_dict + forward_feat (models/vggish.py:87-124) -- SURVEY.md 8f row N2 (audio half)
+ *   dsb_metrics
+ *        metrics.metrics.{CC, SIM, NSS, AUC_Judd} (metrics/metrics.py:7-64,178-252) -- SURVEY.md 8f row N3
  */
 #ifndef DIFFSAL_B200_H
 #define DIFFSAL_B200_H
@@ -158,6 +162,20 @@ int dsb_audio_load_weight(dsb_audio* h, const char* ref_key, const void* data, c
 int dsb_audio_finalize(dsb_audio* h);
 int dsb_audio_forward(dsb_audio* h, const float* audio, float* out, int B, void* stream);
 int dsb_audio_last_launch_count(const dsb_audio* h);
+
+/* ---- VGGish feature stack (models/vggish.py:87-103 `forward_feat`, called once per clip by
+ * VideoSaliencyModel.forward_vggish, models/diff_model.py:70-76) -- SURVEY.md 8f row N2, audio half --------------
+ * Weight keys are VGGish.state_dict()'s ("features.0.weight" ...); "embeddings.*" keys are accepted and ignored
+ * (forward_feat never runs that MLP).  audio: device fp32 [frames][1][112][192] (= audio.view(-1, 1, 112, 192));
+ * out: device fp32 [frames][512][7][12]. */
+typedef struct dsb_vggish dsb_vggish;
+int dsb_vggish_create(int max_frames, dsb_vggish** out);
+void dsb_vggish_destroy(dsb_vggish* h);
+const char* dsb_vggish_last_error(const dsb_vggish* h);
+int dsb_vggish_load_weight(dsb_vggish* h, const char* ref_key, const void* data, const int64_t* shape, int ndim);
+int dsb_vggish_finalize(dsb_vggish* h);
+int dsb_vggish_forward_feat(dsb_vggish* h, const float* audio, float* out, int frames, void* stream);
+int dsb_vggish_last_launch_count(const dsb_vggish* h);
 
 /* ---- single-kernel test entry (tests/test_kernels_gpu.py) ------------------------------------------------- */
 int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt, const void* A,

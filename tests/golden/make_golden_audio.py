@@ -31,6 +31,14 @@ def main():
         dec = ref_loader.build_salunet()
         dec.load_state_dict(synth.make_state_dict("wide"), strict=True)
         out["step_wide_av_attn_t500"] = dec(x, torch.tensor([500]), list(feats), emb)
+    # VGGish feature stack (models/vggish.py:87-103) on one clip's 9 log-mel-like patches; every 4th channel is kept to
+    # bound the fixture size (the CUDA path is additionally compared with the full oracle output on the GPU box)
+    from models.vggish import VGGish
+    vg = VGGish(pretrained=False).eval()
+    vg.load_state_dict(synth.make_vggish_state_dict(), strict=False)
+    with torch.no_grad():
+        feat = vg.forward_feat(synth.make_audio_input(1).view(-1, 1, 112, 192))
+    out["vggish_feat_b1_c4"] = feat[:, ::4]
     for k, v in out.items():
         v = v.detach().float().numpy()
         np.savez_compressed(os.path.join(HERE, k + ".npz"), y=v)

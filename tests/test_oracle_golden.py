@@ -87,3 +87,11 @@ def test_audio_attention_feeds_decoder():
     emb = audio_attention.forward(synth.make_audio_attn_state_dict(), aud)
     y = salunet.forward(synth.make_state_dict("wide"), x, torch.tensor([500]), feats, emb)
     assert (y - gold("step_wide_av_attn_t500")).abs().max().item() < TOL
+
+
+def test_vggish_features():
+    """SURVEY 8f row N2 (audio half): VGGish.forward_feat (models/vggish.py:87-103) against the reference fixture."""
+    from oracle import vggish
+    y = vggish.forward_feat(synth.make_vggish_state_dict(), synth.make_audio_input(1).view(-1, 1, 112, 192))
+    assert y.shape == (9, 512, 7, 12)
+    assert (y[:, ::4] - gold("vggish_feat_b1_c4")).abs().max().item() < 1e-4         # values reach ~30

@@ -217,3 +217,20 @@ def test_ddpm_steps_bit_exact_on_toy_net(monkeypatch):
     assert len(rxs) == len(mxs) == 5 and len(rx0) == len(mx0) == 4
     for a, b in zip(rxs + rx0, mxs + mx0):
         assert torch.equal(a, b)
+
+
+def test_vggish_matches_reference():
+    from oracle import vggish
+    ref_loader.load()
+    from models.vggish import VGGish
+    net = VGGish(pretrained=False).eval()
+    ref_sd = net.state_dict()
+    assert [k for k, _ in synth.vggish_state_dict_spec()] == list(ref_sd.keys())
+    for k, s in synth.vggish_state_dict_spec():
+        assert tuple(ref_sd[k].shape) == tuple(s), k
+    sd = synth.make_vggish_state_dict(seed=2)
+    net.load_state_dict(sd, strict=False)
+    x = synth.make_audio_input(1, seed=9).view(-1, 1, 112, 192)[:3]
+    with torch.no_grad():
+        ref = net.forward_feat(x)
+    assert (vggish.forward_feat(sd, x) - ref).abs().max().item() < 1e-4
