@@ -59,17 +59,19 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     }
 
     {
-        // K sub-blocks per stage: long enough stages that the single-thread MMA issue loop (wait + commit per stage)
-        // stays shorter than the MMAs it issues (>= ~384 tensor cycles per stage), within ~56 KB per stage
+        // K sub-blocks per stage: long stages amortise the barrier round trip of the producer / MMA-issue loops.  A per-role
+        // clock64 trace of upembed.conv1 of the last stage (N = 96, one 22.5 KB sub-block per stage) showed ~500 cycles per
+        // stage against 192 cycles of MMA; three sub-blocks per stage (67.5 KB, 3-deep ring) took it from 175 to 135 us.
+        // Swept on the whole evaluation: <= 72 KB per stage and >= 768 tensor cycles was the best setting.
         const int n_eff = p.two_cta ? bn / 2 : bn;
         const int sub_bytes = (128 + n_eff) * bk * 2;
         const int sub_cycles = (bk / 16) * (bn / 2);
         int ks = 1;
         for (int cand = 1; cand <= p.cin_blocks; ++cand) {
             if (p.cin_blocks % cand) continue;
-            if (cand * sub_bytes > 49152) break;
+            if (cand * sub_bytes > 73728) break;
             ks = cand;
-            if (cand * sub_cycles >= 384) break;
+            if (cand * sub_cycles >= 768) break;
         }
         p.ksub = ks;
     }
