@@ -52,18 +52,12 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.N = op.N;
     p.bn = bn;
     p.ydim = 2;
-    {
-        const long tiles = (long)p.tiles_x * p.tiles_y * p.tiles_f * (op.N / bn);
-        const bool eligible = !op.b_rows_per_frame && !op.out_softmax && (bn / 2) % 8 == 0;
-        p.two_cta = (op.two_cta > 0 || (op.two_cta == 0 && tiles >= 148)) && eligible ? 1 : 0;
-    }
-
-    {
-        // K sub-blocks per stage: long stages amortise the barrier round trip of the producer / MMA-issue loops.  A per-role
-        // clock64 trace of upembed.conv1 of the last stage (N = 96, one 22.5 KB sub-block per stage) showed ~500 cycles per
-        // stage against 192 cycles of MMA; three sub-blocks per stage (67.5 KB, 3-deep ring) took it from 175 to 135 us.
-        // Swept on the whole evaluation: <= 72 KB per stage and >= 768 tensor cycles was the best setting.
-        const int n_eff = p.two_cta ? bn / 2 : bn;
+    // K sub-blocks per stage: long stages amortise the barrier round trip of the producer / MMA-issue loops.  A per-role
+    // clock64 trace of upembed.conv1 of the last stage (N = 96, one 22.5 KB sub-block per stage) showed ~500 cycles per
+    // stage against 192 cycles of MMA; three sub-blocks per stage (67.5 KB, 3-deep ring) took it from 175 to 135 us.
+    // Swept on the whole evaluation: <= 72 KB per stage and >= 768 tensor cycles was the best setting.
+    auto pick_ksub = [&](bool pair) {
+        const int n_eff = pair ? bn / 2 : bn;
         const int sub_bytes = (128 + n_eff) * bk * 2;
         const int sub_cycles = (bk / 16) * (bn / 2);
         int ks = 1;
@@ -73,8 +67,40 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
             ks = cand;
             if (cand * sub_cycles >= 768) break;
         }
-        p.ksub = ks;
+        return ks;
+    };
+    const int taps_ = (op.kind == CONV_3X3 || op.kind == CONV_3X3_S2) ? 9 : (op.kind == CONV_TEMPORAL ? op.kt : 1);
+    const bool pair_ok = !op.b_rows_per_frame && !op.out_softmax && (bn / 2) % 8 == 0;
+
+    // ---- split-K plan (opt-in): few tiles x long K (the encoder's deep convs, ReduceTemp of the small stages).
+    // Everything here is a function of the layer geometry at the NOMINAL frame count only -- tile box, pairing, stage
+    // size, slice count -- so the K partition, and with it the rounding, never depends on the actual batch size.
+    int S_plan = 1;
+    if (op.split_ws && !op.b_rows_per_frame && !op.out_softmax && !op.head_w && !op.f_group) {
+        const int f_nom = op.split_frames_nominal > 0 ? op.split_frames_nominal : op.F;
+        int nbw = 0, nbh = 0;
+        pick_tile(op.W, op.H, f_nom, false, &nbw, &nbh);
+        const int bf_ = 128 >> (nbw + nbh);
+        const long tiles = (long)((op.W + (1 << nbw) - 1) >> nbw) * ((op.H + (1 << nbh) - 1) >> nbh) * ((f_nom + bf_ - 1) / bf_) *
+                           (op.N / bn);
+        if (!(tiles >= 148 && pair_ok)) {                    // the nominal launch would not run as CTA pairs
+            const int nk = taps_ * p.cin_blocks / pick_ksub(false);
+            for (int cand = 2; cand <= 16; ++cand) {
+                if (nk % cand) continue;
+                if (tiles * cand > 148) break;
+                if (nk / cand < 3) break;                    // keep at least 3 pipeline stages of work per slice
+                S_plan = cand;
+            }
+        }
+        if (S_plan > 1 && (long)op.F * op.H * op.W * op.N * S_plan > op.split_ws_elems) return -24;   // scratch too small
     }
+    if (S_plan > 1) {
+        p.two_cta = 0;                                       // slices run on single CTAs at every batch size
+    } else {
+        const long tiles = (long)p.tiles_x * p.tiles_y * p.tiles_f * (op.N / bn);
+        p.two_cta = (op.two_cta > 0 || (op.two_cta == 0 && tiles >= 148)) && pair_ok ? 1 : 0;
+    }
+    p.ksub = pick_ksub(p.two_cta != 0);
 
     uint64_t dims[5], strides[4];
     uint32_t box[5];
@@ -150,37 +176,23 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.epi_transposed = (op.out_f32 && !op.out_bf16 && !op.head_w && !op.out_softmax && bn % 32 == 0) ? 1 : 0;
     p.f_group = op.f_group; p.f_used = op.f_used; p.out_remap = op.out_remap;
 
-    // ---- split-K: few tiles x long K (the encoder's deep convs, ReduceTemp of the small stages at small batch)
-    if (op.split_ws && !p.two_cta && !op.b_rows_per_frame && !op.out_softmax && !op.head_w && !op.f_group) {
-        const int bf_ = 128 >> (p.bw_log2 + p.bh_log2);
-        const int f_nom = op.split_frames_nominal > 0 ? op.split_frames_nominal : op.F;
-        const long tiles = (long)p.tiles_x * p.tiles_y * ((f_nom + bf_ - 1) / bf_) * (op.N / bn);   // at the nominal batch
-        const int nk = p.taps * p.cin_blocks / p.ksub;
+    if (S_plan > 1) {
+        const int S = S_plan;
         const long rows = (long)op.F * op.H * op.W;
-        int S = 1;
-        for (int cand = 2; cand <= 16; ++cand) {
-            if (nk % cand) continue;
-            if (tiles * cand > 148) break;
-            if (nk / cand < 3) break;                       // keep at least 3 pipeline stages of work per slice
-            S = cand;
-        }
-        if (rows * op.N * S > op.split_ws_elems) S = 1;
-        if (S > 1) {
-            SplitReduce& r = out->split;
-            r.ws = op.split_ws; r.S = S; r.slab = rows * op.N;
-            r.rows = (int)rows; r.N = op.N; r.HW = op.H * op.W;
-            r.scale = p.scale; r.shift = p.shift; r.rowbias = p.rowbias; r.residual = p.residual; r.act = p.act;
-            r.out_f32 = p.out_f32; r.out_bf16 = p.out_bf16; r.out2_f32 = p.out2_f32;
-            r.ldo = p.ldo; r.out_fmul = p.out_fmul; r.out_fadd = p.out_fadd; r.out2_fmul = p.out2_fmul; r.out2_fadd = p.out2_fadd;
-            // the GEMM pass writes raw partials, compact rows, plain direct epilogue
-            p.scale = p.shift = p.rowbias = p.residual = nullptr;
-            p.act = ACT_NONE;
-            p.out_f32 = op.split_ws; p.out_bf16 = nullptr; p.out2_f32 = nullptr;
-            p.ldo = op.N; p.out_fmul = 1; p.out_fadd = 0; p.out2_fmul = 1; p.out2_fadd = 0;
-            p.epi_transposed = 0;
-            p.ksplit = S;
-            p.split_stride = r.slab;
-        }
+        SplitReduce& r = out->split;
+        r.ws = op.split_ws; r.S = S; r.slab = rows * op.N;
+        r.rows = (int)rows; r.N = op.N; r.HW = op.H * op.W;
+        r.scale = p.scale; r.shift = p.shift; r.rowbias = p.rowbias; r.residual = p.residual; r.act = p.act;
+        r.out_f32 = p.out_f32; r.out_bf16 = p.out_bf16; r.out2_f32 = p.out2_f32;
+        r.ldo = p.ldo; r.out_fmul = p.out_fmul; r.out_fadd = p.out_fadd; r.out2_fmul = p.out2_fmul; r.out2_fadd = p.out2_fadd;
+        // the GEMM pass writes raw partials, compact rows, plain direct epilogue
+        p.scale = p.shift = p.rowbias = p.residual = nullptr;
+        p.act = ACT_NONE;
+        p.out_f32 = op.split_ws; p.out_bf16 = nullptr; p.out2_f32 = nullptr;
+        p.ldo = op.N; p.out_fmul = 1; p.out_fadd = 0; p.out2_fmul = 1; p.out2_fadd = 0;
+        p.epi_transposed = 0;
+        p.ksplit = S;
+        p.split_stride = r.slab;
     }
     return 0;
 }

@@ -94,3 +94,25 @@ def test_inputs_not_mutated_and_repeatable(engines):
     assert torch.equal(a, b)
     for f, k in zip(fc, keep):
         assert torch.equal(f, k)
+
+
+def test_batch_invariance_at_batch_32():
+    """A clip's evaluation is bitwise the same alone and inside a batch of 32: tile boxes, CTA pairing and split-K
+    slicing change with the batch, the order in which each output's products are added must not (split-K slices are
+    planned at a nominal batch from the layer geometry only)."""
+    from diff_sal_b200.engine import Engine
+    B = 32
+    sd = synth.make_state_dict("wide")
+    x, feats, aud = synth.make_inputs(B, audio=True)
+    big = Engine(B, True)
+    big.load_state_dict(sd)
+    big.set_condition([f.cuda() for f in feats], aud.cuda())
+    t = torch.full((B,), 500.0)
+    yb = big.denoise(x.cuda(), t)
+    one = Engine(1, True)
+    one.load_state_dict(sd)
+    for i in (0, 13, 31):
+        one.set_condition([f[i:i + 1].cuda() for f in feats], aud[i:i + 1].cuda())
+        assert torch.equal(one.denoise(x[i:i + 1].cuda(), t[:1]), yb[i:i + 1]), i
+    big.close()
+    one.close()
