@@ -214,6 +214,11 @@ void dsb_test_set_two_cta(int mode);
 void dsb_test_set_split_ws(float* ws, long elems);
 int dsb_test_last_ksplit(void);
 
+/* hardware-semantics probe: UMMA SWIZZLE_128B operand descriptor with a row-shifted start and a non-atom SBO
+ * (DESIGN.md section 8 item 1).  A bf16 [512][64], B bf16 [32][64], out fp32 [128][32] (device). */
+int dsb_test_umma_shift(const void* A, const void* B, float* out, int shift_rows, int sbo_bytes, int base_offset_mode,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -222,3 +222,22 @@ def test_splitk_temporal_reduce_and_stride2(L, split_ws):
     out = out.reshape(Fr, 9, H, W, C)
     close(out[:, 8].permute(0, 3, 1, 2), ref, 2e-3)
     assert out[:, :8].abs().max().item() == 0.0
+
+
+def test_umma_row_shifted_descriptor(L):
+    """Hardware-semantics probe behind the halo-tile convolution: a SWIZZLE_128B K-major operand descriptor
+    may start at any 128-byte row of a TMA-written tile and space its 8-row groups by any multiple of 128 bytes (the
+    swizzle is a function of the shared-memory address; the descriptor's base-offset field must stay 0)."""
+    lib = L.lib()
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(512, 64, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(32, 64, generator=g).to(torch.bfloat16).cuda()
+    m = torch.arange(128)
+    for sbo in (1024, 1280, 1536):
+        for shift in (0, 1, 3, 8, 13):
+            out = torch.zeros(128, 32, device="cuda")
+            assert lib.dsb_test_umma_shift(L.ptr(A), L.ptr(B), L.ptr(out), shift, sbo, 0, L.stream_ptr()) == 0
+            torch.cuda.synchronize()
+            rows = ((m // 8) * (sbo // 128) + m % 8 + shift).cuda()
+            ref = A[rows].float() @ B.float().t()
+            assert (out - ref).abs().max().item() < 1e-3, (sbo, shift)
