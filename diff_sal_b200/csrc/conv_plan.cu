@@ -102,6 +102,29 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     }
     p.ksub = pick_ksub(p.two_cta != 0);
 
+    // ---- halo-tile path (opt-in): the nine taps of a 3x3 conv re-read every input pixel from L2 nine times; with a small N
+    // the launch is bound by the chip-wide L2 throughput (~43 B/cycle/SM), not by the tensor pipe.  One TMA box per
+    // (8x16-pixel tile, 64-channel block) holding the tile plus its dilation halo replaces the nine per-tap boxes (23-31 KB
+    // instead of 144 KB); the taps become row-shifted UMMA descriptors into it (tests: test_umma_row_shifted_descriptor).
+    bool halo = false;
+    if (op.halo && op.kind == CONV_3X3 && bk == 64 && S_plan == 1 && pair_ok && op.two_cta >= 0 && !op.f_group && bn <= 128 &&
+        op.dilation >= 1 && op.dilation <= 4) {
+        const long tiles8 = (long)((op.W + 7) / 8) * ((op.H + 15) / 16) * op.F * (op.N / bn);
+        const long rows_box = (long)((op.W + 7) / 8) * 8 * ((op.H + 15) / 16) * 16;
+        // worth it when the 8x16 tiling wastes few rows and there are enough tiles for CTA pairs
+        if (tiles8 >= 148 && rows_box * 100 <= (long)op.W * op.H * 120) {
+            halo = true;
+            p.halo = 1;
+            p.halo_d = op.dilation;
+            p.halo_pw = 8 + 2 * op.dilation;
+            p.halo_ph = 16 + 2 * op.dilation;
+            p.bw_log2 = 3; p.bh_log2 = 4;
+            p.tiles_x = (op.W + 7) / 8; p.tiles_y = (op.H + 15) / 16; p.tiles_f = op.F;
+            p.two_cta = 1;
+            p.ksub = 1;
+        }
+    }
+
     uint64_t dims[5], strides[4];
     uint32_t box[5];
     const uint64_t e = 2;   // bytes per bf16
@@ -116,6 +139,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
         strides[0] = C * e; strides[1] = (uint64_t)op.W * C * e; strides[2] = (uint64_t)op.H * op.W * C * e;
         strides[3] = (uint64_t)op.H * op.W * C * e;
         box[0] = bk; box[1] = bw; box[2] = bh; box[3] = 1; box[4] = bf;
+        if (halo) { box[1] = p.halo_pw; box[2] = p.halo_ph; box[4] = 1; }
     } else if (op.kind == CONV_1X1) {
         p.taps = 1;
         dims[0] = C; dims[1] = op.W; dims[2] = op.H; dims[3] = 1; dims[4] = op.F;

@@ -40,6 +40,8 @@ struct ConvOp {
     float* out2_f32;        // optional second fp32 output with its own frame mapping
     int out2_fmul, out2_fadd;
     int two_cta;            // -1: never, 0: automatic (pairs when there are enough tiles), 1: force
+    int halo;               // 1: request the halo-tile path (CONV_3X3, Cin % 64 == 0, N <= 128, enough 8x16 tiles for CTA
+                            //    pairs); silently falls back to the per-tap path when the layer does not qualify
     // split-K (opt-in): fp32 scratch for the per-slice partial sums.  Used when the GEMM has too few tiles to fill
     // the machine and a long K loop; the slices are added in a fixed order by splitk_reduce (bitwise reproducible).
     float* split_ws;

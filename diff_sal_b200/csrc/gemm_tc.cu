@@ -41,9 +41,14 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     const uint32_t a_sub = 128u * p.bk * 2u;
     const uint32_t bn_local = two ? (uint32_t)p.bn / 2u : (uint32_t)p.bn;
     const uint32_t b_sub = bn_local * p.bk * 2u;
-    const uint32_t a_bytes = a_sub * p.ksub;
-    const uint32_t b_bytes = b_sub * p.ksub;
+    // halo mode: a stage = the halo tile of one 64-channel block (rounded up to the 1024-byte swizzle atom) + the nine
+    // per-tap weight tiles of that block
+    const bool halo = p.halo != 0;
+    const uint32_t halo_tx = (uint32_t)(p.halo_pw * p.halo_ph) * 128u;
+    const uint32_t a_bytes = halo ? ((halo_tx + 1023u) & ~1023u) : a_sub * p.ksub;
+    const uint32_t b_bytes = halo ? 9u * b_sub : b_sub * p.ksub;
     const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t tx_bytes = halo ? halo_tx + b_bytes : stage_bytes;      // bytes TMA actually delivers per stage
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + (size_t)num_stages * stage_bytes);
     // per-epilogue-warp transpose tile [32 rows][36 words] + row table, behind the barriers
     float* epi_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(GemmBarriers));
@@ -81,7 +86,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     const int unit_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;         // K slices per tile (split-K for tile-poor, K-long GEMMs)
     const int total_units = total_tiles * ksplit;
-    const int nk = p.taps * p.cin_blocks / p.ksub / ksplit; // pipeline stages per work unit
+    const int nk = halo ? p.cin_blocks : p.taps * p.cin_blocks / p.ksub / ksplit;   // pipeline stages per work unit
     const int bh_log2 = p.bh_log2, bw_log2 = p.bw_log2;
 
     if (warp == 0) {
@@ -111,14 +116,25 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 if (elect_one()) {
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     if constexpr (!two) {
-                        mbar_expect_tx(&bars->full[s], stage_bytes);
+                        mbar_expect_tx(&bars->full[s], tx_bytes);
                     } else {
                         // both CTAs' bytes are credited to the leader's barrier
-                        if (rank == 0) mbar_expect_tx(&bars->full[s], 2u * stage_bytes);
+                        if (rank == 0) mbar_expect_tx(&bars->full[s], 2u * tx_bytes);
                         else mbar_arrive_leader(&bars->full[s]);
                     }
+                    if (halo) {
+                        // one box = the tile's pixels plus the dilation halo (out-of-image parts zero-filled = padding)
+                        const int c0 = kb * 64, hx = x0 - p.halo_d, hy = y0 - p.halo_d;
+                        if constexpr (!two) tma_load_5d(sa, &tmA, &bars->full[s], c0, hx, hy, 0, f0);
+                        else tma_load_5d_2sm(sa, &tmA, &bars->full[s], c0, hx, hy, 0, f0);
+                        for (int t = 0; t < 9; ++t) {
+                            const int kcol = (t * p.cin_blocks + kb) * 64;
+                            if constexpr (!two) tma_load_2d(sa + a_bytes + t * b_sub, &tmB, &bars->full[s], kcol, brow);
+                            else tma_load_2d_2sm(sa + a_bytes + t * b_sub, &tmB, &bars->full[s], kcol, brow);
+                        }
+                    }
                     int tp = tap, c = cb;
-                    for (int j = 0; j < p.ksub; ++j) {
+                    for (int j = 0; j < (halo ? 0 : p.ksub); ++j) {
                         const int c0 = p.tap_off[tp][0] + c * p.bk;
                         const int c1 = p.tap_off[tp][1] + x0;
                         const int c2 = p.tap_off[tp][2] + y2;
@@ -167,7 +183,22 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     if (elect_one()) {
                         uint64_t da = da0 + (uint64_t)((uint32_t)s * stage_step);
                         uint64_t db = db0 + (uint64_t)((uint32_t)s * stage_step);
-                        for (int j = 0; j < p.ksub; ++j) {
+                        if (halo) {
+                            // nine taps = nine row-shifted views of the halo tile: start + ((ty*d)*PW + tx*d) rows of 128 B,
+                            // 8-row groups (one image row of the 8-pixel-wide tile) PW rows apart
+                            const uint64_t dah = (da & ~(0x3FFFull << 32)) | ((uint64_t)((uint32_t)p.halo_pw * 128u >> 4) << 32);
+#pragma unroll 1
+                            for (int t = 0; t < 9; ++t) {
+                                const uint32_t roff = (uint32_t)((t / 3) * p.halo_d * p.halo_pw + (t % 3) * p.halo_d) * 8u;   // 16-B units
+                                const uint64_t a_t = dah + roff, b_t = db + (uint64_t)((uint32_t)t * (uint32_t)b_sub_step);
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t acc_f = (kb | t | k) ? 1u : 0u;
+                                    if constexpr (two) umma_bf16_2sm(d_tmem, a_t + 2 * k, b_t + 2 * k, idesc, acc_f);
+                                    else umma_bf16(d_tmem, a_t + 2 * k, b_t + 2 * k, idesc, acc_f);
+                                }
+                            }
+                        }
+                        for (int j = 0; j < (halo ? 0 : p.ksub); ++j) {
                             const uint32_t first = (kb | j) ? 1u : 0u;
                             if constexpr (two) {
                                 umma_bf16_2sm(d_tmem, da, db, idesc, first);
@@ -525,7 +556,13 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
             return -22;
         if ((p.taps * p.cin_blocks / p.ksub) % p.ksplit) return -22;
     }
-    const uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
+    uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
+    if (p.halo) {
+        if (p.bk != 64 || p.taps != 9 || p.bw_log2 != 3 || p.bh_log2 != 4 || p.ksplit > 1 || p.ydim != 2 || p.halo_d < 1 ||
+            p.halo_pw != 8 + 2 * p.halo_d || p.halo_ph != 16 + 2 * p.halo_d)
+            return -23;
+        stage_bytes = (((uint32_t)(p.halo_pw * p.halo_ph) * 128u + 1023u) & ~1023u) + 9u * (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * 128u;
+    }
     const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;
     int stages = (int)(budget / stage_bytes);

@@ -43,6 +43,8 @@ struct GemmParams {
     const float* residual;          // fp32 [pix][N] or null
     int act;
     int epi_transposed;             // 1: stage 32-column chunks through smem for row-coalesced global access
+    int halo;                       // 1: halo-tile 3x3 conv -- one TMA box of (8 + 2d) x (16 + 2d) pixels per 64-channel block
+    int halo_pw, halo_ph, halo_d;   //    serves all nine taps as row-shifted UMMA descriptors (tile = 8 x 16 pixels, bk = 64)
     int ksplit;                     // > 1: split-K -- work unit = (tile, K slice); slice ks writes its raw fp32 partial to
     long split_stride;              //      out_f32 + ks * split_stride (plain epilogue; splitk_reduce finishes the op)
     float* out_f32;                 // [pix][ldo] or null

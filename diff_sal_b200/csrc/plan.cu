@@ -435,6 +435,7 @@ int build_program(dsb_handle* h) {
                 ConvOp op = make_op(CONV_3X3, F, H, Wd, Cp, C, up, WP(pe + "1.weight"));
                 op.dilation = 2; op.scale = WF(pe + "2.scale"); op.shift = WF(pe + "2.shift"); op.act = ACT_RELU;
                 op.out_bf16 = h->mid;
+                op.halo = 1;                                   // taken where the layer qualifies (N <= 128: the last stage)
                 b.conv(op, "upembed.conv1");
             }
             {
@@ -614,6 +615,7 @@ int build_program(dsb_handle* h) {
         float hb = 0.0f;
         cudaMemcpy(&hb, W(h, "logits.linear_pred.bias"), sizeof(float), cudaMemcpyDeviceToHost);
         op.head_b = hb; op.out_head = h->p;
+        op.halo = 1;
         b.conv(op, "mt_proj_head");
         const float* p = h->p;
         b.add([h, p, B](cudaStream_t s) { return final_up_launch(p, B, h->cur_out, s); }, "final_up", (double)B * (86016.0 + 344064.0));

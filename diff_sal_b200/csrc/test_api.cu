@@ -13,6 +13,11 @@ static int num_sms_cached() {
     return n;
 }
 
+static int g_test_halo = 0;
+// 1: request the halo-tile path in dsb_test_conv; dsb_test_last_halo() tells whether the last lowered op took it
+static int g_test_last_halo = 0;
+extern "C" void dsb_test_set_halo(int on) { g_test_halo = on; }
+extern "C" int dsb_test_last_halo(void) { return g_test_last_halo; }
 static int g_test_two_cta = 0;
 // -1: never use CTA pairs, 0: automatic, 1: always (for the per-kernel tests)
 extern "C" void dsb_test_set_two_cta(int mode) { g_test_two_cta = mode; }
@@ -38,10 +43,12 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     op.head_w = head_w; op.head_b = head_b; op.out_head = out_head;
     op.two_cta = g_test_two_cta;
     op.split_ws = g_test_split_ws; op.split_ws_elems = g_test_split_elems;
+    op.halo = g_test_halo;
     ConvLaunch l;
     int r = conv_lower(op, &l);
     if (r) return r;
     g_test_last_ksplit = l.split.S;
+    g_test_last_halo = l.p.halo;
     return conv_run(l, num_sms_cached(), (cudaStream_t)stream);
 }
 

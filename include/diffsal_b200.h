@@ -213,6 +213,9 @@ void dsb_test_set_two_cta(int mode);
 /* split-K scratch of dsb_test_conv (NULL: never split) and the slice count its last call used (0: not split) */
 void dsb_test_set_split_ws(float* ws, long elems);
 int dsb_test_last_ksplit(void);
+/* request the halo-tile 3x3 path in dsb_test_conv, and whether its last call took it */
+void dsb_test_set_halo(int on);
+int dsb_test_last_halo(void);
 
 /* hardware-semantics probe: UMMA SWIZZLE_128B operand descriptor with a row-shifted start and a non-atom SBO
  * (DESIGN.md section 8 item 1).  A bf16 [512][64], B bf16 [32][64], out fp32 [128][32] (device). */

@@ -241,3 +241,45 @@ def test_umma_row_shifted_descriptor(L):
             rows = ((m // 8) * (sbo // 128) + m % 8 + shift).cuda()
             ref = A[rows].float() @ B.float().t()
             assert (out - ref).abs().max().item() < 1e-3, (sbo, shift)
+
+
+@pytest.fixture
+def halo(L):
+    lib = L.lib()
+    lib.dsb_test_set_halo(1)
+    yield lib
+    lib.dsb_test_set_halo(0)
+
+
+@pytest.mark.parametrize("Fr,H,W,Cin,N,dil", [(8, 56, 96, 192, 96, 2), (4, 56, 96, 64, 96, 1), (3, 112, 192, 128, 96, 1),
+                                              (5, 60, 92, 128, 64, 2)])
+def test_conv3x3_halo_tiles(L, halo, Fr, H, W, Cin, N, dil):
+    """Halo-tile path: one TMA box per (8x16 tile, 64-channel block) serves all nine taps as row-shifted descriptors.
+    Same results as the per-tap path (bitwise: same products, same K order per output) and as torch."""
+    x = _rand(Fr, Cin, H, W, seed=40).to(torch.bfloat16)
+    w = _rand(N, Cin, 3, 3, seed=41, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    scale, shift = 1.0 + 0.1 * _rand(N, seed=42), _rand(N, seed=43)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, Cin, dilation=dil, scale=scale, shift=shift, act=ACT_RELU, want="bf16")
+    assert halo.dsb_test_last_halo() == 1
+    ref = F.relu(F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil) * scale[None, :, None, None] + shift[None, :, None, None])
+    close(out.permute(0, 3, 1, 2), ref, 1e-2)
+    halo.dsb_test_set_halo(0)
+    plain = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, Cin, dilation=dil, scale=scale, shift=shift, act=ACT_RELU, want="bf16")
+    assert halo.dsb_test_last_halo() == 0
+    halo.dsb_test_set_halo(1)
+    assert (out.float() - plain.float()).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+def test_conv3x3_halo_head_epilogue(L, halo):
+    Fr, H, W, Cin, N = 2, 112, 192, 256, 96
+    x = _rand(Fr, Cin, H, W, seed=44).to(torch.bfloat16)
+    w = _rand(N, Cin, 3, 3, seed=45, scale=(9 * Cin) ** -0.5).to(torch.bfloat16)
+    scale, shift, hw = 1.0 + 0.1 * _rand(N, seed=46), _rand(N, seed=47), _rand(N, seed=48, scale=0.3)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = run_conv(L, CONV_3X3, a, pack_w(w), N, Fr, H, W, Cin, scale=scale, shift=shift, act=ACT_RELU, want="head", head_w=hw,
+                   head_b=0.25)
+    assert halo.dsb_test_last_halo() == 1
+    ref = F.relu(F.conv2d(x.float(), w.float(), None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    ref = torch.sigmoid((ref * hw[None, :, None, None]).sum(1) + 0.25)
+    close(out, ref, 2e-3)
