@@ -39,7 +39,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     const int C = op.Cin;
     const int bk = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
     if (!bk) return -20;
-    const int bn = pick_bn(op.N);
+    int bn = pick_bn(op.N);
     if (!bn) return -21;
     p.W = op.W; p.H = op.H; p.F = op.F;
     pick_tile(op.W, op.H, op.F, op.b_rows_per_frame != 0 || op.f_group != 0, &p.bw_log2, &p.bh_log2);
@@ -107,13 +107,29 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     // (8x16-pixel tile, 64-channel block) holding the tile plus its dilation halo replaces the nine per-tap boxes (23-31 KB
     // instead of 144 KB); the taps become row-shifted UMMA descriptors into it (tests: test_umma_row_shifted_descriptor).
     bool halo = false;
-    if (op.halo && op.kind == CONV_3X3 && bk == 64 && S_plan == 1 && pair_ok && op.two_cta >= 0 && !op.f_group && bn <= 128 &&
-        op.dilation >= 1 && op.dilation <= 4) {
-        const long tiles8 = (long)((op.W + 7) / 8) * ((op.H + 15) / 16) * op.F * (op.N / bn);
+    if (op.halo && op.kind == CONV_3X3 && S_plan == 1 && !op.b_rows_per_frame && !op.out_softmax && op.two_cta >= 0 &&
+        !op.f_group && op.dilation >= 1 && op.dilation <= 4) {
+        // N tile: at most 128 columns (a stage holds the nine weight tiles of a channel block); wider layers are cut into
+        // up to 4 N tiles, each of which re-reads the (cheap) halo tiles
+        // two stages must fit beside the epilogue's shared memory (61 KB when the row-coalesced epilogue is used)
+        const bool epi_t = op.out_f32 && !op.out_bf16 && !op.head_w;
+        const long budget = 225L * 1024 - 2048 - (epi_t ? 12L * (32 * 36 + 128) * 4 : 0) - 3 * 128 * 4;
+        const long a_h = (((long)(8 + 2 * op.dilation) * (16 + 2 * op.dilation) * bk * 2) + 1023) & ~1023L;
+        int bn_h = 0;
+        for (int cand = 128; cand >= 32; cand -= 32) {
+            if (op.N % cand || op.N / cand > 4) continue;
+            if (2 * (a_h + 9L * (cand / 2) * bk * 2) > budget) continue;
+            bn_h = cand;
+            break;
+        }
+        if (op.head_w && bn_h != op.N) bn_h = 0;             // the fused head needs the whole row in one tile
+        const long tiles8 = bn_h ? (long)((op.W + 7) / 8) * ((op.H + 15) / 16) * op.F * (op.N / bn_h) : 0;
         const long rows_box = (long)((op.W + 7) / 8) * 8 * ((op.H + 15) / 16) * 16;
         // worth it when the 8x16 tiling wastes few rows and there are enough tiles for CTA pairs
-        if (tiles8 >= 148 && rows_box * 100 <= (long)op.W * op.H * 120) {
+        if (bn_h && tiles8 >= 148 && rows_box * 100 <= (long)op.W * op.H * 120) {
             halo = true;
+            bn = bn_h;
+            p.bn = bn;
             p.halo = 1;
             p.halo_d = op.dilation;
             p.halo_pw = 8 + 2 * op.dilation;

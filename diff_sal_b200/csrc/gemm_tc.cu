@@ -44,7 +44,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     // halo mode: a stage = the halo tile of one 64-channel block (rounded up to the 1024-byte swizzle atom) + the nine
     // per-tap weight tiles of that block
     const bool halo = p.halo != 0;
-    const uint32_t halo_tx = (uint32_t)(p.halo_pw * p.halo_ph) * 128u;
+    const uint32_t halo_tx = (uint32_t)(p.halo_pw * p.halo_ph) * (uint32_t)p.bk * 2u;
     const uint32_t a_bytes = halo ? ((halo_tx + 1023u) & ~1023u) : a_sub * p.ksub;
     const uint32_t b_bytes = halo ? 9u * b_sub : b_sub * p.ksub;
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -110,7 +110,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             // per-frame B operand is indexed by the SOURCE frame; a pair splits the B rows between its CTAs
             const int brow = nt * p.bn + (two ? (int)(rank * bn_local) : f0 * p.b_rows_per_frame);
             const int sub0 = ks * nk * p.ksub;                 // first K sub-block of this slice
-            int tap = sub0 / p.cin_blocks, cb = sub0 % p.cin_blocks;
+            // K order: channel block outer, tap inner -- the order the halo path needs (one box per channel block), used by
+            // both paths so that a layer's rounding does not depend on which of them a batch size selects
+            int cb = sub0 / p.taps, tap = sub0 % p.taps;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&bars->empty[s], phase ^ 1u);
                 if (elect_one()) {
@@ -124,11 +126,11 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     }
                     if (halo) {
                         // one box = the tile's pixels plus the dilation halo (out-of-image parts zero-filled = padding)
-                        const int c0 = kb * 64, hx = x0 - p.halo_d, hy = y0 - p.halo_d;
+                        const int c0 = kb * p.bk, hx = x0 - p.halo_d, hy = y0 - p.halo_d;
                         if constexpr (!two) tma_load_5d(sa, &tmA, &bars->full[s], c0, hx, hy, 0, f0);
                         else tma_load_5d_2sm(sa, &tmA, &bars->full[s], c0, hx, hy, 0, f0);
                         for (int t = 0; t < 9; ++t) {
-                            const int kcol = (t * p.cin_blocks + kb) * 64;
+                            const int kcol = (t * p.cin_blocks + kb) * p.bk;
                             if constexpr (!two) tma_load_2d(sa + a_bytes + t * b_sub, &tmB, &bars->full[s], kcol, brow);
                             else tma_load_2d_2sm(sa + a_bytes + t * b_sub, &tmB, &bars->full[s], kcol, brow);
                         }
@@ -147,12 +149,12 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             tma_load_5d_2sm(sa + j * a_sub, &tmA, &bars->full[s], c0, c1, c2, c3, f0);
                             tma_load_2d_2sm(sa + a_bytes + j * b_sub, &tmB, &bars->full[s], kcol, brow);
                         }
-                        if (++c == p.cin_blocks) { c = 0; ++tp; }
+                        if (++tp == p.taps) { tp = 0; ++c; }
                     }
                 }
                 __syncwarp();
-                cb += p.ksub;
-                if (cb >= p.cin_blocks) { cb -= p.cin_blocks; ++tap; }     // ksub divides cin_blocks
+                tap += p.ksub;
+                while (tap >= p.taps) { tap -= p.taps; ++cb; }
                 if (++s == num_stages) { s = 0; phase ^= 1u; }
             }
         }
@@ -169,6 +171,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const uint32_t stage_step = stage_bytes >> 4;   // descriptor start-address units (16 B)
             const uint64_t a_sub_step = a_sub >> 4, b_sub_step = b_sub >> 4;
             const bool k64 = p.bk == 64;
+            // halo mode: descriptor field for the 8-row group stride (= one halo row) and the per-tap start offsets
+            const uint32_t row16 = row_bytes >> 4;                                  // 16-byte units per pixel row
+            const uint64_t halo_sbo = (uint64_t)((uint32_t)p.halo_pw * row16) << 32;
+            const uint32_t halo_step_x = (uint32_t)p.halo_d * row16, halo_step_y = halo_step_x * (uint32_t)p.halo_pw;
             int s = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -186,15 +192,28 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         if (halo) {
                             // nine taps = nine row-shifted views of the halo tile: start + ((ty*d)*PW + tx*d) rows of 128 B,
                             // 8-row groups (one image row of the 8-pixel-wide tile) PW rows apart
-                            const uint64_t dah = (da & ~(0x3FFFull << 32)) | ((uint64_t)((uint32_t)p.halo_pw * 128u >> 4) << 32);
-#pragma unroll 1
+                            // (fully unrolled, constants folded: this single-thread loop must stay well below the
+                            // 48-cycle MMA it issues)
+                            const uint64_t dah = (da & ~(0x3FFFull << 32)) | halo_sbo;
+#pragma unroll
                             for (int t = 0; t < 9; ++t) {
-                                const uint32_t roff = (uint32_t)((t / 3) * p.halo_d * p.halo_pw + (t % 3) * p.halo_d) * 8u;   // 16-B units
-                                const uint64_t a_t = dah + roff, b_t = db + (uint64_t)((uint32_t)t * (uint32_t)b_sub_step);
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint32_t acc_f = (kb | t | k) ? 1u : 0u;
-                                    if constexpr (two) umma_bf16_2sm(d_tmem, a_t + 2 * k, b_t + 2 * k, idesc, acc_f);
-                                    else umma_bf16(d_tmem, a_t + 2 * k, b_t + 2 * k, idesc, acc_f);
+                                const uint64_t a_t = dah + (uint64_t)((uint32_t)(t / 3) * halo_step_y + (uint32_t)(t % 3) * halo_step_x);
+                                const uint64_t b_t = db + (uint64_t)((uint32_t)t * (uint32_t)b_sub_step);
+                                const uint32_t first = (kb | t) ? 1u : 0u;
+                                if constexpr (two) {
+                                    umma_bf16_2sm(d_tmem, a_t, b_t, idesc, first);
+                                    umma_bf16_2sm(d_tmem, a_t + 2, b_t + 2, idesc, 1u);
+                                    if (k64) {
+                                        umma_bf16_2sm(d_tmem, a_t + 4, b_t + 4, idesc, 1u);
+                                        umma_bf16_2sm(d_tmem, a_t + 6, b_t + 6, idesc, 1u);
+                                    }
+                                } else {
+                                    umma_bf16(d_tmem, a_t, b_t, idesc, first);
+                                    umma_bf16(d_tmem, a_t + 2, b_t + 2, idesc, 1u);
+                                    if (k64) {
+                                        umma_bf16(d_tmem, a_t + 4, b_t + 4, idesc, 1u);
+                                        umma_bf16(d_tmem, a_t + 6, b_t + 6, idesc, 1u);
+                                    }
                                 }
                             }
                         }
@@ -558,10 +577,11 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     }
     uint32_t stage_bytes = (128u * p.bk * 2u + (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * p.bk * 2u) * p.ksub;
     if (p.halo) {
-        if (p.bk != 64 || p.taps != 9 || p.bw_log2 != 3 || p.bh_log2 != 4 || p.ksplit > 1 || p.ydim != 2 || p.halo_d < 1 ||
+        if (p.taps != 9 || p.bw_log2 != 3 || p.bh_log2 != 4 || p.ksplit > 1 || p.ydim != 2 || p.halo_d < 1 ||
             p.halo_pw != 8 + 2 * p.halo_d || p.halo_ph != 16 + 2 * p.halo_d)
             return -23;
-        stage_bytes = (((uint32_t)(p.halo_pw * p.halo_ph) * 128u + 1023u) & ~1023u) + 9u * (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * 128u;
+        stage_bytes = (((uint32_t)(p.halo_pw * p.halo_ph) * (uint32_t)p.bk * 2u + 1023u) & ~1023u) +
+                      9u * (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * (uint32_t)p.bk * 2u;
     }
     const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;

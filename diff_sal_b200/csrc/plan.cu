@@ -392,6 +392,7 @@ int build_program(dsb_handle* h) {
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cin, Cout, act, WP(rk + "conv1.weight"));
                 op.shift = W(h, rk + "conv1.bias"); op.rowbias = h->tp[i]; op.out_f32 = c1;
                 op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
+                op.halo = 1;
                 b.conv(op, "res.conv1");
             }
             b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); }, "gn_stats", (double)B * HW * Cout * 4.0);
@@ -401,6 +402,7 @@ int build_program(dsb_handle* h) {
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
                 op.shift = W(h, rk + "conv2.bias"); op.residual = sc; op.out_bf16 = res;
                 op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
+                op.halo = 1;
                 b.conv(op, "res.conv2");
             }
             const std::string dk = "res_encoder." + std::to_string(i) + ".1.conv.";
@@ -443,6 +445,7 @@ int build_program(dsb_handle* h) {
                 op.dilation = 2; op.scale = WF(pe + "5.scale"); op.shift = WF(pe + "5.shift"); op.act = ACT_RELU;
                 op.residual = (i == 1 || i == 2) ? h->back[i] : nullptr;   // stage 3 has no skip (transformer.py:265-270)
                 op.out_f32 = h->X[i];
+                op.halo = (i != 2);                            // stage 2 (two N tiles + fp32 residual epilogue) measured 8 % slower with it
                 b.conv(op, "upembed.conv2");
             }
             Xi = h->X[i];

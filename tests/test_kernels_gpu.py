@@ -252,7 +252,7 @@ def halo(L):
 
 
 @pytest.mark.parametrize("Fr,H,W,Cin,N,dil", [(8, 56, 96, 192, 96, 2), (4, 56, 96, 64, 96, 1), (3, 112, 192, 128, 96, 1),
-                                              (5, 60, 92, 128, 64, 2)])
+                                              (5, 60, 92, 128, 64, 2), (8, 56, 96, 96, 96, 2), (8, 56, 96, 96, 192, 1), (9, 28, 48, 192, 192, 2)])
 def test_conv3x3_halo_tiles(L, halo, Fr, H, W, Cin, N, dil):
     """Halo-tile path: one TMA box per (8x16 tile, 64-channel block) serves all nine taps as row-shifted descriptors.
     Same results as the per-tap path (bitwise: same products, same K order per output) and as torch."""
