@@ -12,12 +12,13 @@ import torch
 import torch.nn as nn
 
 from . import synth
+from ._module import EngineModule
 from .engine import AudioEngine, DsbError
 
 _SUPPORTED = dict(heads=2, dim=512, mlp_dim=256, dim_head=64, height=7, width=12)
 
 
-class AudioAttnNetB200(nn.Module):
+class AudioAttnNetB200(EngineModule):
     def __init__(self, depth, heads, mlp_dim, dim=512, patch_dim=768, num_patches=16, height=7, width=7, pool="cls",
                  dim_head=64, dropout=0.0, emb_dropout=0.0, max_batch=8):
         super().__init__()
@@ -31,32 +32,17 @@ class AudioAttnNetB200(nn.Module):
         self.depth = int(depth)
         self.num_patches = num_patches
         self.max_batch = int(max_batch)
-        self._engine = None
-        self._sd = None
 
-    def load_state_dict(self, state_dict, strict=True, prefix=""):
-        want = [k for k, _ in synth.audio_attn_state_dict_spec(self.depth)]
-        have = {k[len(prefix):] for k in state_dict if k.startswith(prefix)}
-        used = [k for k in want if k.startswith("transformer.")]
-        missing = [k for k in (want if strict else used) if k not in have]
-        unexpected = [k for k in have if k not in set(want)]
-        if missing or (strict and unexpected):
-            raise DsbError("load_state_dict: missing %s unexpected %s" % (missing[:5], unexpected[:5]))
-        self._sd = {k: state_dict[prefix + k].detach().float().cpu().clone() for k in want if prefix + k in state_dict}
-        if self._engine is not None:
-            self._engine.close()
-        self._engine = AudioEngine(self.max_batch)
-        self._engine.load_state_dict(self._sd)
-        return self
+    # weights: see _module.EngineModule (to_patch_embedding.* / pos_embedding never influence the output, exactly as in the
+    # reference, but are kept for state_dict round trips)
+    def _spec(self):
+        return synth.audio_attn_state_dict_spec(self.depth)
 
-    def state_dict(self, *args, **kwargs):
-        return dict(self._sd) if self._sd is not None else {}
+    def _required(self, key):
+        return key.startswith("transformer.")
 
-    @property
-    def engine(self):
-        if self._engine is None:
-            raise DsbError("AudioAttnNetB200 has no weights: call load_state_dict(reference_state_dict) first")
-        return self._engine
+    def _make_engine(self):
+        return AudioEngine(self.max_batch)
 
     @torch.no_grad()
     def forward(self, audio):

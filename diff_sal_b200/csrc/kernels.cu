@@ -1102,6 +1102,40 @@ int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8
     DSB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------ content fingerprint
+// 64-bit order-independent fingerprint of a device buffer (sum over 16-byte words of a position-keyed splitmix64 of their
+// two halves).  Lets the host recognise that the conditioning tensors of this denoiser call hold the same values as the
+// last call's (the reference's sample_ddim deep-copies the feature list every step, diffusion_trainer.py:452, so the
+// pointers change while the content does not) without re-running the conditioning.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) content_hash_kernel(const uint4* __restrict__ p, size_t n16, unsigned long long seed,
+                                                          unsigned long long* __restrict__ out) {
+    unsigned long long h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = p[i];
+        const unsigned long long a = ((unsigned long long)v.x << 32) | v.y, b = ((unsigned long long)v.z << 32) | v.w;
+        const unsigned long long k = seed + (unsigned long long)i * 0x9E3779B97F4A7C15ull;
+        h += mix64(a + k) + mix64(b ^ (k * 0xD6E8FEB86659FD93ull + 1ull));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);          // integer sum: order-independent, deterministic
+}
+
+int content_hash_launch(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s) {
+    if (bytes % 16 || (reinterpret_cast<uintptr_t>(p) & 15)) return -40;
+    const size_t n16 = bytes / 16;
+    int grid = (int)((n16 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) return 0;
+    content_hash_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(p), n16, seed, out);
+    DSB_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------ layout conversion
 // [B][C][Tv][HW] -> [(b*T+t)][HW][C] through a 32x32 smem transpose (coalesced on both sides)
 __global__ void __launch_bounds__(256) nct_to_frames_kernel(const float* __restrict__ vis, int C, int Tv, int HW, int T,

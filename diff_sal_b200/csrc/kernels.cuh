@@ -74,6 +74,9 @@ int axpy_launch(int nin, const float* const in[4], const float c[4], const float
 // util/utils.py:11-16); either output may be null.  n = pixels per map.
 int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s);
 
+// *out += 64-bit content fingerprint of a 16-byte-aligned device buffer (out must be zeroed by the caller)
+int content_hash_launch(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s);
+
 // vis[B][C][Tv][HW] fp32 -> frames[(b*T + t)][HW][C] for t < Tv  (T = frames per clip in dst)
 int nct_to_frames_launch(const float* vis, int B, int C, int Tv, int HW, int T, float* dst, cudaStream_t s);
 // audio[B][512][T][84] fp32 -> tokens[(b*T+t)*84 + p][512] bf16

@@ -45,7 +45,9 @@ typedef std::function<int(cudaStream_t)> Launch;
 
 struct SamplerGraph {
     cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
 };
+constexpr size_t kMaxGraphs = 8;              // cached (program, batch) graphs per handle, least recently used evicted
 
 }  // namespace
 
@@ -110,7 +112,14 @@ struct dsb_handle {
     float* cur_out = nullptr;
     int64_t last_launches = 0;
     std::map<std::string, SamplerGraph> graphs;
+    uint64_t graph_clock = 0;
     uint64_t cond_epoch = 0;
+    // handle-owned staging so that a captured graph never bakes in a caller pointer
+    float* noise_stage = nullptr;                 // [noise_slabs][max_batch][224*384]
+    size_t noise_slabs = 0;
+    uint8_t* u8_stage = nullptr;                  // [max_batch][224*384] normalised maps of DSB_OP_POSTPROCESS
+    unsigned long long* hash_dev = nullptr;
+    std::vector<float> ts_uploaded;               // model times currently in t_all (skip the upload when unchanged)
 };
 
 namespace {
@@ -262,6 +271,8 @@ int alloc_workspace(dsb_handle* h) {
     if (int r = dev_alloc(h, &h->splitws, (size_t)kSplitWsPerClip * B)) return r;
     h->t_all_cap = 1024;
     if (int r = dev_alloc(h, &h->t_all, (size_t)h->t_all_cap * B)) return r;
+    if (int r = dev_alloc(h, &h->u8_stage, B * kMapElems)) return r;
+    if (int r = dev_alloc(h, &h->hash_dev, 1)) return r;
     h->ws_ready = true;
     return 0;
 }
@@ -674,6 +685,7 @@ extern "C" void dsb_destroy(dsb_handle* h) {
     for (auto& g : h->graphs)
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->noise_stage) cudaFree(h->noise_stage);
     for (int i = 0; i < 2; ++i)
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
     for (int i = 0; i < 8; ++i)
@@ -893,7 +905,7 @@ static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cuda
                 ins[k] = h->sbuf[op.src[k]];
                 cs[k] = op.coef[k];
             }
-            const float* nz = (op.noise_index >= 0 && d->noise) ? d->noise + (size_t)op.noise_index * n : nullptr;
+            const float* nz = (op.noise_index >= 0 && d->noise) ? h->noise_stage + (size_t)op.noise_index * n : nullptr;
             int r = axpy_launch(op.nin, ins, cs, nz, op.noise_coef, h->sbuf[op.dst], n, s);
             if (r) return fail(h, DSB_ERR_CUDA, "axpy launch failed (%d)", r);
             h->last_launches += 1;
@@ -905,6 +917,12 @@ static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cuda
             if (op.dst < 0 || op.dst > 7) return fail(h, DSB_ERR_ARG, "sampler op %d malformed", i);
             if (int r = dyn_threshold_launch(h->sbuf[op.dst], B, kMapElems, op.noise_index, op.coef[0], op.coef[1], s))
                 return fail(h, DSB_ERR_ARG, "dynamic thresholding launch failed (%d)", r);
+            h->last_launches += 1;
+        } else if (op.kind == DSB_OP_POSTPROCESS) {
+            if (op.dst < 0 || op.dst > 7) return fail(h, DSB_ERR_ARG, "sampler op %d malformed", i);
+            if (!d->out_u8) return fail(h, DSB_ERR_ARG, "sampler op %d: DSB_OP_POSTPROCESS without desc.out_u8", i);
+            if (int r = postprocess_launch(h->sbuf[op.dst], B, (int)kMapElems, h->sbuf[op.dst], h->u8_stage, s))
+                return fail(h, DSB_ERR_CUDA, "postprocess launch failed (%d)", r);
             h->last_launches += 1;
         } else {
             return fail(h, DSB_ERR_ARG, "sampler op %d: unknown kind %d", i, op.kind);
@@ -918,24 +936,66 @@ extern "C" int dsb_sample(dsb_handle* h, const dsb_sampler_desc* d, float* x_ino
     if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_sample before dsb_set_condition");
     if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t bytes = (size_t)B * kMapElems * sizeof(float);
-    // model times of all EVAL ops, replicated per clip
+    const size_t n = (size_t)B * kMapElems;
+    const size_t bytes = n * sizeof(float);
+    // model times of all EVAL ops, replicated per clip; noise slabs / post-processing the program refers to
     std::vector<float> ts;
-    for (int i = 0; i < d->n_ops; ++i)
-        if (d->ops[i].kind == DSB_OP_EVAL)
-            for (int b = 0; b < B; ++b) ts.push_back(d->ops[i].t);
-    if ((int)(ts.size() / B) > h->t_all_cap) return fail(h, DSB_ERR_UNSUPPORTED, "more than %d evaluations", h->t_all_cap);
+    int slabs = 0, evals = 0, others = 0;
+    bool post = false;
+    for (int i = 0; i < d->n_ops; ++i) {
+        const dsb_sampler_op& op = d->ops[i];
+        if (op.kind == DSB_OP_EVAL) {
+            ++evals;
+            for (int b = 0; b < B; ++b) ts.push_back(op.t);
+        } else {
+            ++others;
+            if (op.kind == DSB_OP_AXPY && op.noise_index >= slabs) slabs = op.noise_index + 1;
+            if (op.kind == DSB_OP_POSTPROCESS) post = true;
+        }
+    }
+    if (evals > h->t_all_cap) return fail(h, DSB_ERR_UNSUPPORTED, "more than %d evaluations", h->t_all_cap);
+    if (slabs > 0 && !d->noise) slabs = 0;
     h->last_launches = 0;
-    if (!ts.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->t_all, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));     // ts is a stack/heap temporary
+    if (ts != h->ts_uploaded) {
+        // (rare: a new program) synchronous upload, so that the host vector may go away
+        if (!ts.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->t_all, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        h->ts_uploaded = ts;
+    }
+    if (slabs > 0) {
+        // the caller's noise goes through a handle-owned buffer with a fixed address: a captured graph stays valid for
+        // fresh randn tensors (eta > 0 DDIM, ancestral sampling allocate new noise on every call)
+        const size_t slab_cap = (size_t)h->cfg.max_batch * kMapElems;
+        if ((size_t)slabs > h->noise_slabs) {
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            for (auto& g : h->graphs)
+                if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+            h->graphs.clear();
+            if (h->noise_stage) cudaFree(h->noise_stage);
+            h->noise_stage = nullptr;
+            h->noise_slabs = 0;
+            CUDA_TRY(h, cudaMalloc(&h->noise_stage, (size_t)slabs * slab_cap * sizeof(float)));
+            h->noise_slabs = (size_t)slabs;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->noise_stage, d->noise, (size_t)slabs * bytes, cudaMemcpyDeviceToDevice, s));
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->sbuf[0], x_inout, bytes, cudaMemcpyDeviceToDevice, s));
     int rc = DSB_OK;
     if (d->use_graph) {
         std::string key((const char*)d->ops, sizeof(dsb_sampler_op) * (size_t)d->n_ops);
-        key.append((const char*)&d->noise, sizeof(d->noise));
+        const int flags = (slabs > 0 ? 1 : 0) | (post ? 2 : 0);
+        key.append((const char*)&flags, sizeof(flags));
         key.append((const char*)&B, sizeof(B));
         auto it = h->graphs.find(key);
         if (it == h->graphs.end()) {
+            if (h->graphs.size() >= kMaxGraphs) {                     // evict the least recently used graph
+                auto old = h->graphs.begin();
+                for (auto g = h->graphs.begin(); g != h->graphs.end(); ++g)
+                    if (g->second.last_use < old->second.last_use) old = g;
+                CUDA_TRY(h, cudaStreamSynchronize(s));
+                if (old->second.exec) cudaGraphExecDestroy(old->second.exec);
+                h->graphs.erase(old);
+            }
             cudaGraph_t graph = nullptr;
             cudaStream_t cs = nullptr;
             CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -953,16 +1013,40 @@ extern "C" int dsb_sample(dsb_handle* h, const dsb_sampler_desc* d, float* x_ino
             it = h->graphs.emplace(key, sg).first;
         } else {
             // launches counted as if enqueued individually
-            int evals = 0, axpys = 0;
-            for (int i = 0; i < d->n_ops; ++i) (d->ops[i].kind == DSB_OP_EVAL ? evals : axpys)++;
-            h->last_launches = (int64_t)evals * (int64_t)h->prog_launches + axpys;
+            h->last_launches = (int64_t)evals * (int64_t)h->prog_launches + others;
         }
+        it->second.last_use = ++h->graph_clock;
         CUDA_TRY(h, cudaGraphLaunch(it->second.exec, s));
     } else {
         rc = enqueue_sampler(h, d, B, s);
         if (rc) return rc;
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_inout, h->sbuf[0], bytes, cudaMemcpyDeviceToDevice, s));
+    if (post) CUDA_TRY(h, cudaMemcpyAsync(d->out_u8, h->u8_stage, n, cudaMemcpyDeviceToDevice, s));
+    return DSB_OK;
+}
+
+// 64-bit fingerprint of the conditioning tensors (same shapes as dsb_set_condition); synchronises `stream`.
+extern "C" int dsb_condition_hash(dsb_handle* h, const void* const feat[4], const void* audio, int B, uint64_t* out,
+                                  void* stream) {
+    if (!h || !feat || !out) return DSB_ERR_ARG;
+    if (!h->finalized) return fail(h, DSB_ERR_ARG, "dsb_condition_hash before dsb_finalize_weights");
+    if (B < 1 || B > h->cfg.max_batch) return fail(h, DSB_ERR_ARG, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->hash_dev, 0, sizeof(unsigned long long), s));
+    for (int i = 0; i < 3; ++i) {
+        if (!feat[i]) return fail(h, DSB_ERR_ARG, "feat[%d] is null", i);
+        const size_t bytes = (size_t)B * kTv * frame_elems(i) * sizeof(float);
+        if (int r = content_hash_launch(feat[i], bytes, 0x1000ull * (i + 1), h->hash_dev, s))
+            return fail(h, DSB_ERR_ARG, "feat[%d] must be a 16-byte aligned contiguous fp32 tensor (%d)", i, r);
+    }
+    if (audio)
+        if (int r = content_hash_launch(audio, (size_t)B * 512 * kT * 84 * sizeof(float), 0x5000ull, h->hash_dev, s))
+            return fail(h, DSB_ERR_ARG, "audio must be a 16-byte aligned contiguous fp32 tensor (%d)", r);
+    unsigned long long v = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&v, h->hash_dev, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    *out = (uint64_t)v ^ ((uint64_t)B << 56) ^ (audio ? 0x8000000000ull : 0ull);
     return DSB_OK;
 }
 

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-OP_EVAL, OP_AXPY, OP_CLAMP, OP_DYNTHRESH = 0, 1, 2, 3
+OP_EVAL, OP_AXPY, OP_CLAMP, OP_DYNTHRESH, OP_POSTPROCESS = 0, 1, 2, 3, 4
 
 
 class DsbConfig(ctypes.Structure):
@@ -25,7 +25,7 @@ class DsbSamplerOp(ctypes.Structure):
 
 class DsbSamplerDesc(ctypes.Structure):
     _fields_ = [("ops", ctypes.POINTER(DsbSamplerOp)), ("n_ops", ctypes.c_int), ("noise", ctypes.c_void_p),
-                ("use_graph", ctypes.c_int)]
+                ("use_graph", ctypes.c_int), ("out_u8", ctypes.c_void_p)]
 
 
 class DsbError(RuntimeError):
@@ -50,6 +50,8 @@ def _bind(lib):
     lib.dsb_finalize_weights.restype = ci
     lib.dsb_set_condition.argtypes = [vp, ctypes.POINTER(vp), vp, ci, vp]
     lib.dsb_set_condition.restype = ci
+    lib.dsb_condition_hash.argtypes = [vp, ctypes.POINTER(vp), vp, ci, ctypes.POINTER(ctypes.c_uint64), vp]
+    lib.dsb_condition_hash.restype = ci
     lib.dsb_denoise.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.dsb_denoise.restype = ci
     lib.dsb_sampler_update.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(vp), ci, vp, cf, vp, ctypes.c_int64, vp]
@@ -162,7 +164,9 @@ class Engine:
             self._check(self.lib.dsb_finalize_weights(self._h), "dsb_finalize_weights")
 
     # ------------------------------------------------------------------ condition
-    def set_condition(self, feat_list, audio=None):
+    def prepare_condition(self, feat_list, audio=None):
+        """Validates the conditioning tensors and returns them as fp32 contiguous tensors on this engine's device
+        (the tensors themselves when they already are)."""
         feats = [f.to(device=self.device, dtype=torch.float32).contiguous() for f in feat_list[:3]]
         B = feats[0].shape[0]
         exp = [(768, 8, 7, 12), (384, 8, 14, 24), (192, 8, 28, 48)]
@@ -174,11 +178,25 @@ class Engine:
             aud = audio.to(device=self.device, dtype=torch.float32).contiguous()
             if tuple(aud.shape) != (B, 512, 9, 7, 12):
                 raise DsbError("audio features of shape %s, expected [%d,512,9,7,12]" % (tuple(aud.shape), B))
+        return feats, aud
+
+    def set_condition(self, feat_list, audio=None, prepared=False):
+        feats, aud = (feat_list, audio) if prepared else self.prepare_condition(feat_list, audio)
+        B = feats[0].shape[0]
         ptrs = (ctypes.c_void_p * 4)(feats[0].data_ptr(), feats[1].data_ptr(), feats[2].data_ptr(), 0)
         with torch.cuda.device(self.device):
             self._check(self.lib.dsb_set_condition(self._h, ptrs, _lib.ptr(aud), B, _stream()), "dsb_set_condition")
         self._cond = (feats, aud)      # keep alive until the enqueued conversion kernels have run
         self.batch = B
+
+    def condition_hash(self, feats, aud=None):
+        """64-bit content fingerprint of prepared conditioning tensors (dsb_condition_hash; synchronises the stream)."""
+        ptrs = (ctypes.c_void_p * 4)(feats[0].data_ptr(), feats[1].data_ptr(), feats[2].data_ptr(), 0)
+        out = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_condition_hash(self._h, ptrs, _lib.ptr(aud), feats[0].shape[0], ctypes.byref(out),
+                                                    _stream()), "dsb_condition_hash")
+        return int(out.value)
 
     # ------------------------------------------------------------------ one evaluation
     def denoise(self, x, t, out=None):
@@ -209,10 +227,20 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ whole loop
-    def sample(self, ops, x, noise=None, use_graph=True):
+    def sample(self, ops, x, noise=None, use_graph=True, out_u8=None):
         """Runs a sampler program (list of ('eval', t) / ('axpy', dst, [(src, coef), ...], noise_coef,
-        noise_index) / ('clamp', buf, lo, hi) / ('thresh', buf, k, w, max_val)) in place on x [B,1,224,384]."""
+        noise_index) / ('clamp', buf, lo, hi) / ('thresh', buf, k, w, max_val) / ('post', buf)) in place on
+        x [B,1,224,384] (CUDA, fp32, contiguous, on this engine's device).  ``noise``: [n_slabs,B,1,224,384] on the same
+        device.  ``out_u8``: uint8 [B,1,224,384] receiving the min-max-normalised maps of a ('post', buf) op."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.device == self.device and x.dtype == torch.float32
+                and x.is_contiguous() and x.dim() == 4 and tuple(x.shape[1:]) == (1, 224, 384)):
+            raise DsbError("Engine.sample: x must be a contiguous fp32 CUDA tensor [B,1,224,384] on %s, got %s %s on %s"
+                           % (self.device, tuple(x.shape), x.dtype, x.device))
+        B = x.shape[0]
+        if B != self.batch:
+            raise DsbError("Engine.sample: batch %d differs from the conditioned batch %d" % (B, self.batch))
         arr = (DsbSamplerOp * len(ops))()
+        slabs, post = 0, False
         for i, op in enumerate(ops):
             o = arr[i]
             if op[0] == "eval":
@@ -223,6 +251,9 @@ class Engine:
             elif op[0] == "thresh":                     # ('thresh', buf, k, w, max_val)
                 o.kind, o.dst, o.noise_index = OP_DYNTHRESH, int(op[1]), int(op[2])
                 o.coef[0], o.coef[1] = float(op[3]), float(op[4])
+            elif op[0] == "post":                       # ('post', buf)
+                o.kind, o.dst, o.noise_index = OP_POSTPROCESS, int(op[1]), -1
+                post = True
             else:
                 _, dst, terms, ncoef, nidx = op
                 o.kind, o.dst, o.nin = OP_AXPY, int(dst), len(terms)
@@ -231,9 +262,22 @@ class Engine:
                     o.coef[k] = float(c)
                 o.noise_coef = float(ncoef)
                 o.noise_index = int(nidx)
-        desc = DsbSamplerDesc(arr, len(ops), _lib.ptr(noise).value, int(bool(use_graph)))
+                slabs = max(slabs, int(nidx) + 1)
+        if slabs:
+            if noise is None:
+                raise DsbError("Engine.sample: the program uses %d noise slabs but no noise tensor was given" % slabs)
+            if not (noise.is_cuda and noise.device == self.device and noise.dtype == torch.float32 and noise.is_contiguous()
+                    and noise.numel() >= slabs * x.numel()):
+                raise DsbError("Engine.sample: noise must be a contiguous fp32 CUDA tensor [>=%d,%d,1,224,384] on %s, got "
+                               "%s %s on %s" % (slabs, B, self.device, tuple(noise.shape), noise.dtype, noise.device))
+        if post:
+            if out_u8 is None or not (out_u8.is_cuda and out_u8.device == self.device and out_u8.dtype == torch.uint8
+                                      and out_u8.is_contiguous() and out_u8.numel() == x.numel()):
+                raise DsbError("Engine.sample: a ('post', buf) op needs out_u8 = contiguous uint8 CUDA tensor [B,1,224,384]")
+        desc = DsbSamplerDesc(arr, len(ops), _lib.ptr(noise).value if slabs else None, int(bool(use_graph)),
+                              _lib.ptr(out_u8).value if post else None)
         with torch.cuda.device(self.device):
-            self._check(self.lib.dsb_sample(self._h, ctypes.byref(desc), _lib.ptr(x), x.shape[0], _stream()), "dsb_sample")
+            self._check(self.lib.dsb_sample(self._h, ctypes.byref(desc), _lib.ptr(x), B, _stream()), "dsb_sample")
         return x
 
     def profile_denoise(self, x, t):

@@ -1,10 +1,13 @@
 """Clip sharding across the GPUs of one box.
 
 Denoising is independent per clip (eval-mode norms use running statistics, diffusion_trainer.py:862), so the loop
-runs with no collective: rank r owns a contiguous block of ceil(N / world) clips -- the same partition
-DistributedSampler gives the reference's test loaders (datasets/prepare_data.py:87-103) -- and the predicted maps are
-gathered once after the loop (344 KB per clip).  torch.distributed is the plumbing (NCCL over NVLink on the GPUs,
-gloo in the CPU tests).
+runs with no collective: rank r owns a contiguous block of ceil(N / world) clips and the predicted maps are gathered
+once after the loop (344 KB per clip as fp32, 86 KB as uint8).  The reference shards its test loaders with
+``DistributedSampler`` (datasets/prepare_data.py:87-103), which deals clips out round-robin (rank r gets r, r + world,
+...) after padding to a multiple of world; contiguous blocks are used here instead because they make the gathered
+tensor come back in clip order with one equal-size all_gather -- which clip a rank processes does not change its map
+(tests/test_sharding_gloo.py, the batch-invariance tests).  torch.distributed is the plumbing (NCCL over NVLink on the
+GPUs, gloo in the CPU tests).
 """
 import torch
 import torch.distributed as dist
@@ -17,16 +20,39 @@ def shard_range(n_clips, rank, world):
     return start, min(n_clips, start + per)
 
 
+def micro_batches(start, stop, size):
+    """[(lo, hi)] covering [start, stop) in micro-batches of at most ``size`` clips (BASELINE config 4: 32 per GPU)."""
+    return [(lo, min(stop, lo + size)) for lo in range(start, stop, size)]
+
+
+class MapGatherer:
+    """Equal-size all_gather of the per-rank map blocks into preallocated buffers (nothing is allocated per call).
+
+    ``local_maps`` is this rank's [n_local, 1, H, W] block (n_local may be smaller than ceil(n/world) on the last ranks:
+    the padded tail keeps whatever it held and is trimmed from the result)."""
+
+    def __init__(self, n_clips, map_shape, dtype, device, group=None):
+        self.group = group
+        self.n_clips = int(n_clips)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.per = (self.n_clips + self.world - 1) // self.world
+        self.pad = torch.zeros((self.per,) + tuple(map_shape), dtype=dtype, device=device)
+        self.out = torch.empty((self.world * self.per,) + tuple(map_shape), dtype=dtype, device=device)
+
+    def __call__(self, local_maps):
+        if self.world == 1:
+            return local_maps[: self.n_clips]
+        n = local_maps.shape[0]
+        src = local_maps if (n == self.per and local_maps.is_contiguous()) else self.pad
+        if src is self.pad:
+            self.pad[:n].copy_(local_maps)
+        dist.all_gather_into_tensor(self.out, src, group=self.group)
+        return self.out[: self.n_clips]
+
+
 def gather_maps(local_maps, n_clips, group=None):
-    """All ranks receive the [n_clips, 1, H, W] maps in clip order.  ``local_maps`` is this rank's
-    [n_local, 1, H, W] block (n_local may be smaller than ceil(n/world) on the last ranks: it is zero-padded
-    for the equal-size all_gather and trimmed afterwards)."""
+    """All ranks receive the [n_clips, 1, H, W] maps in clip order (one-shot convenience around MapGatherer)."""
     if not dist.is_available() or not dist.is_initialized():
         return local_maps[:n_clips]
-    world = dist.get_world_size(group)
-    per = (n_clips + world - 1) // world
-    pad = torch.zeros((per,) + tuple(local_maps.shape[1:]), dtype=local_maps.dtype, device=local_maps.device)
-    pad[: local_maps.shape[0]] = local_maps
-    out = torch.empty((world * per,) + tuple(local_maps.shape[1:]), dtype=local_maps.dtype, device=local_maps.device)
-    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
-    return out[:n_clips]
+    g = MapGatherer(n_clips, local_maps.shape[1:], local_maps.dtype, local_maps.device, group)
+    return g(local_maps)

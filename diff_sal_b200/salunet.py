@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import synth
+from ._module import EngineModule
 from .engine import DsbError, Engine
 
 _SUPPORTED = dict(
@@ -30,7 +31,7 @@ def _norm(v):
     return v
 
 
-class SalUNetB200(nn.Module):
+class SalUNetB200(EngineModule):
     def __init__(self, max_batch=8, audio_visual=True, **kwargs):
         super().__init__()
         # the kernels are specialised for the one decoder configuration both reference configs use
@@ -41,42 +42,48 @@ class SalUNetB200(nn.Module):
         self.img_size = (224, 384)
         self.max_batch = int(max_batch)
         self.audio_visual = bool(audio_visual)
-        self._engine = None
-        self._sd = None
-        self._cond_key = None
+        self._cond_ident = None
+        self._cond_hash = None
+        self._cond_refs = None
 
-    # ------------------------------------------------------------------ weights
-    def load_state_dict(self, state_dict, strict=True, prefix=""):
-        want = [k for k, _ in synth.state_dict_spec()]
-        have = {k[len(prefix):] for k in state_dict if k.startswith(prefix)}
-        missing = [k for k in want if k not in have and not k.endswith("num_batches_tracked")]
-        unexpected = [k for k in have if k not in set(want)]
-        if missing or (strict and unexpected):
-            raise DsbError("load_state_dict: missing %s unexpected %s" % (missing[:5], unexpected[:5]))
-        self._sd = {k: state_dict[prefix + k].detach().float().cpu().clone() for k in want if prefix + k in state_dict}
-        if self._engine is not None:
-            self._engine.close()
-        self._engine = Engine(self.max_batch, self.audio_visual)
-        self._engine.load_state_dict(self._sd)
-        self._cond_key = None
-        return self
+    # ------------------------------------------------------------------ weights (see _module.EngineModule)
+    def _spec(self):
+        return synth.state_dict_spec()
 
-    def state_dict(self, *args, **kwargs):
-        return dict(self._sd) if self._sd is not None else {}
+    def _make_engine(self):
+        return Engine(self.max_batch, self.audio_visual)
 
-    @property
-    def engine(self):
-        if self._engine is None:
-            raise DsbError("SalUNetB200 has no weights: call load_state_dict(reference_state_dict) first")
-        return self._engine
+    def _weights_changed(self):
+        self._cond_ident = self._cond_hash = self._cond_refs = None
 
     # ------------------------------------------------------------------ condition cache
+    @staticmethod
+    def _identity(feat_list, audio):
+        """(pointer, version, shape, dtype) of the caller's tensors, or None when a tensor carries no version counter
+        (inference-mode tensors): then only the content fingerprint can tell whether the conditioning changed."""
+        try:
+            key = tuple((f.data_ptr(), f._version, tuple(f.shape), f.dtype, f.device) for f in feat_list[:3])
+            key += ((audio.data_ptr(), audio._version, tuple(audio.shape), audio.dtype, audio.device)
+                    if audio is not None else None,)
+            return key
+        except RuntimeError:
+            return None
+
     def _condition(self, feat_list, audio):
-        key = tuple((f.data_ptr(), f._version, tuple(f.shape)) for f in feat_list[:3])
-        key += ((audio.data_ptr(), audio._version) if audio is not None else None,)
-        if key != self._cond_key:
-            self.engine.set_condition(feat_list, audio)
-            self._cond_key = key
+        """Runs dsb_set_condition only when the conditioning VALUES changed.  Fast path: the very same, unmodified tensor
+        objects as last time (strong references are kept, so an equal address cannot be a recycled allocation).
+        Otherwise -- e.g. the reference's ``copy.deepcopy(tmp_img)`` per step (diffusion_trainer.py:452), fp16 / CPU /
+        non-contiguous inputs that are converted to fresh tensors -- a 64-bit content fingerprint decides."""
+        ident = self._identity(feat_list, audio)
+        if ident is not None and ident == self._cond_ident:
+            return
+        feats, aud = self.engine.prepare_condition(feat_list, audio)
+        h = self.engine.condition_hash(feats, aud)
+        if h != self._cond_hash:
+            self.engine.set_condition(feats, aud, prepared=True)
+            self._cond_hash = h
+        self._cond_ident = ident
+        self._cond_refs = (list(feat_list[:3]), audio)
 
     # ------------------------------------------------------------------ reference signature
     @torch.no_grad()
@@ -90,6 +97,8 @@ class SalUNetB200(nn.Module):
         audio = (model_kwargs or {}).get("audio_feat_list")
         self._condition(feat_list, audio)
         out = x.to(device=self.engine.device, dtype=torch.float32).clone().contiguous()
+        if noise is not None:
+            noise = noise.to(device=self.engine.device, dtype=torch.float32).contiguous()
         return self.engine.sample(ops, out, noise=noise, use_graph=use_graph)
 
 

@@ -11,42 +11,30 @@ import torch
 import torch.nn as nn
 
 from . import synth
+from ._module import EngineModule
 from .engine import DsbError, VggishEngine
 
 
-class VGGishB200(nn.Module):
+class VGGishB200(EngineModule):
     def __init__(self, pretrained=False, max_frames=72):
         super().__init__()
         if pretrained:
             raise DsbError("VGGishB200(pretrained=True): load the checkpoint yourself and call load_state_dict "
                            "(the reference reads data/pretrained_models/vggish.pth, models/vggish.py:110-119)")
         self.max_frames = int(max_frames)
-        self._engine = None
-        self._sd = None
 
-    def load_state_dict(self, state_dict, strict=True, prefix=""):
-        want = [k for k, _ in synth.vggish_state_dict_spec()]
-        have = {k[len(prefix):] for k in state_dict if k.startswith(prefix)}
-        missing = [k for k in want if k.startswith("features.") and k not in have]
-        unexpected = [k for k in have if k not in set(want)]
-        if missing or (strict and unexpected):
-            raise DsbError("load_state_dict: missing %s unexpected %s" % (missing[:5], unexpected[:5]))
-        self._sd = {k: state_dict[prefix + k].detach().float().cpu().clone() for k in want
-                    if k.startswith("features.") and prefix + k in state_dict}
-        if self._engine is not None:
-            self._engine.close()
-        self._engine = VggishEngine(self.max_frames)
-        self._engine.load_state_dict(self._sd)
-        return self
+    # weights: see _module.EngineModule (``embeddings.*`` is accepted, kept for state_dict round trips, never uploaded)
+    def _spec(self):
+        return synth.vggish_state_dict_spec()
 
-    def state_dict(self, *args, **kwargs):
-        return dict(self._sd) if self._sd is not None else {}
+    def _required(self, key):
+        return key.startswith("features.")
 
-    @property
-    def engine(self):
-        if self._engine is None:
-            raise DsbError("VGGishB200 has no weights: call load_state_dict(reference_state_dict) first")
-        return self._engine
+    def _optional(self, key):
+        return key.startswith("embeddings.")            # the 113 M-parameter AudioSet head forward_feat never runs
+
+    def _make_engine(self):
+        return VggishEngine(self.max_frames)
 
     @torch.no_grad()
     def forward_feat(self, x):

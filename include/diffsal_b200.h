@@ -72,6 +72,12 @@ int dsb_finalize_weights(dsb_handle* h);
  * the reference); audio: device fp32 [B,512,9,7,12] or NULL for the visual-only configuration. */
 int dsb_set_condition(dsb_handle* h, const void* const feat[4], const void* audio_or_null, int B, void* stream);
 
+/* 64-bit fingerprint of the values dsb_set_condition would read (same arguments).  The reference's sample_ddim hands
+ * the decoder a fresh deep copy of the feature list on every step (diffusion_trainer.py:452): the host side compares
+ * fingerprints instead of pointers to skip the (loop-invariant) conditioning.  Synchronises `stream`. */
+int dsb_condition_hash(dsb_handle* h, const void* const feat[4], const void* audio_or_null, int B, uint64_t* out,
+                       void* stream);
+
 /* x: device fp32 [B,1,224,384]; t: device fp32 [B] (model time, may be fractional); out: device fp32 [B,1,224,384] */
 int dsb_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream);
 
@@ -90,6 +96,9 @@ int dsb_sampler_update(dsb_handle* h, const float* coef, const float* const* in,
 #define DSB_OP_DYNTHRESH 3 /* DPM_Solver.dynamic_thresholding_fn (sampler.py:417-426) on buf[dst], per clip:
                             * s = max(lerp(|x|_(k), |x|_(k+1), coef[0]), coef[1]) with k = noise_index the floor of
                             * torch.quantile's fp32 rank p * (n - 1); buf = clamp(buf, -s, s) / s                     */
+#define DSB_OP_POSTPROCESS 4 /* output side of the loop fused into the program: buf[dst] =
+                            * clamp(buf[dst], 0, 1) = inverse_data_transform (datasets/__init__.py:26-35) and
+                            * desc.out_u8 = normalize_data(buf[dst]) (util/utils.py:11-16, per-map min-max -> uint8)      */
 typedef struct dsb_sampler_op {
     int kind;
     float t;
@@ -104,8 +113,10 @@ typedef struct dsb_sampler_op {
 typedef struct dsb_sampler_desc {
     const dsb_sampler_op* ops;
     int n_ops;
-    const float* noise; /* device fp32 [n_slabs][B,1,224,384] or NULL */
-    int use_graph;      /* 1: capture the program into a CUDA graph (cached per program) and replay it */
+    const float* noise; /* device fp32 [n_slabs][B,1,224,384] or NULL (copied to handle-owned staging: a cached graph
+                         * stays valid when the caller passes a fresh randn tensor on every call)                       */
+    int use_graph;      /* 1: capture the program into a CUDA graph (cached per program, LRU of 8) and replay it */
+    uint8_t* out_u8;    /* device uint8 [B][224*384], written by DSB_OP_POSTPROCESS; NULL if the program has none     */
 } dsb_sampler_desc;
 
 int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int B, void* stream);

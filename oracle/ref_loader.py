@@ -1,9 +1,11 @@
-"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference from /root/reference.
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference.
 
-Used only in the build container (where /root/reference exists) to (a) validate the
-restatement in oracle/ against the real reference and (b) generate the golden
-fixtures under tests/golden/.  Nothing in the product path imports this module and
-nothing on the GPU box can (the reference tree does not travel).
+In the build container the reference is imported from /root/reference to (a) validate the
+restatement in oracle/ against the real reference and (b) generate the golden fixtures under
+tests/golden/.  On the GPU box /root/reference does not exist; there the same unmodified
+modules are imported from oracle/_ref/, the sourceless-bytecode build of the reference that
+oracle/build_ref.py produces (git-ignored, travels with gpurun).  Nothing in the product path
+imports this module: only tests/, bench.py's reference arm / cpu_baseline leg do.
 
 The reference needs mmcv / timm / skimage / soundfile / resampy which are absent in
 this image; tiny stand-ins are injected in sys.modules (no arithmetic lives in them,
@@ -13,11 +15,26 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DIFFSAL_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("DIFFSAL_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "models", "saliency_decoder")):
+            return cand
+    return os.environ.get("DIFFSAL_REFERENCE", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "models", "saliency_decoder"))
+
+
+def is_source_tree():
+    """True when the reference is imported from its sources, False for the bytecode build in oracle/_ref/."""
+    return available() and os.path.exists(os.path.join(REF_ROOT, "models", "saliency_decoder", "sal_unet.py"))
 
 
 def _install_stubs():
@@ -35,10 +52,16 @@ def _install_stubs():
                 self._mods = {}
 
             def register_module(self, name=None, force=False, module=None):
-                def deco(cls):
-                    self._mods[cls.__name__] = cls
+                # mmcv semantics: usable as ``@register_module()`` or ``register_module(name=..., module=cls)``
+                def _reg(cls):
+                    key = name or cls.__name__
+                    if key in self._mods and not force and self._mods[key] is not cls:
+                        raise KeyError("%s is already registered in %s" % (key, self.name))
+                    self._mods[key] = cls
                     return cls
-                return deco
+                if module is not None:
+                    return _reg(module)
+                return _reg
 
             def build(self, cfg):
                 cfg = dict(cfg)

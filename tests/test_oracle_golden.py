@@ -61,6 +61,25 @@ def test_config1_visual_only_dpm():
     assert (y - gold("cfg1_dpm_refinit_vis_xstart_o2_s9")).abs().max().item() < TOL
 
 
+def test_config2_bench_configuration():
+    """BASELINE config 2 (what bench.py times): audio-visual, DPM-solver multistep-2, 10 NFE; clips 6-7 of the batch of 8
+    as one oracle batch of 2 (the oracle is batch-capable; the reference's x_start conversion is not, see
+    tests/golden/make_golden_cfg2.py) against the reference fixture."""
+    sd = synth.make_state_dict("wide")
+    x, feats, aud = synth.make_inputs(8, audio=True)
+    x, feats, aud = x[6:], [f[6:] for f in feats], aud[6:]
+    y = samplers.sample_dpm(lambda x_, t_: salunet.forward(sd, x_, t_, feats, aud), x, steps=9, order=2,
+                            algorithm_type="dpmsolver", model_type="x_start")
+    assert (y - gold("cfg2_dpm_wide_av_b8_s9")[6:]).abs().max().item() < 1e-5
+
+
+def test_ddim_10_steps_batch2():
+    x, feats, aud = synth.make_inputs(2, audio=True)
+    sd = synth.make_state_dict("wide")
+    y = samplers.sample_ddim(lambda x_, t_: salunet.forward(sd, x_, t_, feats, aud), x, 10, eta=0.0, training_target="x0")
+    assert (y - gold("ddim_wide_av_b2_s10")).abs().max().item() < 1e-5
+
+
 def test_visual_only_is_noise_invariant():
     """in visual-only eval mode the output does not depend on x_t or t (only frames
     0..4 reach ReduceTemp and the noise slice is frame 8)."""
