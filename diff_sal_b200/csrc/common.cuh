@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
 #error "libdiffsal_b200 is written for sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a)"
@@ -203,6 +204,48 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of a denoiser evaluation / sampler program calls pdl_wait() before
+// its first access to global memory that another kernel of the program writes or reads, and pdl_trigger() once its CTAs
+// hold their on-chip resources.  Launched through launch_pdl(), kernel k+1 of a stream is scheduled while kernel k drains
+// (its prologue -- barrier init, TMEM allocation, tensor-map prefetch, index math -- runs under k's tail) and blocks in
+// pdl_wait() until k has completed and flushed.  Both instructions are no-ops for a launch without the attribute.
+// Ordering argument: every kernel waits before touching memory, so completion is transitive along a stream; kernels
+// joined through events keep full dependencies (the first launch after a cross-stream wait is made without the attribute).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// host side: process-wide mode (dsb_set_pdl / DSB_PDL: 0 off, 1 light kernels only, 2 every kernel) and a per-launch veto
+// set by the program runner.  `heavy` marks the tcgen05 kernels: a CTA of theirs that waits in pdl_wait() pins a whole SM
+// (~220 KB shared memory, 448-480 threads, all 512 TMEM columns) and starves kernels of the OTHER streams of an evaluation
+// that could have used it, so they are only launched early in mode 2.
+int& pdl_mode();
+bool& pdl_allow_next();
+inline bool pdl_use(bool heavy) { return pdl_allow_next() && pdl_mode() >= (heavy ? 2 : 1); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl_ex(bool heavy, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_use(heavy) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    return launch_pdl_ex(false, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -238,6 +238,8 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitReduce r) {
+    pdl_trigger();
+    pdl_wait();
     const int nv = r.N >> 2;
     const long total = (long)r.rows * nv;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -279,8 +281,8 @@ int conv_run(const ConvLaunch& l, int num_sms, cudaStream_t stream) {
     if (l.split.S > 1) {
         long g = ((long)l.split.rows * (l.split.N >> 2) + 255) / 256;
         if (g > 148 * 8) g = 148 * 8;
-        splitk_reduce_kernel<<<(int)g, 256, 0, stream>>>(l.split);
-        return (int)cudaGetLastError();
+        pdl_allow_next() = true;                       // follows its own GEMM on the same stream
+        return (int)launch_pdl(splitk_reduce_kernel, dim3((int)g), dim3(256), 0, stream, l.split);
     }
     return 0;
 }

@@ -77,6 +77,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     if constexpr (two) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // PDL: this CTA now holds its shared memory and TMEM, so the next kernel of the stream may be scheduled behind it;
+    // nothing above touched global memory written by the previous kernel, everything below may
+    pdl_trigger();
+    pdl_wait();
 
     const int n_tiles = p.N / p.bn;
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
@@ -595,8 +599,7 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
         const int total = m_tiles * (p.N / p.bn) * (p.ksplit > 1 ? p.ksplit : 1);
         int grid = total < num_sms ? total : num_sms;
         if (grid < 1) return -16;
-        gemm_tc_kernel<false><<<grid, kGemmThreads, smem, stream>>>(p, tmA, tmB, stages);
-        return (int)cudaGetLastError();
+        return (int)launch_pdl_ex(true, gemm_tc_kernel<false>, dim3(grid), dim3(kGemmThreads), smem, stream, p, tmA, tmB, stages);
     }
     const int pairs = ((m_tiles + 1) / 2) * (p.N / p.bn);
     int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
@@ -607,13 +610,15 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_use(true) ? 2 : 1;
     return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, p, tmA, tmB, stages);
 }
 

@@ -2,9 +2,23 @@
 // warp-shuffle reductions for the LayerNorm / softmax statistics.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace dsb {
 
 #define DSB_LAUNCH_CHECK() return (int)cudaGetLastError()
+// launch with the programmatic-dependent-launch attribute (see common.cuh); errors surface through cudaGetLastError
+#define DSB_PDL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (void)launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
+int& pdl_mode() {
+    static int mode = [] { const char* e = getenv("DSB_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+    return mode;
+}
+bool& pdl_allow_next() {
+    static thread_local bool allow = true;
+    return allow;
+}
 
 __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
     v = warp_sum(v);
@@ -36,6 +50,8 @@ __device__ __forceinline__ float4 temb_slice(const float* __restrict__ wt, int l
 
 __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, TembWeights w, float* tp0, float* tp1,
                                                   float* tp2) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float emb[96];
     __shared__ float h1[384];
     __shared__ float h2[384];
@@ -86,13 +102,15 @@ __global__ void __launch_bounds__(384) temb_kernel(const float* __restrict__ t, 
 }
 
 int temb_launch(const float* t, int B, const TembWeights& w, float* const tp[3], cudaStream_t s) {
-    temb_kernel<<<dim3(B, 4), 384, 0, s>>>(t, w, tp[0], tp[1], tp[2]);
+    DSB_PDL_LAUNCH(temb_kernel, dim3(B, 4), 384, 0, s, t, w, tp[0], tp[1], tp[2]);
     DSB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------ stem 5x5 stride 4
 __global__ void __launch_bounds__(96) stem_kernel(const float* __restrict__ x, const float* __restrict__ w5,
                                                  const float* __restrict__ b5, float* __restrict__ h0) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float patch[5][132];
     const int xo0 = blockIdx.x * 32, y = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
     const float* xb = x + (size_t)b * 224 * 384;
@@ -118,7 +136,7 @@ __global__ void __launch_bounds__(96) stem_kernel(const float* __restrict__ x, c
 }
 
 int stem_launch(const float* x, int B, const float* w5, const float* b5, float* h0, cudaStream_t s) {
-    stem_kernel<<<dim3(3, 56, B), 96, 0, s>>>(x, w5, b5, h0);
+    DSB_PDL_LAUNCH(stem_kernel, dim3(3, 56, B), 96, 0, s, x, w5, b5, h0);
     DSB_LAUNCH_CHECK();
 }
 
@@ -126,6 +144,8 @@ int stem_launch(const float* x, int B, const float* w5, const float* b5, float* 
 // Deterministic two-level reduction (no atomics): block (split, frame) writes the (sum, sum of squares) of its
 // pixel range for each of the 32 groups to part[frame][split][group]; gn_apply adds the splits in a fixed order.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, double* part) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float ssum[960];
     __shared__ float ssq[960];
     const int f = blockIdx.y, tid = threadIdx.x;
@@ -195,7 +215,7 @@ static int gn_splits(int HW) { int S = HW / 8; return S > 63 ? 63 : (S < 1 ? 1 :
 
 int gn_stats_launch(const float* x, int F, int HW, int C, double* part, cudaStream_t s) {
     if (C % 32 || C > 768 || C < 96) return -30;
-    gn_stats_kernel<<<dim3(gn_splits(HW), F), 256, 0, s>>>(x, HW, C, part);
+    DSB_PDL_LAUNCH(gn_stats_kernel, dim3(gn_splits(HW), F), 256, 0, s, x, HW, C, part);
     DSB_LAUNCH_CHECK();
 }
 
@@ -203,6 +223,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                       const double* __restrict__ part_sums, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, bf16* __restrict__ out_act,
                                                       bf16* __restrict__ out_raw) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float mean[32];
     __shared__ float rstd[32];
     const int f = blockIdx.y, tid = threadIdx.x;
@@ -242,7 +264,7 @@ int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, con
     long total = (long)HW * (C / 4);
     int gx = (int)((total + 767) / 768) * 3;             // multiple of 3: 768 threads cover whole C/4 periods
     if (gx > 297) gx = 297;
-    gn_apply_kernel<<<dim3(gx, F), 256, 0, s>>>(x, HW, C, gn_splits(HW), acc, gamma, beta, out_act, out_raw);
+    DSB_PDL_LAUNCH(gn_apply_kernel, dim3(gx, F), 256, 0, s, x, HW, C, gn_splits(HW), acc, gamma, beta, out_act, out_raw);
     DSB_LAUNCH_CHECK();
 }
 
@@ -303,6 +325,8 @@ struct Up2Walk {
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int H, int W, int C,
                                                         bf16* __restrict__ out, int XT) {
+    pdl_trigger();
+    pdl_wait();
     const int cv_n = C >> 2;
     const int lanes = blockDim.x;                        // vector lanes per row group
     const int cv = blockIdx.z * lanes + threadIdx.x;
@@ -327,7 +351,7 @@ int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cud
     const int XT = 24;                                   // 2W is 24, 48, 96 or 192: all multiples of 24
     if ((2 * W) % XT || (2 * H) % rows) return -35;
     dim3 grid(F * ((2 * W) / XT), (2 * H) / rows, cv_n / lanes);
-    upsample2x_kernel<<<grid, dim3(lanes, rows), 0, s>>>(x, H, W, C, out, XT);
+    DSB_PDL_LAUNCH(upsample2x_kernel, grid, dim3(lanes, rows), 0, s, x, H, W, C, out, XT);
     DSB_LAUNCH_CHECK();
 }
 
@@ -353,6 +377,8 @@ template <int C, bool APPLY>
 __global__ void __launch_bounds__(256) ln_vec_kernel(const float* __restrict__ x, long tokens, float2* __restrict__ stats,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     bf16* __restrict__ out, int hw, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
     using G = LnGeom<C>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / G::LPT, l = lane % G::LPT;
@@ -396,7 +422,7 @@ static int ln_vec_launch(const float* x, long tokens, int C, float2* stats, cons
 #define DSB_LN_CASE(CC)                                                                                              \
     case CC: {                                                                                                       \
         const int g = (int)((tokens + 8 * LnGeom<CC>::TPW - 1) / (8 * LnGeom<CC>::TPW));                              \
-        ln_vec_kernel<CC, APPLY><<<g, 256, 0, s>>>(x, tokens, stats, gamma, beta, out, hw, T, tmax);                  \
+        DSB_PDL_LAUNCH((ln_vec_kernel<CC, APPLY>), g, 256, 0, s, x, tokens, stats, gamma, beta, out, hw, T, tmax);     \
         break;                                                                                                       \
     }
     switch (C) {
@@ -429,6 +455,8 @@ __global__ void __launch_bounds__(256) q_dwln_kernel(const float* __restrict__ x
                                                     const float* __restrict__ nb, const float* __restrict__ wq,
                                                     const float* __restrict__ qg, const float* __restrict__ qb,
                                                     bf16* __restrict__ out, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
     using G = LnGeom<C>;
     static_assert(G::LPT == 32, "one token per warp");
     constexpr int NV = G::NVEC, CV = C / 4;
@@ -501,6 +529,8 @@ __global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restri
                                                           const float* __restrict__ nb, const float* __restrict__ wq,
                                                           const float* __restrict__ qg, const float* __restrict__ qb,
                                                           bf16* __restrict__ out, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
     using G = LnGeom<C>;
     static_assert(G::NVEC == 3 && XT == 8 * G::TPW, "tile geometry");
     constexpr int TW = XT + 2, CV = C / 4, NT = 3 * TW, PER = 8 * G::TPW, NPASS = (NT + PER - 1) / PER;
@@ -596,16 +626,16 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
     const long tokens = (long)F * H * W;
     const int g = (int)((tokens + 7) / 8);
     if (C == 96 && W % 32 == 0) {
-        q_dwln_tiled_kernel<96, 32><<<F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        DSB_PDL_LAUNCH((q_dwln_tiled_kernel<96, 32>), F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s, x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
         DSB_LAUNCH_CHECK();
     }
     if (C == 192 && W % 16 == 0) {
-        q_dwln_tiled_kernel<192, 16><<<F * H * (W / 16), 256, 3 * 18 * 192 * sizeof(float), s>>>(x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
+        DSB_PDL_LAUNCH((q_dwln_tiled_kernel<192, 16>), F * H * (W / 16), 256, 3 * 18 * 192 * sizeof(float), s, x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
         DSB_LAUNCH_CHECK();
     }
     switch (C) {
-        case 384: q_dwln_kernel<384><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        case 768: q_dwln_kernel<768><<<g, 256, 0, s>>>(x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 384: DSB_PDL_LAUNCH((q_dwln_kernel<384>), g, 256, 0, s, x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
+        case 768: DSB_PDL_LAUNCH((q_dwln_kernel<768>), g, 256, 0, s, x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
         default: return -31;     // C = 96 / 192 need W % 32 / W % 16 == 0 (tiled kernel above)
     }
     DSB_LAUNCH_CHECK();
@@ -641,6 +671,8 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
                                int s_, const float* __restrict__ ng, const float* __restrict__ nb,
                                const float* __restrict__ wv, const float* __restrict__ vg,
                                const float* __restrict__ vb, bf16* __restrict__ out, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];          // part[G][C]; pre[C] aliases part[0]
     __shared__ float red[32];
     const int tokv = blockIdx.x;           // f*18 + Y*6 + X
@@ -685,7 +717,7 @@ int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int
     const int nthr = pool_threads(C);
     if (C % 4 || C / 4 > nthr) return -34;
     const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
-    pool_ln_kernel<<<F * 18, nthr, smem, s>>>(x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax);
+    DSB_PDL_LAUNCH(pool_ln_kernel, F * 18, nthr, smem, s, x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax);
     DSB_LAUNCH_CHECK();
 }
 
@@ -693,6 +725,8 @@ int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int
 // one block per (y, b, 32-channel chunk): m[x][c] = mean_t a*x ; softmax over x ; g written as [b][c][y][x]
 __global__ void __launch_bounds__(256) av_gate_kernel(const float* __restrict__ x, const float* __restrict__ a_low,
                                                      int T, int H, int W, int C, int rshift, float* __restrict__ g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float m[96 * 33];           // [W][33]
     const int y = blockIdx.x, b = blockIdx.y, c0 = blockIdx.z * 32;
     const float invT = 1.0f / (float)T;
@@ -749,7 +783,7 @@ int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int 
     int rshift = 0;
     while ((1 << rshift) < r) ++rshift;
     if ((1 << rshift) != r || H != 7 * r || W != 12 * r) return -33;
-    av_gate_kernel<<<dim3(H, B, C / 32), 256, 0, s>>>(x, a_low, T, H, W, C, rshift, g);
+    DSB_PDL_LAUNCH(av_gate_kernel, dim3(H, B, C / 32), 256, 0, s, x, a_low, T, H, W, C, rshift, g);
     DSB_LAUNCH_CHECK();
 }
 
@@ -760,6 +794,8 @@ template <int C, int H, int W, int S_, int T_>
 __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int tmax,
                                 const float* __restrict__ wk, const float* __restrict__ kg,
                                 const float* __restrict__ kb, bf16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     __shared__ float red[32];
     constexpr int HW = H * W, R = H / 7, CV = C / 4, THW = T_ * HW, NPX = S_ * S_;
@@ -816,10 +852,10 @@ int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int
     if (T != 9 || C / 4 > nthr) return -34;
     const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
     const int grid = B * T * 18;
-    if (C == 768 && H == 7 && W == 12 && s_ == 2) kpool_av_kernel<768, 7, 12, 2, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 384 && H == 14 && W == 24 && s_ == 4) kpool_av_kernel<384, 14, 24, 4, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 192 && H == 28 && W == 48 && s_ == 8) kpool_av_kernel<192, 28, 48, 8, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 96 && H == 56 && W == 96 && s_ == 16) kpool_av_kernel<96, 56, 96, 16, 9><<<grid, nthr, smem, s>>>(g, a_low, tmax, wk, kg, kb, out);
+    if (C == 768 && H == 7 && W == 12 && s_ == 2) DSB_PDL_LAUNCH((kpool_av_kernel<768, 7, 12, 2, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 384 && H == 14 && W == 24 && s_ == 4) DSB_PDL_LAUNCH((kpool_av_kernel<384, 14, 24, 4, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 192 && H == 28 && W == 48 && s_ == 8) DSB_PDL_LAUNCH((kpool_av_kernel<192, 28, 48, 8, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
+    else if (C == 96 && H == 56 && W == 96 && s_ == 16) DSB_PDL_LAUNCH((kpool_av_kernel<96, 56, 96, 16, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
     else return -34;
     DSB_LAUNCH_CHECK();
 }
@@ -828,6 +864,8 @@ int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int
 __global__ void __launch_bounds__(256) attn_operands_kernel(const float* __restrict__ kp, const float* __restrict__ vp,
                                                            int C, float scale, bf16* __restrict__ KB,
                                                            bf16* __restrict__ VB) {
+    pdl_trigger();
+    pdl_wait();
     // blockIdx.y = frame.  Items 0 .. 48*C/8-1: one uint4 (8 channels) of KB[f][row][c]; then one 128-byte row
     // VB[f][c][0..63] per item.  A head owns a contiguous half of the channels (d = C/2, a multiple of 8).
     const int f = blockIdx.y, d = C >> 1, c8n = C >> 3, nK = 48 * c8n;
@@ -867,7 +905,7 @@ int attn_operands_launch(const float* kp, const float* vp, int F, int C, float s
                          cudaStream_t s) {
     if (C % 16) return -36;
     const int items = 48 * (C / 8) + C;
-    attn_operands_kernel<<<dim3((items + 255) / 256, F), 256, 0, s>>>(kp, vp, C, scale, KB, VB);
+    DSB_PDL_LAUNCH(attn_operands_kernel, dim3((items + 255) / 256, F), 256, 0, s, kp, vp, C, scale, KB, VB);
     DSB_LAUNCH_CHECK();
 }
 
@@ -881,6 +919,8 @@ __global__ void __launch_bounds__(384) attn_fold_kernel(const float* __restrict_
                                                        const float* __restrict__ wq, const float* __restrict__ bq,
                                                        const float* __restrict__ wpT, int C, float scale, int T, int tmax,
                                                        bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int KPB = 3;
     __shared__ float sk[KPB][192];
     __shared__ float sv[KPB][192];
@@ -924,7 +964,7 @@ __global__ void __launch_bounds__(384) attn_fold_kernel(const float* __restrict_
 int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
                      float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s) {
     if (C > 384 || C < 32) return -36;
-    attn_fold_kernel<<<dim3(12, F), C, 0, s>>>(kp, vp, wq, bq, wpT, C, scale, T, tmax, K1, sb, V2);
+    DSB_PDL_LAUNCH(attn_fold_kernel, dim3(12, F), C, 0, s, kp, vp, wq, bq, wpT, C, scale, T, tmax, K1, sb, V2);
     DSB_LAUNCH_CHECK();
 }
 
@@ -980,6 +1020,8 @@ struct MsWalk {
 };
 
 __global__ void __launch_bounds__(256, 4) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int C = 768, CV = C / 4, OH = 112, OW = 192, XT = 32;
     const int cv = blockIdx.z % 12 * 16 + (threadIdx.x & 15);
     const int b = blockIdx.z / 12;
@@ -1003,11 +1045,13 @@ __global__ void __launch_bounds__(256, 4) ms_sum_kernel(MsSrc src, bf16* __restr
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {
     MsSrc src;
     for (int k = 0; k < 4; ++k) src.r[k] = r[k];
-    ms_sum_kernel<<<dim3(192 / 32, 112 / 16, B * 12), 256, 0, s>>>(src, S);
+    DSB_PDL_LAUNCH(ms_sum_kernel, dim3(192 / 32, 112 / 16, B * 12), 256, 0, s, src, S);
     DSB_LAUNCH_CHECK();
 }
 
 __global__ void __launch_bounds__(256) final_up_kernel(const float* __restrict__ p, int B, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const long total = (long)B * 224 * 384;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
         const int xo = (int)(i % 384);
@@ -1026,7 +1070,7 @@ int final_up_launch(const float* p, int B, float* out, cudaStream_t s) {
     const long total = (long)B * 224 * 384;
     long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    final_up_kernel<<<(int)g, 256, 0, s>>>(p, B, out);
+    DSB_PDL_LAUNCH(final_up_kernel, (int)g, 256, 0, s, p, B, out);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1035,6 +1079,8 @@ struct AxpyArgs { const float* in[4]; float c[4]; };
 
 __global__ void __launch_bounds__(256) axpy_kernel(int nin, AxpyArgs a, const float* __restrict__ noise, float cn,
                                                   float* __restrict__ out, long n4) {
+    pdl_trigger();
+    pdl_wait();
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
         float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll 4
@@ -1059,7 +1105,7 @@ int axpy_launch(int nin, const float* const in[4], const float c[4], const float
     const long n4 = n >> 2;
     long g = (n4 + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    axpy_kernel<<<(int)g, 256, 0, s>>>(nin, a, noise, cn, out, n4);
+    DSB_PDL_LAUNCH(axpy_kernel, (int)g, 256, 0, s, nin, a, noise, cn, out, n4);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1068,6 +1114,8 @@ int axpy_launch(int nin, const float* const in[4], const float c[4], const float
 // uint8, util/utils.py:11-16): one block per clip, two passes over its 86 016 pixels.
 __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restrict__ x, int n, float* __restrict__ clamped,
                                                           uint8_t* __restrict__ u8) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     __shared__ float smin, smax;
     const float* xb = x + (size_t)blockIdx.x * n;
@@ -1098,7 +1146,7 @@ __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restri
 }
 
 int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s) {
-    postprocess_kernel<<<B, 1024, 0, s>>>(x, n, clamped, u8);
+    DSB_PDL_LAUNCH(postprocess_kernel, B, 1024, 0, s, x, n, clamped, u8);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1327,6 +1375,8 @@ int ln_nct_launch(const float* x, int B, int n, int C, const float* gamma, const
 
 // ------------------------------------------------------------------------------------------ sampler correctors
 __global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ x, long n4, float lo, float hi) {
+    pdl_trigger();
+    pdl_wait();
     float4* x4 = reinterpret_cast<float4*>(x);
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
         float4 v = x4[i];
@@ -1340,7 +1390,7 @@ int clamp_launch(float* x, long n, float lo, float hi, cudaStream_t s) {
     if (n & 3) return -39;
     long g = (n / 4 + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    clamp_kernel<<<(int)g, 256, 0, s>>>(x, n / 4, lo, hi);
+    DSB_PDL_LAUNCH(clamp_kernel, (int)g, 256, 0, s, x, n / 4, lo, hi);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1350,6 +1400,8 @@ int clamp_launch(float* x, long n, float lo, float hi, cudaStream_t s) {
 // One block per clip: exact order statistics by a 4-pass radix select on the bit patterns of |x| (monotone for
 // non-negative floats), no sort.
 __global__ void __launch_bounds__(1024) dyn_threshold_kernel(float* __restrict__ x, int n, int k, float w, float max_val) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned hist[256];
     __shared__ unsigned sh_prefix, sh_rank, sh_eq, sh_next;
     float* xb = x + (size_t)blockIdx.x * n;
@@ -1404,7 +1456,7 @@ __global__ void __launch_bounds__(1024) dyn_threshold_kernel(float* __restrict__
 
 int dyn_threshold_launch(float* x, int B, int n, int k, float w, float max_val, cudaStream_t s) {
     if (k < 0 || k >= n || !(w >= 0.0f && w < 1.0f) || (w != 0.0f && k + 1 >= n)) return -40;
-    dyn_threshold_kernel<<<B, 1024, 0, s>>>(x, n, k, w, max_val);
+    DSB_PDL_LAUNCH(dyn_threshold_kernel, B, 1024, 0, s, x, n, k, w, max_val);
     DSB_LAUNCH_CHECK();
 }
 

@@ -86,6 +86,8 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_trigger();                                    // PDL (common.cuh): resources held -> the next kernel may queue up
+    pdl_wait();                                       // ... and nothing below runs before the previous kernel is done
 
     const int tiles_per_frame = (p.HW + 127) >> 7;
     const int total_tiles = tiles_per_frame * p.F;
@@ -418,8 +420,7 @@ int mlp_fused_run(const MlpLaunch& l, int num_sms, cudaStream_t stream) {
     const int tiles = ((p.HW + 127) / 128) * p.F;
     int grid = tiles < num_sms ? tiles : num_sms;
     if (grid < 1) return -41;
-    mlp_fused_kernel<<<grid, kMlpThreads, smem, stream>>>(p, l.tmA, l.tmW1, l.tmW2, NS);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl_ex(true, mlp_fused_kernel, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
 }
 
 }  // namespace dsb

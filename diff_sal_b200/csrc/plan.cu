@@ -638,14 +638,22 @@ int build_program(dsb_handle* h) {
 }
 
 int run_program(dsb_handle* h, cudaStream_t s, bool serial = false) {
+    // programmatic dependent launch (common.cuh): a launch that directly follows a cross-stream wait keeps a full
+    // dependency (no PDL attribute); every other launch may be scheduled under the tail of its stream predecessor
+    bool after_wait[3] = {false, false, false};
     for (size_t i = 0; i < h->prog.size(); ++i) {
         const int kind = h->prog_kind[i], si = h->prog_stream[i];
         cudaStream_t st = (serial || si == 0) ? s : h->side[si - 1];
         int r = 0;
-        if (kind == 0) r = h->prog[i](st);
+        if (kind == 0) {
+            pdl_allow_next() = !after_wait[si] || serial;
+            after_wait[si] = false;
+            r = h->prog[i](st);
+            pdl_allow_next() = true;
+        }
         else if (serial) continue;
         else if (kind == 1) r = (int)cudaEventRecord(h->ev[h->prog_ev[i]], st);
-        else r = (int)cudaStreamWaitEvent(st, h->ev[h->prog_ev[i]], 0);
+        else { r = (int)cudaStreamWaitEvent(st, h->ev[h->prog_ev[i]], 0); after_wait[si] = true; }
         if (r) return fail(h, DSB_ERR_CUDA, "denoiser step %zu (%s) failed: %s (%d)", i, h->prog_name[i].c_str(),
                            r > 0 ? cudaGetErrorString((cudaError_t)r) : "launcher error", r);
     }
@@ -1057,6 +1065,9 @@ extern "C" int dsb_postprocess(const float* x, int B, int64_t pixels_per_map, fl
 }
 
 extern "C" int64_t dsb_last_launch_count(const dsb_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" void dsb_set_pdl(int mode) { pdl_mode() = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+extern "C" int dsb_get_pdl(void) { return pdl_mode(); }
 
 extern "C" int64_t dsb_debug_read(dsb_handle* h, const char* name, float* dst, int64_t max_elems, void* stream) {
     if (!h || !name || !dst || h->B == 0) return DSB_ERR_ARG;

@@ -144,6 +144,12 @@ int dsb_metrics(const float* pred, const float* density, const float* fixations,
 /* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
 int64_t dsb_last_launch_count(const dsb_handle* h);
 
+/* process-wide mode of programmatic dependent launch for the kernels of a program: 0 off, 1 the memory-bound kernels
+ * only (default), 2 also the tcgen05 kernels (DSB_PDL in the environment sets the initial value).  Changing it does not
+ * invalidate graphs that were already captured. */
+void dsb_set_pdl(int mode);
+int dsb_get_pdl(void);
+
 /* kernel launches enqueued by the last dsb_set_condition call */
 int64_t dsb_condition_launch_count(const dsb_handle* h);
 

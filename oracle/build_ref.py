@@ -1,8 +1,8 @@
 """TEST / BASELINE INFRASTRUCTURE ONLY -- builds oracle/_ref/: the UNMODIFIED reference compiled to sourceless bytecode.
 
 The reference is pure Python, so its "build" is byte-compilation: every /root/reference/**/*.py is compiled with
-py_compile from where it lies into oracle/_ref/<same relative path>.pyc (sourceless layout: ``module.pyc`` next to where
-``module.py`` would be, which Python's SourcelessFileLoader imports).  No reference source is copied into the repository;
+py_compile from where it lies into oracle/_ref/<same relative path with the suffix .refbc> (a .pyc under another suffix: snapshot
+tools tend to drop *.pyc; oracle/ref_loader.py installs a small importer that executes these code objects).  No reference source is copied into the repository;
 oracle/_ref/ is git-ignored (it stays out of history) but NOT gpurun-ignored, so it travels to the GPU box like our own
 built .so files.  There it lets
   * ``bench.py --impl reference`` time the reference's own fp32 PyTorch sampler on the box's host cores
@@ -34,7 +34,7 @@ def build(verbose=False):
             if not f.endswith(".py"):
                 continue
             src = os.path.join(root, f)
-            dst = os.path.join(DST, rel, f + "c")
+            dst = os.path.join(DST, rel, f[:-3] + ".refbc")
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
                 continue

@@ -32,6 +32,48 @@ def available():
     return os.path.isdir(os.path.join(REF_ROOT, "models", "saliency_decoder"))
 
 
+class _BytecodeFinder:
+    """Imports modules from the sourceless build oracle/_ref/ (files ``<module>.refbc`` = py_compile output)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def _locate(self, fullname):
+        base = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(os.path.join(base, "__init__.refbc")):
+            return os.path.join(base, "__init__.refbc"), True
+        if os.path.isfile(base + ".refbc"):
+            return base + ".refbc", False
+        if os.path.isdir(base) and any(f.endswith(".refbc") for f in os.listdir(base)):
+            return None, True                             # namespace-style directory without __init__
+        return None, False
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        path_, is_pkg = self._locate(fullname)
+        if path_ is None and not is_pkg:
+            return None
+        spec = importlib.machinery.ModuleSpec(fullname, self, origin=path_ or os.path.join(self.root, *fullname.split(".")),
+                                              is_package=is_pkg)
+        if is_pkg:
+            spec.submodule_search_locations = [os.path.join(self.root, *fullname.split("."))]
+        spec.has_location = path_ is not None
+        return spec
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        path_, _ = self._locate(module.__name__)
+        if path_ is None:
+            return
+        module.__file__ = path_
+        with open(path_, "rb") as fh:
+            code = marshal.loads(fh.read()[16:])          # 16-byte pyc header (magic, flags, mtime, size)
+        exec(code, module.__dict__)
+
+
 def is_source_tree():
     """True when the reference is imported from its sources, False for the bytecode build in oracle/_ref/."""
     return available() and os.path.exists(os.path.join(REF_ROOT, "models", "saliency_decoder", "sal_unet.py"))
@@ -159,8 +201,14 @@ def load():
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     _install_stubs()
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if is_source_tree():
+        if REF_ROOT not in sys.path:
+            sys.path.insert(0, REF_ROOT)
+    elif not any(isinstance(f, _BytecodeFinder) for f in sys.meta_path):
+        ver = open(os.path.join(REF_ROOT, "PYTHON_VERSION")).read().strip() if os.path.exists(os.path.join(REF_ROOT, "PYTHON_VERSION")) else None
+        if ver and ver != "%d.%d" % sys.version_info[:2]:
+            raise RuntimeError("oracle/_ref was built for Python %s, this is %d.%d" % ((ver,) + tuple(sys.version_info[:2])))
+        sys.meta_path.insert(0, _BytecodeFinder(REF_ROOT))     # ahead of site-packages, like sys.path[0] for the sources
     from models.saliency_decoder.sal_unet import SalUNet
     from models.dpm_solver.sampler import NoiseScheduleVP, model_wrapper, DPM_Solver
     from models.diffusion_decoder.diffusion_utils import get_beta_schedule, to_torch

@@ -21,6 +21,23 @@ def test_reference_arm_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_runs_the_unmodified_reference_from_its_bytecode_build():
+    """oracle/build_ref.py compiles /root/reference to sourceless bytecode under oracle/_ref/ (what travels to the GPU
+    box); pointed at that tree alone, the reference arm must run the real reference (kind "reference")."""
+    sys.path.insert(0, ROOT)
+    from oracle import build_ref
+    if build_ref.build() is None and not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "models")):
+        import pytest
+        pytest.skip("no reference tree and no prebuilt oracle/_ref")
+    env = dict(os.environ, DIFFSAL_REFERENCE=os.path.join(ROOT, "oracle", "_ref"))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert d["cpu_baseline"]["kind"] == "reference", d["cpu_baseline"]
+    assert "bytecode build" in d["cpu_baseline"]["sample"]
+
+
 def test_b200_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
