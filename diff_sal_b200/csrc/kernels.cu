@@ -12,7 +12,7 @@ namespace dsb {
     (void)launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
 int& pdl_mode() {
-    static int mode = [] { const char* e = getenv("DSB_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+    static int mode = [] { const char* e = getenv("DSB_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
     return mode;
 }
 bool& pdl_allow_next() {
@@ -621,10 +621,187 @@ __global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restri
     }
 }
 
+// Second generation of the tiled variant (C = 96, 192): a block owns a TH x TW pixel tile of one frame.
+//  * phase 1 stages the plain normalised values n = (x - mean) * rstd of the (TH + 2) x (TW + 2) neighbourhood (one FFMA
+//    per element; zero outside the image = the conv's zero padding of LN(x)).  The LayerNorm affine is folded out of the
+//    tile:  conv(g * n + b) = sum_k (w_k g) n_k + sum_{k in image} w_k b, with the tables wg = w * g, wb = w * b and
+//    wbs = sum_k wb_k prepared once per weight set (q_dw_prep_launch);
+//  * phase 2: a lane group (LPT lanes x 3 float4 = one token's channels) owns a tile column and walks its TH rows with the
+//    nine taps of one channel vector held in registers, so tap loads, index math and the block's fixed costs are
+//    amortised over TH tokens; the out-of-image taps of border tokens are subtracted from wbs.
+// Against the first version (one token per lane group and block row: 3.2 staged tokens and 27 tap loads per output token,
+// three FP operations per staged element) this stages 1.6 - 2.1 tokens per output token at a third of the arithmetic.
+template <int C, int TW, int TH>
+__global__ void __launch_bounds__(256, 2) q_dwln_tile2_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                                             int H, int W, const float* __restrict__ wg,
+                                                             const float* __restrict__ wb, const float* __restrict__ wbs,
+                                                             const float* __restrict__ qg, const float* __restrict__ qb,
+                                                             bf16* __restrict__ out, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
+    using G = LnGeom<C>;
+    static_assert(G::NVEC == 3 && TW == 8 * G::TPW, "tile geometry: one lane group per tile column");
+    constexpr int HWT = TW + 2, HHT = TH + 2, CV = C / 4, NT = HHT * HWT, PER = 8 * G::TPW, NPASS = (NT + PER - 1) / PER;
+    extern __shared__ float4 tile4[];                    // [HHT][HWT][CV]
+    const int nseg = W / TW, nrow = H / TH;
+    const int seg = blockIdx.x % nseg;
+    const int yb = (blockIdx.x / nseg) % nrow;
+    const int f = blockIdx.x / (nseg * nrow);
+    if (f % T >= tmax) return;
+    const int x0 = seg * TW, y0 = yb * TH;
+    const size_t fbase = (size_t)f * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / G::LPT, l = lane % G::LPT;
+    const int slot = warp * G::TPW + sub;                // tile column of this lane group, 0 .. TW-1
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    // ---- phase 1: normalised neighbourhood -> shared memory (batches of 4 tokens per lane group keep 12 loads in flight)
+#pragma unroll 1
+    for (int p0 = 0; p0 < NPASS; p0 += 4) {
+        float4 v[4][3];
+        float2 st[4];
+        bool ok[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int t = slot + (p0 + p) * PER;
+            const int r = t / HWT, col = t - r * HWT;
+            const int yy = y0 + r - 1, xx = x0 + col - 1;
+            ok[p] = t < NT && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const size_t tok = ok[p] ? fbase + (size_t)yy * W + xx : fbase;
+            st[p] = stats[tok];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[p][i] = x4[tok * CV + l + G::LPT * i];
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int t = slot + (p0 + p) * PER;
+            if (t < NT) {
+                const float rs = ok[p] ? st[p].y : 0.0f, c0 = -st[p].x * rs;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tile4[t * CV + l + G::LPT * i] = make_float4(fmaf(v[p][i].x, rs, c0), fmaf(v[p][i].y, rs, c0),
+                                                                 fmaf(v[p][i].z, rs, c0), fmaf(v[p][i].w, rs, c0));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: depthwise 3x3 down the column, then the channel LayerNorm of each of the TH tokens
+    const float4* wg4 = reinterpret_cast<const float4*>(wg);
+    const float4* wb4 = reinterpret_cast<const float4*>(wb);
+    const int xx = x0 + slot;
+    float4 q[TH][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int cvi = l + G::LPT * i;
+        float4 w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = __ldg(wg4 + k * CV + cvi);
+        const float4 bs = __ldg(reinterpret_cast<const float4*>(wbs) + cvi);
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+            float4 a = bs;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4 tv = tile4[((r + dy) * HWT + slot + dx) * CV + cvi];
+                    const float4 wv = w[dy * 3 + dx];
+                    a.x = fmaf(wv.x, tv.x, a.x); a.y = fmaf(wv.y, tv.y, a.y);
+                    a.z = fmaf(wv.z, tv.z, a.z); a.w = fmaf(wv.w, tv.w, a.w);
+                }
+            const int yy = y0 + r;
+            if (yy == 0 || yy == H - 1 || xx == 0 || xx == W - 1) {          // border token: drop the out-of-image bias taps
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int y2 = yy + dy - 1, x2 = xx + dx - 1;
+                        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) {
+                            const float4 t = __ldg(wb4 + (dy * 3 + dx) * CV + cvi);
+                            a.x -= t.x; a.y -= t.y; a.z -= t.z; a.w -= t.w;
+                        }
+                    }
+            }
+            q[r][i] = a;
+        }
+    }
+    float4 gq[3], bq[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        gq[i] = __ldg(reinterpret_cast<const float4*>(qg) + l + G::LPT * i);
+        bq[i] = __ldg(reinterpret_cast<const float4*>(qb) + l + G::LPT * i);
+    }
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s += (q[r][i].x + q[r][i].y) + (q[r][i].z + q[r][i].w);
+        const float mean = group_sum<G::LPT>(s) * (1.0f / C);
+        float v2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float a = q[r][i].x - mean, b = q[r][i].y - mean, c = q[r][i].z - mean, d = q[r][i].w - mean;
+            v2 = fmaf(a, a, v2); v2 = fmaf(b, b, v2); v2 = fmaf(c, c, v2); v2 = fmaf(d, d, v2);
+        }
+        const float rstd = rsqrtf(group_sum<G::LPT>(v2) * (1.0f / C) + 1e-5f);
+        uint2* o = reinterpret_cast<uint2*>(out + (fbase + (size_t)(y0 + r) * W + xx) * C);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            o[l + G::LPT * i] = make_uint2(
+                pack_bf16x2((q[r][i].x - mean) * rstd * gq[i].x + bq[i].x, (q[r][i].y - mean) * rstd * gq[i].y + bq[i].y),
+                pack_bf16x2((q[r][i].z - mean) * rstd * gq[i].z + bq[i].z, (q[r][i].w - mean) * rstd * gq[i].w + bq[i].w));
+    }
+}
+
+// wg[k][c] = w[k][c] * g[c], wb[k][c] = w[k][c] * b[c], wbs[c] = sum_k wb[k][c]   (w: [9][C] depthwise taps)
+__global__ void q_dw_prep_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b, int C,
+                                 float* __restrict__ wg, float* __restrict__ wb, float* __restrict__ wbs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.0f;
+    for (int k = 0; k < 9; ++k) {
+        const float wv = w[k * C + c];
+        wg[k * C + c] = wv * g[c];
+        const float t = wv * b[c];
+        wb[k * C + c] = t;
+        s += t;
+    }
+    wbs[c] = s;
+}
+
+int q_dw_prep_launch(const float* w9, const float* ng, const float* nb, int C, float* wg, float* wb, float* wbs, cudaStream_t s) {
+    q_dw_prep_kernel<<<(C + 127) / 128, 128, 0, s>>>(w9, ng, nb, C, wg, wb, wbs);
+    DSB_LAUNCH_CHECK();
+}
+
+template <int C, int TW, int TH>
+static int q_dwln_tile2_launch(const float* x, const float2* stats, int F, int H, int W, const QdwTables& tb, const float* qg,
+                               const float* qb, bf16* out, int T, int tmax, cudaStream_t s) {
+    constexpr size_t smem = (size_t)(TH + 2) * (TW + 2) * C * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(q_dwln_tile2_kernel<C, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    DSB_PDL_LAUNCH((q_dwln_tile2_kernel<C, TW, TH>), F * (H / TH) * (W / TW), 256, smem, s, x, stats, H, W, tb.wg, tb.wb, tb.wbs, qg,
+                   qb, out, T, tmax);
+    DSB_LAUNCH_CHECK();
+}
+
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
-                  const float* wq, const float* qg, const float* qb, bf16* out, int T, int tmax, cudaStream_t s) {
+                  const float* wq, const QdwTables* tb, const float* qg, const float* qb, bf16* out, int T, int tmax,
+                  cudaStream_t s) {
     const long tokens = (long)F * H * W;
     const int g = (int)((tokens + 7) / 8);
+    static const int th = [] { const char* e = getenv("DSB_QDW_TH"); return e ? atoi(e) : 4; }();
+    if (tb && tb->wg && C == 96 && W % 32 == 0 && H % 4 == 0) {
+        if (th == 2) return q_dwln_tile2_launch<96, 32, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 4) return q_dwln_tile2_launch<96, 32, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+    }
+    if (tb && tb->wg && C == 192 && W % 16 == 0 && H % 4 == 0) {
+        if (th == 2) return q_dwln_tile2_launch<192, 16, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 4) return q_dwln_tile2_launch<192, 16, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+    }
     if (C == 96 && W % 32 == 0) {
         DSB_PDL_LAUNCH((q_dwln_tiled_kernel<96, 32>), F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s, x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
         DSB_LAUNCH_CHECK();
@@ -636,7 +813,7 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
     switch (C) {
         case 384: DSB_PDL_LAUNCH((q_dwln_kernel<384>), g, 256, 0, s, x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
         case 768: DSB_PDL_LAUNCH((q_dwln_kernel<768>), g, 256, 0, s, x, stats, tokens, H, W, ng, nb, wq, qg, qb, out, T, tmax); break;
-        default: return -31;     // C = 96 / 192 need W % 32 / W % 16 == 0 (tiled kernel above)
+        default: return -31;     // C = 96 / 192 need W % 32 / W % 16 == 0 (tiled kernels above)
     }
     DSB_LAUNCH_CHECK();
 }
@@ -971,81 +1148,72 @@ int attn_fold_launch(const float* kp, const float* vp, const float* wq, const fl
 // ------------------------------------------------------------------------------------------ multi-scale sum
 struct MsSrc { const float* r[4]; };
 
-// thread = (4-channel vector, output row); produces 32 consecutive output columns.  All four scales are exact powers
-// of two (1/2 .. 1/16), so for an output column xo0 + dx the left source column is (xo0 >> n) + off(dx, n) and the
-// horizontal weight lx(dx, n) are COMPILE-TIME constants of dx: the walk is fully unrolled, the reload points of the
-// vertically interpolated source columns are static and the weights fold into immediates.  Index clamping at the
-// image edges reproduces PyTorch's "clamp the source coordinate at 0 / last" exactly (both taps hit the same pixel).
+// thread = (4-channel vector, output row); produces XT = 16 consecutive output columns.  All four scales are exact powers
+// of two (1/2 .. 1/16), so for an output column xo0 + dx (xo0 a multiple of 16) the left source column is
+// (xo0 >> n) + off(dx, n) and the horizontal weight lx(dx, n) are COMPILE-TIME constants of dx.  The sources are taken one
+// after the other: the 16 outputs touch only NC = 16 / 2^n + 2 source columns, which are loaded (both rows) and
+// interpolated vertically ONCE into registers, then every output adds (1 - lx) * V[j] + lx * V[j + 1] with static j and
+// immediates for the weights.  Index clamping at the image edges reproduces PyTorch's "clamp the source coordinate at
+// 0 / last" exactly (both taps then hit the same pixel).  ~50 SASS instructions per output vector in 14 KB of code (the
+// first version walked all four sources column by column: 88 instructions per vector in 45 KB, beyond the 32 KB
+// instruction cache).
+constexpr int kMsXT = 16;
+
 template <int N, int DX>
-__device__ __forceinline__ void ms_accum(const float4* __restrict__ base, int y0, int y1, float ly, int xb, int& xl,
-                                         float4& colL, float4& colR, float4& acc) {
-    constexpr int W = 192 >> N, CV = 192;
-    constexpr int o = PowX<N>::off(DX);
-    constexpr float lxv = PowX<N>::lx(DX);
-    constexpr bool reload = (DX == 0) || (PowX<N>::off(DX) != PowX<N>::off(DX > 0 ? DX - 1 : 0));
-    if constexpr (reload) {
-        const int xu = xb + o;
-        const int x0 = min(max(xu, 0), W - 1), x1 = min(max(xu + 1, 0), W - 1);
-        const float h0 = 1.0f - ly;
-        if (DX != 0 && x0 == xl + 1) {
-            colL = colR;                                         // the walk advanced by one source column
-        } else {
-            const float4 a = base[((size_t)y0 * W + x0) * CV], c = base[((size_t)y1 * W + x0) * CV];
-            colL = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
-        }
-        const float4 a = base[((size_t)y0 * W + x1) * CV], c = base[((size_t)y1 * W + x1) * CV];
-        colR = make_float4(h0 * a.x + ly * c.x, h0 * a.y + ly * c.y, h0 * a.z + ly * c.z, h0 * a.w + ly * c.w);
-        xl = x0;
-    }
-    constexpr float w0 = 1.0f - lxv;
-    acc.x += w0 * colL.x + lxv * colR.x;
-    acc.y += w0 * colL.y + lxv * colR.y;
-    acc.z += w0 * colL.z + lxv * colR.z;
-    acc.w += w0 * colL.w + lxv * colR.w;
+__device__ __forceinline__ void ms_out(const float4 (&V)[(kMsXT >> N) + 2], float4 (&acc)[kMsXT]) {
+    constexpr int j = PowX<N>::off(DX) + 1;                       // V[0] is source column (xo0 >> N) - 1
+    constexpr float lx = PowX<N>::lx(DX), w0 = 1.0f - lx;
+    acc[DX].x = fmaf(lx, V[j + 1].x, fmaf(w0, V[j].x, acc[DX].x));
+    acc[DX].y = fmaf(lx, V[j + 1].y, fmaf(w0, V[j].y, acc[DX].y));
+    acc[DX].z = fmaf(lx, V[j + 1].z, fmaf(w0, V[j].z, acc[DX].z));
+    acc[DX].w = fmaf(lx, V[j + 1].w, fmaf(w0, V[j].w, acc[DX].w));
+    if constexpr (DX + 1 < kMsXT) ms_out<N, DX + 1>(V, acc);
 }
 
-template <int DX>
-struct MsWalk {
-    static __device__ __forceinline__ void run(const float4* const (&base)[4], const int (&y0)[4], const int (&y1)[4],
-                                               const float (&ly)[4], const int (&xb)[4], int (&xl)[4],
-                                               float4 (&colL)[4], float4 (&colR)[4], uint2* __restrict__ orow) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        ms_accum<4, DX>(base[0], y0[0], y1[0], ly[0], xb[0], xl[0], colL[0], colR[0], acc);   // 7x12   (1/16)
-        ms_accum<3, DX>(base[1], y0[1], y1[1], ly[1], xb[1], xl[1], colL[1], colR[1], acc);   // 14x24  (1/8)
-        ms_accum<2, DX>(base[2], y0[2], y1[2], ly[2], xb[2], xl[2], colL[2], colR[2], acc);   // 28x48  (1/4)
-        ms_accum<1, DX>(base[3], y0[3], y1[3], ly[3], xb[3], xl[3], colL[3], colR[3], acc);   // 56x96  (1/2)
-        orow[(size_t)DX * 192] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
-        if constexpr (DX + 1 < 32) MsWalk<DX + 1>::run(base, y0, y1, ly, xb, xl, colL, colR, orow);
+template <int N>
+__device__ __forceinline__ void ms_source(const float* __restrict__ r, int b, int cv, int yo, int xo0, float4 (&acc)[kMsXT]) {
+    constexpr int H = 112 >> N, W = 192 >> N, CV = 192, NC = (kMsXT >> N) + 2;
+    int y0, y1;
+    float ly;
+    bil_src(yo, 1.0f / (float)(1 << N), H, y0, y1, ly);
+    const float4* row0 = reinterpret_cast<const float4*>(r) + ((size_t)b * H + y0) * W * CV + cv;
+    const float4* row1 = reinterpret_cast<const float4*>(r) + ((size_t)b * H + y1) * W * CV + cv;
+    const int xb = (xo0 >> N) - 1;
+    float4 V[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const int x = min(max(xb + j, 0), W - 1);
+        const float4 a = row0[x * CV], c = row1[x * CV];
+        V[j] = make_float4(fmaf(ly, c.x - a.x, a.x), fmaf(ly, c.y - a.y, a.y), fmaf(ly, c.z - a.z, a.z), fmaf(ly, c.w - a.w, a.w));
     }
-};
+    ms_out<N, 0>(V, acc);
+}
 
-__global__ void __launch_bounds__(256, 4) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
+__global__ void __launch_bounds__(256, 2) ms_sum_kernel(MsSrc src, bf16* __restrict__ S) {
     pdl_trigger();
     pdl_wait();
-    constexpr int C = 768, CV = C / 4, OH = 112, OW = 192, XT = 32;
+    constexpr int CV = 192, OH = 112, OW = 192;
     const int cv = blockIdx.z % 12 * 16 + (threadIdx.x & 15);
     const int b = blockIdx.z / 12;
     const int yo = blockIdx.y * 16 + (threadIdx.x >> 4);
-    const int xo0 = blockIdx.x * XT;
-    const float4* base[4];
-    int y0[4], y1[4], xb[4], xl[4] = {-9, -9, -9, -9};
-    float ly[4];
+    const int xo0 = blockIdx.x * kMsXT;
+    float4 acc[kMsXT];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int H = 7 << k, W = 12 << k;
-        base[k] = reinterpret_cast<const float4*>(src.r[k] + (size_t)b * H * W * C) + cv;
-        bil_src(yo, (float)H / (float)OH, H, y0[k], y1[k], ly[k]);
-        xb[k] = xo0 >> (4 - k);
-    }
-    float4 colL[4], colR[4];
+    for (int i = 0; i < kMsXT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ms_source<4>(src.r[0], b, cv, yo, xo0, acc);          // 7x12    (1/16)
+    ms_source<3>(src.r[1], b, cv, yo, xo0, acc);          // 14x24   (1/8)
+    ms_source<2>(src.r[2], b, cv, yo, xo0, acc);          // 28x48   (1/4)
+    ms_source<1>(src.r[3], b, cv, yo, xo0, acc);          // 56x96   (1/2)
     uint2* orow = reinterpret_cast<uint2*>(S) + (((size_t)b * OH + yo) * OW + xo0) * CV + cv;
-    MsWalk<0>::run(base, y0, y1, ly, xb, xl, colL, colR, orow);
+#pragma unroll
+    for (int i = 0; i < kMsXT; ++i)
+        orow[(size_t)i * CV] = make_uint2(pack_bf16x2(acc[i].x, acc[i].y), pack_bf16x2(acc[i].z, acc[i].w));
 }
 
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {
     MsSrc src;
     for (int k = 0; k < 4; ++k) src.r[k] = r[k];
-    DSB_PDL_LAUNCH(ms_sum_kernel, dim3(192 / 32, 112 / 16, B * 12), 256, 0, s, src, S);
+    DSB_PDL_LAUNCH(ms_sum_kernel, dim3(192 / kMsXT, 112 / 16, B * 12), 256, 0, s, src, S);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1147,6 +1315,31 @@ __global__ void __launch_bounds__(1024) postprocess_kernel(const float* __restri
 
 int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s) {
     DSB_PDL_LAUNCH(postprocess_kernel, B, 1024, 0, s, x, n, clamped, u8);
+    DSB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------ adaptive-step error norm
+// dpm_solver_adaptive (sampler.py:996-999): per sample  E_b = sqrt(mean(((x_higher - x_lower) / delta)^2)),
+// delta = max(atol, rtol * max(|x_lower|, |x_prev|)).  One block per sample, fp32 like the reference.
+__global__ void __launch_bounds__(1024) adaptive_error_kernel(const float* __restrict__ xl, const float* __restrict__ xh,
+                                                             const float* __restrict__ xp, int n, float atol, float rtol,
+                                                             float* __restrict__ out) {
+    __shared__ float red[32];
+    const size_t base = (size_t)blockIdx.x * n;
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float a = xl[base + i], b = xh[base + i], c = xp[base + i];
+        const float delta = fmaxf(atol, rtol * fmaxf(fabsf(a), fabsf(c)));
+        const float e = (b - a) / delta;
+        acc = fmaf(e, e, acc);
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = sqrtf(tot / (float)n);
+}
+
+int adaptive_error_launch(const float* xl, const float* xh, const float* xp, int B, int n, float atol, float rtol, float* out,
+                          cudaStream_t s) {
+    adaptive_error_kernel<<<B, 1024, 0, s>>>(xl, xh, xp, n, atol, rtol, out);
     DSB_LAUNCH_CHECK();
 }
 

@@ -37,8 +37,13 @@ int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, cons
                     int T, int tmax, cudaStream_t s);
 
 // q = LN_q( depthwise3x3( LN_norm(x) ) )  -> bf16 [tokens][C]      (attention.py:36-48,92 ; transformer.py:151)
+// tb (optional): tap tables with the LayerNorm affine folded in (q_dw_prep_launch); with them the narrow stages
+// (C = 96, 192) take the second-generation tiled kernel.
+struct QdwTables { const float* wg; const float* wb; const float* wbs; };     // [9][C], [9][C], [C]
+int q_dw_prep_launch(const float* w9, const float* ng, const float* nb, int C, float* wg, float* wb, float* wbs, cudaStream_t s);
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
-                  const float* wq /*[9][C]*/, const float* qg, const float* qb, bf16* out, int T, int tmax, cudaStream_t s);
+                  const float* wq /*[9][C]*/, const QdwTables* tb, const float* qg, const float* qb, bf16* out, int T, int tmax,
+                  cudaStream_t s);
 
 // v (or visual-only k) = LN( depthwise sxs stride s ( LN_norm(x) ) ) -> bf16 [F*18][C]   (attention.py:53-76,93)
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
@@ -73,6 +78,10 @@ int axpy_launch(int nin, const float* const in[4], const float c[4], const float
 // clamp(x, 0, 1) (inverse_data_transform, datasets/__init__.py:26-35) and per-map min-max -> uint8 (normalize_data,
 // util/utils.py:11-16); either output may be null.  n = pixels per map.
 int postprocess_launch(const float* x, int B, int n, float* clamped, uint8_t* u8, cudaStream_t s);
+
+// per-sample error norm of DPM-Solver's adaptive step-size control (sampler.py:996-999): out[B]
+int adaptive_error_launch(const float* xl, const float* xh, const float* xp, int B, int n, float atol, float rtol, float* out,
+                          cudaStream_t s);
 
 // *out += 64-bit content fingerprint of a 16-byte-aligned device buffer (out must be zeroed by the caller)
 int content_hash_launch(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s);

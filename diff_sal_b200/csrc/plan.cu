@@ -510,7 +510,8 @@ int build_program(dsb_handle* h) {
             b.conv(op, "attn.proj_v");
         }
         b.cur = 0;
-        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
+        const QdwTables qtb = {WF(bk + "attn.conv_proj_q.wg"), WF(bk + "attn.conv_proj_q.wb"), WF(bk + "attn.conv_proj_q.wbs")};
+        b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, &qtb, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
         // algorithmic FLOPs are always the reference's (all 9 frames), also where dead frames are skipped
         const bool fused_attn = C <= 192;
         if (fused_attn) {
@@ -802,6 +803,18 @@ extern "C" int dsb_finalize_weights(dsb_handle* h) {
         if (int r = pack_gemm_weight(h, bk + "mlp.fc2.weight", C, 2 * C, 1)) return r;
         // depthwise Conv3d(3,3,3) on a depth-1 volume: only the middle temporal tap touches data (attention.py:36-44)
         if (int r = pack_dw(h, bk + "attn.conv_proj_q.conv.weight", C, 9, 27, 9)) return r;
+        {   // depthwise taps with the pre-attention LayerNorm affine folded in (q_dwln_tile2_kernel)
+            float *wg = nullptr, *wb = nullptr, *wbs = nullptr;
+            if (int r = dev_alloc(h, &wg, (size_t)9 * C)) return r;
+            if (int r = dev_alloc(h, &wb, (size_t)9 * C)) return r;
+            if (int r = dev_alloc(h, &wbs, (size_t)C)) return r;
+            if (int r = q_dw_prep_launch(h->wf[bk + "attn.conv_proj_q.conv.weight"], W(h, bk + "norm.weight"), W(h, bk + "norm.bias"),
+                                         C, wg, wb, wbs, 0))
+                return fail(h, DSB_ERR_CUDA, "q_dw_prep launch %d", r);
+            h->wf[bk + "attn.conv_proj_q.wg"] = wg;
+            h->wf[bk + "attn.conv_proj_q.wb"] = wb;
+            h->wf[bk + "attn.conv_proj_q.wbs"] = wbs;
+        }
         if (int r = pack_dw(h, bk + "attn.conv_proj_k.conv.weight", C, sk * sk, sk * sk, 0)) return r;
         if (int r = pack_dw(h, bk + "attn.conv_proj_v.conv.weight", C, sk * sk, sk * sk, 0)) return r;
         if (h->cfg.audio_visual) {
@@ -888,6 +901,12 @@ extern "C" int dsb_sampler_clamp(float* x, int64_t n, float lo, float hi, void* 
     return clamp_launch(x, (long)n, lo, hi, (cudaStream_t)stream) ? DSB_ERR_CUDA : DSB_OK;
 }
 
+extern "C" int dsb_sampler_adaptive_error(const float* x_lower, const float* x_higher, const float* x_prev, int B, int64_t n,
+                                          float atol, float rtol, float* out, void* stream) {
+    if (!x_lower || !x_higher || !x_prev || !out || B < 1 || n < 1 || n > (1 << 30)) return DSB_ERR_ARG;
+    return adaptive_error_launch(x_lower, x_higher, x_prev, B, (int)n, atol, rtol, out, (cudaStream_t)stream) ? DSB_ERR_CUDA : DSB_OK;
+}
+
 extern "C" int dsb_sampler_dynamic_threshold(float* x, int B, int64_t n, int k, float w, float max_val, void* stream) {
     if (!x || B < 1 || n < 2 || n > (1 << 30)) return DSB_ERR_ARG;
     return dyn_threshold_launch(x, B, (int)n, k, w, max_val, (cudaStream_t)stream) ? DSB_ERR_ARG : DSB_OK;
@@ -899,7 +918,8 @@ static int enqueue_sampler(dsb_handle* h, const dsb_sampler_desc* d, int B, cuda
     for (int i = 0; i < d->n_ops; ++i) {
         const dsb_sampler_op& op = d->ops[i];
         if (op.kind == DSB_OP_EVAL) {
-            h->cur_x = h->sbuf[0];
+            if (op.src[0] < 0 || op.src[0] > 7 || op.src[0] == 1) return fail(h, DSB_ERR_ARG, "sampler op %d: bad EVAL source buffer", i);
+            h->cur_x = h->sbuf[op.src[0]];
             h->cur_t = h->t_all + (size_t)eval_idx * B;
             h->cur_out = h->sbuf[1];
             ++eval_idx;
@@ -1120,6 +1140,56 @@ extern "C" int dsb_profile_denoise(dsb_handle* h, const float* x, const float* t
         bytes[k] = h->prog_bytes[idx[k]];
     }
     for (auto& e2 : ev) cudaEventDestroy(e2);
+    h->profile_idx = idx;
+    return rc ? rc : n;
+}
+
+// Timeline of one evaluation as it really runs (three streams, event joins): an event pair around every launch on the
+// stream it is enqueued on; start / end in ms relative to the first launch.  Shows the critical path and the idle gaps
+// that the serialised profile above cannot.  Returns the number of launches.
+extern "C" int dsb_profile_timeline(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream,
+                                    float* start_ms, float* end_ms, int* stream_idx, int cap) {
+    if (!h || !x || !t || !out || !start_ms || !end_ms || !stream_idx) return DSB_ERR_ARG;
+    if (h->B == 0 || h->prog.empty()) return fail(h, DSB_ERR_ARG, "dsb_profile_timeline before dsb_set_condition");
+    if (B != h->B) return fail(h, DSB_ERR_ARG, "batch %d differs from the conditioned batch %d", B, h->B);
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<int> idx;
+    for (size_t i = 0; i < h->prog.size(); ++i)
+        if (h->prog_kind[i] == 0) idx.push_back((int)i);
+    const int n = (int)idx.size();
+    if (cap < n) return fail(h, DSB_ERR_ARG, "timeline buffers too small (%d < %d)", cap, n);
+    std::vector<cudaEvent_t> e0(n), e1(n);
+    for (int k = 0; k < n; ++k) { CUDA_TRY(h, cudaEventCreate(&e0[k])); CUDA_TRY(h, cudaEventCreate(&e1[k])); }
+    cudaEvent_t origin;
+    CUDA_TRY(h, cudaEventCreate(&origin));
+    h->cur_x = x; h->cur_t = t; h->cur_out = out;
+    CUDA_TRY(h, cudaEventRecord(origin, s));
+    int rc = 0, k = 0;
+    const int keep = pdl_mode();
+    pdl_mode() = 0;                                   // event records between launches would defeat it anyway
+    for (size_t i = 0; i < h->prog.size() && !rc; ++i) {
+        const int kind = h->prog_kind[i], si = h->prog_stream[i];
+        cudaStream_t st = si == 0 ? s : h->side[si - 1];
+        int r = 0;
+        if (kind == 0) {
+            cudaEventRecord(e0[k], st);
+            r = h->prog[i](st);
+            cudaEventRecord(e1[k], st);
+            stream_idx[k] = si;
+            ++k;
+        } else if (kind == 1) r = (int)cudaEventRecord(h->ev[h->prog_ev[i]], st);
+        else r = (int)cudaStreamWaitEvent(st, h->ev[h->prog_ev[i]], 0);
+        if (r) rc = fail(h, DSB_ERR_CUDA, "timeline step %zu (%s) failed: %d", i, h->prog_name[i].c_str(), r);
+    }
+    pdl_mode() = keep;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (!rc && e != cudaSuccess) rc = fail(h, DSB_ERR_CUDA, "timeline sync: %s", cudaGetErrorString(e));
+    for (int j = 0; j < n && !rc; ++j) {
+        cudaEventElapsedTime(&start_ms[j], origin, e0[j]);
+        cudaEventElapsedTime(&end_ms[j], origin, e1[j]);
+    }
+    for (int j = 0; j < n; ++j) { cudaEventDestroy(e0[j]); cudaEventDestroy(e1[j]); }
+    cudaEventDestroy(origin);
     h->profile_idx = idx;
     return rc ? rc : n;
 }

@@ -74,7 +74,12 @@ extern "C" int dsb_test_q_dwln(const float* x, int F, int H, int W, int C, const
                                int T, int tmax, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = ln_stats_launch(x, (long)F * H * W, C, (float2*)stats_scratch, H * W, T, tmax, s)) return r;
-    return q_dwln_launch(x, (const float2*)stats_scratch, F, H, W, C, ng, nb, wq9, qg, qb, (bf16*)out, T, tmax, s);
+    // folded tap tables of the second-generation tiled kernel (prepared per weight set in the product)
+    static float* tb = nullptr;
+    if (!tb && cudaMalloc(&tb, (size_t)(19 * 768) * sizeof(float)) != cudaSuccess) return -1;
+    if (int r = q_dw_prep_launch(wq9, ng, nb, C, tb, tb + 9 * 768, tb + 18 * 768, s)) return r;
+    const QdwTables qt = {tb, tb + 9 * 768, tb + 18 * 768};
+    return q_dwln_launch(x, (const float2*)stats_scratch, F, H, W, C, ng, nb, wq9, &qt, qg, qb, (bf16*)out, T, tmax, s);
 }
 
 extern "C" int dsb_test_pool_ln(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,

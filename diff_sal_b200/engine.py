@@ -67,12 +67,21 @@ def _bind(lib):
     lib.dsb_profile_denoise.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_double), ci]
     lib.dsb_profile_denoise.restype = ci
+    lib.dsb_profile_timeline.argtypes = [vp, vp, vp, vp, ci, vp, ctypes.POINTER(cf), ctypes.POINTER(cf),
+                                         ctypes.POINTER(ci), ci]
+    lib.dsb_profile_timeline.restype = ci
+    lib.dsb_set_pdl.argtypes = [ci]
+    lib.dsb_set_pdl.restype = None
+    lib.dsb_get_pdl.argtypes = []
+    lib.dsb_get_pdl.restype = ci
     lib.dsb_profile_name.argtypes = [vp, ci]
     lib.dsb_profile_name.restype = ctypes.c_char_p
     lib.dsb_sampler_clamp.argtypes = [vp, ctypes.c_int64, cf, cf, vp]
     lib.dsb_sampler_clamp.restype = ci
     lib.dsb_sampler_dynamic_threshold.argtypes = [vp, ci, ctypes.c_int64, ci, cf, cf, vp]
     lib.dsb_sampler_dynamic_threshold.restype = ci
+    lib.dsb_sampler_adaptive_error.argtypes = [vp, vp, vp, ci, ctypes.c_int64, cf, cf, vp, vp]
+    lib.dsb_sampler_adaptive_error.restype = ci
     lib.dsb_audio_create.argtypes = [ci, ctypes.POINTER(vp)]
     lib.dsb_audio_create.restype = ci
     lib.dsb_audio_destroy.argtypes = [vp]
@@ -243,8 +252,9 @@ class Engine:
         slabs, post = 0, False
         for i, op in enumerate(ops):
             o = arr[i]
-            if op[0] == "eval":
+            if op[0] == "eval":                         # ('eval', t[, source buffer])
                 o.kind, o.t, o.noise_index = OP_EVAL, float(op[1]), -1
+                o.src[0] = int(op[2]) if len(op) > 2 else 0
             elif op[0] == "clamp":                      # ('clamp', buf, lo, hi)
                 o.kind, o.dst, o.noise_index = OP_CLAMP, int(op[1]), -1
                 o.coef[0], o.coef[1] = float(op[2]), float(op[3])
@@ -293,6 +303,18 @@ class Engine:
             n = self._check(self.lib.dsb_profile_denoise(self._h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), x.shape[0],
                                                          _stream(), ms, fl, by, cap), "debug")
         return [(self.lib.dsb_profile_name(self._h, i).decode(), ms[i], fl[i], by[i]) for i in range(n)]
+
+    def profile_timeline(self, x, t):
+        """[(name, start_ms, end_ms, stream)] of one evaluation run on its three streams (CUDA events per launch)."""
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        t = torch.as_tensor(t).to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        out = torch.empty_like(x)
+        cap = 512
+        a, b, si = (ctypes.c_float * cap)(), (ctypes.c_float * cap)(), (ctypes.c_int * cap)()
+        with torch.cuda.device(self.device):
+            n = self._check(self.lib.dsb_profile_timeline(self._h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), x.shape[0],
+                                                          _stream(), a, b, si, cap), "debug")
+        return [(self.lib.dsb_profile_name(self._h, i).decode(), a[i], b[i], si[i]) for i in range(n)]
 
     def condition_launch_count(self):
         return int(self.lib.dsb_condition_launch_count(self._h))

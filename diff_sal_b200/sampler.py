@@ -384,6 +384,243 @@ def build_dpm_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type
     return ops, times
 
 
+def singlestep_orders(steps, order):
+    """get_orders_and_timesteps_for_singlestep_solver (sampler.py:514-536): (orders, K)."""
+    if order == 3:
+        K = steps // 3 + 1
+        if steps % 3 == 0:
+            return [3] * (K - 2) + [2, 1], K
+        if steps % 3 == 1:
+            return [3] * (K - 1) + [1], K
+        return [3] * (K - 1) + [2], K
+    if order == 2:
+        if steps % 2 == 0:
+            return [2] * (steps // 2), steps // 2
+        return [2] * (steps // 2) + [1], steps // 2 + 1
+    if order == 1:
+        return [1] * steps, 1
+    raise ValueError("'order' must be '1' or '2' or '3'.")
+
+
+class _SinglestepBuilder:
+    """Emits dpm_solver_first_update / singlestep_dpm_solver_second_update / _third_update (sampler.py:548-795) as
+    EVAL/AXPY ops.  Buffers: x = 0, model_s / model_s1 / model_s2 = 2 / 3 / 4, the intermediate iterate = 5.  Unlike the
+    reference (which calls ``self.model_fn(x, s)`` without ``img`` there, sampler.py:573,585,630,...), every evaluation runs
+    the conditioned network: SURVEY 8f row N4."""
+    MS, MS1, MS2, XI = 2, 3, 4, 5
+
+    def __init__(self, ns, algorithm_type, model_type, solver_type, thresholding=None, map_elems=224 * 384):
+        if solver_type not in ("dpmsolver", "taylor"):
+            raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+        self.ns, self.pp, self.model_type, self.st = ns, algorithm_type == "dpmsolver++", model_type, solver_type
+        self.wm = _WrappedModel(None, ns, model_type, {})
+        self.thr, self.map_elems = thresholding, map_elems
+        self.ops, self.times = [], []
+
+    def model_value(self, t, slot, xbuf):
+        """buf[slot] = model_fn(buf[xbuf], t): noise prediction (dpmsolver) or data prediction (dpmsolver++)."""
+        ns = self.ns
+        self.times.append(ns.model_time(t))
+        self.ops.append(("eval", ns.model_time(t), xbuf))
+        cx, cr = self.wm.mix(t)
+        if self.pp:
+            a, s_ = ns.marginal_alpha(t), ns.marginal_std(t)
+            cx, cr = (1.0 - s_ * cx) / a, -s_ * cr / a
+            if self.model_type == "x_start":
+                cx, cr = 0.0, 1.0
+        terms = [(_RAW, cr)] if cx == 0.0 else [(xbuf, cx), (_RAW, cr)]
+        self.ops.append(("axpy", slot, terms, 0.0, -1))
+        if self.pp and self.thr is not None:
+            self.ops.append(("thresh", slot) + quantile_rank(self.thr[0], self.map_elems) + (float(self.thr[1]),))
+
+    def _base(self, s, t):
+        ns = self.ns
+        h = ns.marginal_lambda(t) - ns.marginal_lambda(s)
+        return ns, h
+
+    def _lin(self, s, u, h_frac_phi):
+        """(coefficient of x, coefficient of model_s) of the first-order part from s to u."""
+        ns = self.ns
+        if self.pp:
+            return ns.marginal_std(u) / ns.marginal_std(s), -ns.marginal_alpha(u) * math.expm1(-h_frac_phi)
+        return math.exp(ns.marginal_log_mean_coeff(u) - ns.marginal_log_mean_coeff(s)), -ns.marginal_std(u) * math.expm1(h_frac_phi)
+
+    def first(self, s, t, have_model_s=False, dst=_X):
+        ns, h = self._base(s, t)
+        if not have_model_s:
+            self.model_value(s, self.MS, _X)
+        cx, cm = self._lin(s, t, h)
+        self.ops.append(("axpy", dst, [(_X, cx), (self.MS, cm)], 0.0, -1))
+
+    def second(self, s, t, r1=None, have_model_s=False, dst=_X):
+        ns, h = self._base(s, t)
+        r1 = 0.5 if r1 is None else r1
+        s1 = ns.inverse_lambda(ns.marginal_lambda(s) + r1 * h)
+        if not have_model_s:
+            self.model_value(s, self.MS, _X)
+        cx1, cm1 = self._lin(s, s1, r1 * h)
+        self.ops.append(("axpy", self.XI, [(_X, cx1), (self.MS, cm1)], 0.0, -1))
+        self.model_value(s1, self.MS1, self.XI)
+        cx, cm = self._lin(s, t, h)                          # cm = -(alpha_t | sigma_t) * phi_1
+        if self.st == "dpmsolver":
+            d = (0.5 / r1) * cm                              # ... - (0.5 / r1) (a phi_1) (m1 - m0)
+        elif self.pp:
+            d = (1.0 / r1) * (ns.marginal_alpha(t) * (math.expm1(-h) / h + 1.0))
+        else:
+            d = -(1.0 / r1) * (ns.marginal_std(t) * (math.expm1(h) / h - 1.0))
+        self.ops.append(("axpy", dst, [(_X, cx), (self.MS, cm - d), (self.MS1, d)], 0.0, -1))
+
+    def third(self, s, t, r1=None, r2=None, have_model_s=False, have_model_s1=False, dst=_X):
+        ns, h = self._base(s, t)
+        r1 = 1.0 / 3.0 if r1 is None else r1
+        r2 = 2.0 / 3.0 if r2 is None else r2
+        lam_s = ns.marginal_lambda(s)
+        s1, s2 = ns.inverse_lambda(lam_s + r1 * h), ns.inverse_lambda(lam_s + r2 * h)
+        if not have_model_s:
+            self.model_value(s, self.MS, _X)
+        if not have_model_s1:
+            cx1, cm1 = self._lin(s, s1, r1 * h)
+            self.ops.append(("axpy", self.XI, [(_X, cx1), (self.MS, cm1)], 0.0, -1))
+            self.model_value(s1, self.MS1, self.XI)
+        cx2, cm2 = self._lin(s, s2, r2 * h)
+        if self.pp:
+            phi_1 = math.expm1(-h)
+            phi_22 = math.expm1(-r2 * h) / (r2 * h) + 1.0
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            a2, at = ns.marginal_alpha(s2), ns.marginal_alpha(t)
+            d2 = r2 / r1 * (a2 * phi_22)                     # + d2 (m1 - m0)
+            e1, e2, e3 = (1.0 / r2) * (at * phi_2), at * phi_2, -at * phi_3
+        else:
+            phi_1 = math.expm1(h)
+            phi_22 = math.expm1(r2 * h) / (r2 * h) - 1.0
+            phi_2 = phi_1 / h - 1.0
+            phi_3 = phi_2 / h - 0.5
+            g2, gt = ns.marginal_std(s2), ns.marginal_std(t)
+            d2 = -r2 / r1 * (g2 * phi_22)
+            e1, e2, e3 = -(1.0 / r2) * (gt * phi_2), -gt * phi_2, -gt * phi_3
+        self.ops.append(("axpy", self.XI, [(_X, cx2), (self.MS, cm2 - d2), (self.MS1, d2)], 0.0, -1))
+        self.model_value(s2, self.MS2, self.XI)
+        cx, cm = self._lin(s, t, h)
+        if self.st == "dpmsolver":
+            self.ops.append(("axpy", dst, [(_X, cx), (self.MS, cm - e1), (self.MS2, e1)], 0.0, -1))
+        else:
+            # D1_0 = (m1 - m0) / r1, D1_1 = (m2 - m0) / r2, D1 = (r2 D1_0 - r1 D1_1) / (r2 - r1), D2 = 2 (D1_1 - D1_0) / (r2 - r1)
+            k0 = (e2 * r2 - 2.0 * e3) / (r2 - r1) / r1       # coefficient of (m1 - m0)
+            k1 = (-e2 * r1 + 2.0 * e3) / (r2 - r1) / r2      # coefficient of (m2 - m0)
+            self.ops.append(("axpy", dst, [(_X, cx), (self.MS, cm - k0 - k1), (self.MS1, k0), (self.MS2, k1)], 0.0, -1))
+
+    def denoise_to_zero(self, t_0):
+        ns = self.ns
+        self.times.append(ns.model_time(t_0))
+        self.ops.append(("eval", ns.model_time(t_0), _X))
+        cx, cr = self.wm.mix(t_0)
+        a, s_ = ns.marginal_alpha(t_0), ns.marginal_std(t_0)
+        cx, cr = (1.0 - s_ * cx) / a, -s_ * cr / a
+        if self.model_type == "x_start":
+            cx, cr = 0.0, 1.0
+        terms = [(_RAW, cr)] if cx == 0.0 else [(_X, cx), (_RAW, cr)]
+        self.ops.append(("axpy", _X, terms, 0.0, -1))
+        if self.thr is not None:
+            self.ops.append(("thresh", _X) + quantile_rank(self.thr[0], self.map_elems) + (float(self.thr[1]),))
+
+
+def build_dpm_singlestep_program(ns, steps, order=2, algorithm_type="dpmsolver", model_type="x_start", skip_type="logSNR",
+                                 method="singlestep", denoise_to_zero=True, solver_type="dpmsolver", t_start=None, t_end=None,
+                                 thresholding=None, map_elems=224 * 384):
+    """DPM_Solver.sample(method='singlestep' | 'singlestep_fixed') (sampler.py:1216-1239); returns (ops, model_times)."""
+    t_0 = 1.0 / ns.total_N if t_end is None else t_end
+    t_T = ns.T if t_start is None else t_start
+    assert t_0 > 0 and t_T > 0
+    if method == "singlestep":
+        orders, K = singlestep_orders(steps, order)
+        if skip_type == "logSNR":
+            outer = dpm_time_steps(ns, skip_type, t_T, t_0, K)
+        else:
+            full = dpm_time_steps(ns, skip_type, t_T, t_0, steps)
+            idx = [0]
+            for o in orders:
+                idx.append(idx[-1] + o)
+            outer = [full[i] for i in idx]
+    elif method == "singlestep_fixed":
+        K = steps // order
+        orders = [order] * K
+        outer = dpm_time_steps(ns, skip_type, t_T, t_0, K)
+    else:
+        raise ValueError("Got wrong method {}".format(method))
+    b = _SinglestepBuilder(ns, algorithm_type, model_type, solver_type, thresholding, map_elems)
+    for step, o in enumerate(orders):
+        s_, t_ = outer[step], outer[step + 1]            # IndexError for order 1 + logSNR, exactly like the reference
+        # the reference round-trips s, t through fp32 (.item() of fp32 tensors) before it spaces the inner steps
+        inner = dpm_time_steps(ns, skip_type, float(np.float32(s_)), float(np.float32(t_)), o)
+        lam = [ns.marginal_lambda(v) for v in inner]
+        h = lam[-1] - lam[0]
+        r1 = None if o <= 1 else (lam[1] - lam[0]) / h
+        r2 = None if o <= 2 else (lam[2] - lam[0]) / h
+        if o == 1:
+            b.first(s_, t_)
+        elif o == 2:
+            b.second(s_, t_, r1)
+        else:
+            b.third(s_, t_, r1, r2)
+    if denoise_to_zero:
+        b.denoise_to_zero(t_0)
+    return b.ops, b.times
+
+
+def _adaptive_error(x_lower, x_higher, x_prev, atol, rtol):
+    """max over the batch of dpm_solver_adaptive's error norm (sampler.py:996-999), computed on the device."""
+    import ctypes
+    from . import _lib
+    from .engine import _bind, _stream
+    lib = _bind(_lib.lib())
+    B = x_lower.shape[0]
+    out = torch.empty(B, dtype=torch.float32, device=x_lower.device)
+    with torch.cuda.device(x_lower.device):
+        rc = lib.dsb_sampler_adaptive_error(_lib.ptr(x_lower), _lib.ptr(x_higher), _lib.ptr(x_prev), B, x_lower.numel() // B,
+                                            float(atol), float(rtol), _lib.ptr(out), _stream())
+    if rc != 0:
+        raise RuntimeError("dsb_sampler_adaptive_error failed (%d)" % rc)
+    return float(out.max().item())
+
+
+def sample_dpm_adaptive(ns, x, model, order=2, algorithm_type="dpmsolver", model_type="x_start", t_T=None, t_0=None,
+                        h_init=0.05, atol=0.0078, rtol=0.05, theta=0.9, t_err=1e-5, solver_type="dpmsolver"):
+    """DPM_Solver.dpm_solver_adaptive (sampler.py:958-1009).  The step-size control is data dependent, so this is a host
+    loop: per trial step one small program (lower- and higher-order update sharing their evaluations) through the fused
+    update / denoiser kernels, the error norm on the device, one scalar read back.  ``model(x, t[B]) -> raw output``.
+    Returns (x_0, nfe)."""
+    if order not in (2, 3):
+        raise ValueError("For adaptive step size solver, order must be 2 or 3, got {}".format(order))
+    t_T = ns.T if t_T is None else t_T
+    t_0 = 1.0 / ns.total_N if t_0 is None else t_0
+    s = t_T
+    lam_s, lam_0 = ns.marginal_lambda(s), ns.marginal_lambda(t_0)
+    h = h_init
+    x = x.to(dtype=torch.float32).contiguous().clone()
+    x_prev = x
+    nfe = 0
+    LO = 6                                                    # buffer of the lower-order iterate
+    while abs(s - t_0) > t_err:
+        t = ns.inverse_lambda(lam_s + h)
+        b = _SinglestepBuilder(ns, algorithm_type, model_type, solver_type)
+        if order == 2:
+            b.first(s, t, dst=LO)
+            b.second(s, t, 0.5, have_model_s=True, dst=7)
+        else:
+            b.second(s, t, 1.0 / 3.0, dst=LO)
+            b.third(s, t, 1.0 / 3.0, 2.0 / 3.0, have_model_s=True, have_model_s1=True, dst=7)
+        bufs = run_program_generic(b.ops, x, model, return_buffers=True)
+        x_lower, x_higher = bufs[LO], bufs[7]
+        E = _adaptive_error(x_lower, x_higher, x_prev, atol, rtol)
+        if E <= 1.0:
+            x, s, x_prev = x_higher, t, x_lower
+            lam_s = ns.marginal_lambda(s)
+        h = min(theta * h * float(np.float32(float(np.float32(E)) ** (-1.0 / order))), lam_0 - lam_s)
+        nfe += order
+    return x, nfe
+
+
 def build_ddim_program(tables, timesteps, eta=0.0, training_target="x0"):
     """DiffusionTrainer.sample_ddim (diffusion_trainer.py:439-480) as EVAL/AXPY ops.
     Returns (ops, n_noise_slabs); noise slab k belongs to the k-th non-final step."""
@@ -461,28 +698,29 @@ def _correct(kind, buf, args):
     return buf
 
 
-def run_program_generic(ops, x, model, noise=None):
+def run_program_generic(ops, x, model, noise=None, return_buffers=False):
     """Executes a sampler program with an arbitrary denoiser callable ``model(x, t[B]) -> tensor`` (one fused
     update launch per AXPY).  The SalUNetB200 fast path runs the same ops inside dsb_sample instead."""
     bufs = {_X: x}
     for op in ops:
         if op[0] == "eval":
             t = torch.full((x.shape[0],), op[1], dtype=torch.float32, device=x.device)
-            bufs[_RAW] = model(bufs[_X], t)
+            bufs[_RAW] = model(bufs[op[2] if len(op) > 2 else _X], t)
         elif op[0] in ("clamp", "thresh"):
             bufs[op[1]] = _correct(op[0], bufs[op[1]], op[2:])
         else:
             _, dst, terms, ncoef, nidx = op
             nz = noise[nidx] if (nidx >= 0 and noise is not None) else None
             bufs[dst] = _axpy([c for _, c in terms], [bufs[s] for s, _ in terms], nz, ncoef)
-    return bufs[_X]
+    return bufs if return_buffers else bufs[_X]
 
 
 # ============================================================================================ DPM_Solver
 
 
 class DPM_Solver:
-    """sampler.py:336-1247, multistep path.  ``model_fn`` is what model_wrapper returned."""
+    """sampler.py:336-1247: multistep, singlestep / singlestep_fixed (compiled to EVAL/AXPY programs) and adaptive (host
+    loop).  ``model_fn`` is what model_wrapper returned."""
 
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None,
                  correcting_xt_fn=None, thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
@@ -501,17 +739,33 @@ class DPM_Solver:
     def sample(self, x, img=None, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform",
                method="multistep", lower_order_final=True, denoise_to_zero=False, solver_type="dpmsolver",
                atol=0.0078, rtol=0.05, return_intermediate=False, use_graph=True):
-        if method != "multistep":
-            # the reference's singlestep / adaptive branches drop the conditioning argument (sampler.py:573-635)
-            raise NotImplementedError("method=%r: only 'multistep' forwards the conditioning in the reference" % method)
         if return_intermediate:
             raise NotImplementedError("return_intermediate is not supported by the fused loop")
         ns = self.noise_schedule
-        ops, _ = build_dpm_program(ns, steps, order, self.algorithm_type, self.wrapped.model_type, skip_type,
-                                   lower_order_final, denoise_to_zero, solver_type, t_start, t_end,
-                                   thresholding=self.thresholding, map_elems=x[0].numel())
         model = self.wrapped.model
         kwargs = self.wrapped.model_kwargs
+        if method == "adaptive":
+            # data-dependent step sizes: host loop around the same kernels (sampler.py:958-1009,1171-1172).  Unlike the
+            # reference, whose adaptive branch never forwards ``img`` to the network, the conditioning is applied.
+            if self.thresholding is not None:
+                raise NotImplementedError("dynamic thresholding with the adaptive solver is outside the hot path")
+            xs, _ = sample_dpm_adaptive(ns, x, lambda x_, t_: model(x_, t_, img, **kwargs), order, self.algorithm_type,
+                                        self.wrapped.model_type, t_start, t_end, atol=atol, rtol=rtol, solver_type=solver_type)
+            if denoise_to_zero:
+                b = _SinglestepBuilder(ns, self.algorithm_type, self.wrapped.model_type, solver_type)
+                b.denoise_to_zero(1.0 / ns.total_N if t_end is None else t_end)
+                xs = run_program_generic(b.ops, xs, lambda x_, t_: model(x_, t_, img, **kwargs))
+            return xs
+        if method == "multistep":
+            ops, _ = build_dpm_program(ns, steps, order, self.algorithm_type, self.wrapped.model_type, skip_type,
+                                       lower_order_final, denoise_to_zero, solver_type, t_start, t_end,
+                                       thresholding=self.thresholding, map_elems=x[0].numel())
+        elif method in ("singlestep", "singlestep_fixed"):
+            ops, _ = build_dpm_singlestep_program(ns, steps, order, self.algorithm_type, self.wrapped.model_type, skip_type,
+                                                  method, denoise_to_zero, solver_type, t_start, t_end,
+                                                  thresholding=self.thresholding, map_elems=x[0].numel())
+        else:
+            raise ValueError("Got wrong method {}".format(method))
         fused = getattr(model, "_dsb_fused_sample", None)
         if fused is not None:
             return fused(ops, x, img, kwargs, use_graph=use_graph)

@@ -87,7 +87,8 @@ int dsb_sampler_update(dsb_handle* h, const float* coef, const float* const* in,
 
 /* ---- whole sampling loop as a small program over device buffers -------------------------------------------
  * Buffer ids: 0 = x (the state, in/out), 1 = raw network output of the last EVAL, 2..7 = scratch (model history).
- * DSB_OP_EVAL : buf[1] = SalUNet(buf[0], t)                      (t = op.t for every clip)
+ * DSB_OP_EVAL : buf[1] = SalUNet(buf[src[0]], t)                 (t = op.t for every clip; src[0] = 0 unless the solver
+ *               evaluates the network at an intermediate point, as the singlestep DPM-Solver updates do)
  * DSB_OP_AXPY : buf[dst] = sum_k coef[k] * buf[src[k]] + noise_coef * noise[noise_index]
  */
 #define DSB_OP_EVAL 0
@@ -126,6 +127,10 @@ int dsb_sample(dsb_handle* h, const dsb_sampler_desc* desc, float* x_inout, int 
  * (models/dpm_solver/sampler.py:417-426; x: [B][n], k / w = floor / frac of torch.quantile's fp32 rank p*(n-1)) */
 int dsb_sampler_clamp(float* x, int64_t n, float lo, float hi, void* stream);
 int dsb_sampler_dynamic_threshold(float* x, int B, int64_t n, int k, float w, float max_val, void* stream);
+/* error norm of DPM_Solver.dpm_solver_adaptive's step-size control (models/dpm_solver/sampler.py:996-999), per sample:
+ * out[b] = sqrt(mean(((x_higher - x_lower) / max(atol, rtol * max(|x_lower|, |x_prev|)))^2)); all device fp32 [B][n] */
+int dsb_sampler_adaptive_error(const float* x_lower, const float* x_higher, const float* x_prev, int B, int64_t n, float atol,
+                               float rtol, float* out, void* stream);
 
 /* output side of the loop: clamp(x,0,1) = inverse_data_transform (datasets/__init__.py:26-35, cfgs/diffusion.yml data.*)
  * and the per-map min-max -> uint8 of normalize_data (util/utils.py:11-16).  x: device fp32 [B][pixels_per_map];
@@ -158,6 +163,10 @@ int64_t dsb_condition_launch_count(const dsb_handle* h);
  * reference graph; 0 for memory-bound kernels), bytes[i] = algorithmic bytes where stated.  Returns #launches. */
 int dsb_profile_denoise(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream, float* ms,
                         double* flops, double* bytes, int cap);
+/* the same evaluation as it really runs (side streams, event joins): start / end of every launch in ms since the first,
+ * and the stream it ran on (0 = caller's).  Names through dsb_profile_name.  Returns #launches. */
+int dsb_profile_timeline(dsb_handle* h, const float* x, const float* t, float* out, int B, void* stream, float* start_ms,
+                         float* end_ms, int* stream_idx, int cap);
 const char* dsb_profile_name(const dsb_handle* h, int i);
 
 /* ---- debugging / parity taps (read-only views of the workspace after dsb_denoise) ------------------------- */

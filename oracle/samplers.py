@@ -195,9 +195,10 @@ class NoiseScheduleDiscrete:
         return _interp(log_alpha, torch.flip(self.log_alpha_array, [0]), torch.flip(self.t_array, [0]))
 
 
-def dpm_time_steps(ns, steps, skip_type="logSNR"):
-    """sampler.py:454-481."""
-    t_T, t_0 = ns.T, 1.0 / ns.total_N
+def dpm_time_steps(ns, steps, skip_type="logSNR", t_T=None, t_0=None):
+    """sampler.py:454-481 (t_T / t_0: python floats, default the whole range)."""
+    t_T = ns.T if t_T is None else t_T
+    t_0 = 1.0 / ns.total_N if t_0 is None else t_0
     if skip_type == "logSNR":
         lam_T = ns.lam(torch.tensor(t_T))
         lam_0 = ns.lam(torch.tensor(t_0))
@@ -306,6 +307,238 @@ def sample_dpm(model, x, betas=None, steps=9, order=2, algorithm_type="dpmsolver
     if return_model_times:
         return x, model_times
     return x
+
+
+def _dpm_model_fns(model, ns, n, algorithm_type, model_type, model_times):
+    """model_wrapper(uncond) + DPM_Solver.{noise_prediction_fn, data_prediction_fn, model_fn} (sampler.py:282-298,428-452)."""
+    def noise_pred(x, t):
+        t_in = (t - 1.0 / ns.total_N) * 1000.0
+        model_times.append(float(t_in))
+        out = model(x, t_in.reshape(1).expand(n))
+        if model_type == "noise":
+            return out
+        if model_type == "x_start":
+            return (x - ns.alpha(t) * out) / ns.sigma(t)
+        raise ValueError(model_type)
+
+    def data_pred(x, t):
+        return (x - ns.sigma(t) * noise_pred(x, t)) / ns.alpha(t)
+
+    model_fn = data_pred if algorithm_type == "dpmsolver++" else noise_pred
+    return noise_pred, data_pred, model_fn
+
+
+class _Singlestep:
+    """dpm_solver_first_update / singlestep_dpm_solver_second_update / _third_update (sampler.py:548-795).  The reference
+    calls ``self.model_fn(x, s)`` WITHOUT the conditioning there (:573,585,630,635,...); ``model_fn`` here is a closure that
+    already carries it, which is the only deviation ("singlestep/adaptive paths with conditioning")."""
+
+    def __init__(self, ns, model_fn, algorithm_type, solver_type):
+        self.ns, self.model_fn, self.pp, self.solver_type = ns, model_fn, algorithm_type == "dpmsolver++", solver_type
+
+    def first(self, x, s, t, model_s=None, return_intermediate=False):
+        ns = self.ns
+        h = ns.lam(t) - ns.lam(s)
+        la_s, la_t = ns.log_alpha(s), ns.log_alpha(t)
+        sig_s, sig_t = ns.sigma(s), ns.sigma(t)
+        alpha_t = torch.exp(la_t)
+        if model_s is None:
+            model_s = self.model_fn(x, s)
+        if self.pp:
+            x_t = sig_t / sig_s * x - alpha_t * torch.expm1(-h) * model_s
+        else:
+            x_t = torch.exp(la_t - la_s) * x - (sig_t * torch.expm1(h)) * model_s
+        return (x_t, {"model_s": model_s}) if return_intermediate else x_t
+
+    def second(self, x, s, t, r1=0.5, model_s=None, return_intermediate=False):
+        ns, st = self.ns, self.solver_type
+        if r1 is None:
+            r1 = 0.5
+        lam_s, lam_t = ns.lam(s), ns.lam(t)
+        h = lam_t - lam_s
+        s1 = ns.inverse_lambda(lam_s + r1 * h)
+        la_s, la_s1, la_t = ns.log_alpha(s), ns.log_alpha(s1), ns.log_alpha(t)
+        sig_s, sig_s1, sig_t = ns.sigma(s), ns.sigma(s1), ns.sigma(t)
+        alpha_s1, alpha_t = torch.exp(la_s1), torch.exp(la_t)
+        if model_s is None:
+            model_s = self.model_fn(x, s)
+        if self.pp:
+            phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
+            x_s1 = (sig_s1 / sig_s) * x - (alpha_s1 * phi_11) * model_s
+            model_s1 = self.model_fn(x_s1, s1)
+            if st == "dpmsolver":
+                x_t = (sig_t / sig_s) * x - (alpha_t * phi_1) * model_s - (0.5 / r1) * (alpha_t * phi_1) * (model_s1 - model_s)
+            else:
+                x_t = (sig_t / sig_s) * x - (alpha_t * phi_1) * model_s + (1.0 / r1) * (alpha_t * (phi_1 / h + 1.0)) * (model_s1 - model_s)
+        else:
+            phi_11, phi_1 = torch.expm1(r1 * h), torch.expm1(h)
+            x_s1 = torch.exp(la_s1 - la_s) * x - (sig_s1 * phi_11) * model_s
+            model_s1 = self.model_fn(x_s1, s1)
+            if st == "dpmsolver":
+                x_t = torch.exp(la_t - la_s) * x - (sig_t * phi_1) * model_s - (0.5 / r1) * (sig_t * phi_1) * (model_s1 - model_s)
+            else:
+                x_t = torch.exp(la_t - la_s) * x - (sig_t * phi_1) * model_s - (1.0 / r1) * (sig_t * (phi_1 / h - 1.0)) * (model_s1 - model_s)
+        return (x_t, {"model_s": model_s, "model_s1": model_s1}) if return_intermediate else x_t
+
+    def third(self, x, s, t, r1=1.0 / 3.0, r2=2.0 / 3.0, model_s=None, model_s1=None, return_intermediate=False):
+        ns, st = self.ns, self.solver_type
+        if r1 is None:
+            r1 = 1.0 / 3.0
+        if r2 is None:
+            r2 = 2.0 / 3.0
+        lam_s, lam_t = ns.lam(s), ns.lam(t)
+        h = lam_t - lam_s
+        s1, s2 = ns.inverse_lambda(lam_s + r1 * h), ns.inverse_lambda(lam_s + r2 * h)
+        la_s, la_s1, la_s2, la_t = ns.log_alpha(s), ns.log_alpha(s1), ns.log_alpha(s2), ns.log_alpha(t)
+        sig_s, sig_s1, sig_s2, sig_t = ns.sigma(s), ns.sigma(s1), ns.sigma(s2), ns.sigma(t)
+        alpha_s1, alpha_s2, alpha_t = torch.exp(la_s1), torch.exp(la_s2), torch.exp(la_t)
+        if model_s is None:
+            model_s = self.model_fn(x, s)
+        if self.pp:
+            phi_11, phi_12, phi_1 = torch.expm1(-r1 * h), torch.expm1(-r2 * h), torch.expm1(-h)
+            phi_22 = torch.expm1(-r2 * h) / (r2 * h) + 1.0
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            if model_s1 is None:
+                x_s1 = (sig_s1 / sig_s) * x - (alpha_s1 * phi_11) * model_s
+                model_s1 = self.model_fn(x_s1, s1)
+            x_s2 = (sig_s2 / sig_s) * x - (alpha_s2 * phi_12) * model_s + r2 / r1 * (alpha_s2 * phi_22) * (model_s1 - model_s)
+            model_s2 = self.model_fn(x_s2, s2)
+            if st == "dpmsolver":
+                x_t = (sig_t / sig_s) * x - (alpha_t * phi_1) * model_s + (1.0 / r2) * (alpha_t * phi_2) * (model_s2 - model_s)
+            else:
+                D1_0 = (1.0 / r1) * (model_s1 - model_s)
+                D1_1 = (1.0 / r2) * (model_s2 - model_s)
+                D1 = (r2 * D1_0 - r1 * D1_1) / (r2 - r1)
+                D2 = 2.0 * (D1_1 - D1_0) / (r2 - r1)
+                x_t = (sig_t / sig_s) * x - (alpha_t * phi_1) * model_s + (alpha_t * phi_2) * D1 - (alpha_t * phi_3) * D2
+        else:
+            phi_11, phi_12, phi_1 = torch.expm1(r1 * h), torch.expm1(r2 * h), torch.expm1(h)
+            phi_22 = torch.expm1(r2 * h) / (r2 * h) - 1.0
+            phi_2 = phi_1 / h - 1.0
+            phi_3 = phi_2 / h - 0.5
+            if model_s1 is None:
+                x_s1 = torch.exp(la_s1 - la_s) * x - (sig_s1 * phi_11) * model_s
+                model_s1 = self.model_fn(x_s1, s1)
+            x_s2 = torch.exp(la_s2 - la_s) * x - (sig_s2 * phi_12) * model_s - r2 / r1 * (sig_s2 * phi_22) * (model_s1 - model_s)
+            model_s2 = self.model_fn(x_s2, s2)
+            if st == "dpmsolver":
+                x_t = torch.exp(la_t - la_s) * x - (sig_t * phi_1) * model_s - (1.0 / r2) * (sig_t * phi_2) * (model_s2 - model_s)
+            else:
+                D1_0 = (1.0 / r1) * (model_s1 - model_s)
+                D1_1 = (1.0 / r2) * (model_s2 - model_s)
+                D1 = (r2 * D1_0 - r1 * D1_1) / (r2 - r1)
+                D2 = 2.0 * (D1_1 - D1_0) / (r2 - r1)
+                x_t = torch.exp(la_t - la_s) * x - (sig_t * phi_1) * model_s - (sig_t * phi_2) * D1 - (sig_t * phi_3) * D2
+        if return_intermediate:
+            return x_t, {"model_s": model_s, "model_s1": model_s1, "model_s2": model_s2}
+        return x_t
+
+
+def singlestep_orders(steps, order):
+    """get_orders_and_timesteps_for_singlestep_solver (sampler.py:514-536): (orders, K)."""
+    if order == 3:
+        K = steps // 3 + 1
+        if steps % 3 == 0:
+            return [3] * (K - 2) + [2, 1], K
+        if steps % 3 == 1:
+            return [3] * (K - 1) + [1], K
+        return [3] * (K - 1) + [2], K
+    if order == 2:
+        if steps % 2 == 0:
+            return [2] * (steps // 2), steps // 2
+        return [2] * (steps // 2) + [1], steps // 2 + 1
+    if order == 1:
+        return [1] * steps, 1
+    raise ValueError("'order' must be '1' or '2' or '3'.")
+
+
+def sample_dpm_singlestep(model, x, betas=None, steps=9, order=2, algorithm_type="dpmsolver", model_type="x_start",
+                          skip_type="logSNR", method="singlestep", denoise_to_zero=True, solver_type="dpmsolver",
+                          return_model_times=False):
+    """DPM_Solver.sample(method='singlestep' | 'singlestep_fixed') (sampler.py:1216-1239)."""
+    betas = betas_fp32() if betas is None else betas
+    ns = NoiseScheduleDiscrete(betas)
+    model_times = []
+    _, data_pred, model_fn = _dpm_model_fns(model, ns, x.shape[0], algorithm_type, model_type, model_times)
+    ss = _Singlestep(ns, model_fn, algorithm_type, solver_type)
+    if method == "singlestep":
+        orders, K = singlestep_orders(steps, order)
+        if skip_type == "logSNR":
+            outer = dpm_time_steps(ns, K, skip_type)
+        else:
+            full = dpm_time_steps(ns, steps, skip_type)
+            idx = [0]
+            for o in orders:
+                idx.append(idx[-1] + o)
+            outer = [full[i] for i in idx]
+    elif method == "singlestep_fixed":
+        K = steps // order
+        orders = [order] * K
+        outer = dpm_time_steps(ns, K, skip_type)
+    else:
+        raise ValueError(method)
+    for step, o in enumerate(orders):
+        s_, t_ = outer[step], outer[step + 1]
+        inner = dpm_time_steps(ns, o, skip_type, t_T=float(s_), t_0=float(t_))
+        lam_inner = [ns.lam(torch.as_tensor(v, dtype=torch.float32)) for v in inner]
+        h = lam_inner[-1] - lam_inner[0]
+        r1 = None if o <= 1 else (lam_inner[1] - lam_inner[0]) / h
+        r2 = None if o <= 2 else (lam_inner[2] - lam_inner[0]) / h
+        if o == 1:
+            x = ss.first(x, s_, t_)
+        elif o == 2:
+            x = ss.second(x, s_, t_, r1=r1)
+        else:
+            x = ss.third(x, s_, t_, r1=r1, r2=r2)
+    if denoise_to_zero:
+        x = data_pred(x, torch.ones(()) * (1.0 / ns.total_N))
+    return (x, model_times) if return_model_times else x
+
+
+def sample_dpm_adaptive(model, x, betas=None, order=2, algorithm_type="dpmsolver", model_type="x_start", h_init=0.05,
+                        atol=0.0078, rtol=0.05, theta=0.9, t_err=1e-5, solver_type="dpmsolver", denoise_to_zero=False,
+                        return_model_times=False):
+    """DPM_Solver.sample(method='adaptive') -> dpm_solver_adaptive (sampler.py:958-1009,1171-1172)."""
+    betas = betas_fp32() if betas is None else betas
+    ns = NoiseScheduleDiscrete(betas)
+    model_times = []
+    _, data_pred, model_fn = _dpm_model_fns(model, ns, x.shape[0], algorithm_type, model_type, model_times)
+    ss = _Singlestep(ns, model_fn, algorithm_type, solver_type)
+    t_T, t_0 = ns.T, 1.0 / ns.total_N
+    s = t_T * torch.ones((1,))
+    lam_s = ns.lam(s)
+    lam_0 = ns.lam(t_0 * torch.ones_like(s))
+    h = h_init * torch.ones_like(s)
+    x_prev = x
+    nfe = 0
+    if order == 2:
+        r1 = 0.5
+        lower = lambda x_, s_, t_: ss.first(x_, s_, t_, return_intermediate=True)
+        higher = lambda x_, s_, t_, **kw: ss.second(x_, s_, t_, r1=r1, **kw)
+    elif order == 3:
+        r1, r2 = 1.0 / 3.0, 2.0 / 3.0
+        lower = lambda x_, s_, t_: ss.second(x_, s_, t_, r1=r1, return_intermediate=True)
+        higher = lambda x_, s_, t_, **kw: ss.third(x_, s_, t_, r1=r1, r2=r2, **kw)
+    else:
+        raise ValueError("For adaptive step size solver, order must be 2 or 3, got {}".format(order))
+    while torch.abs(s - t_0).mean() > t_err:
+        t = ns.inverse_lambda(lam_s + h)
+        x_lower, kw = lower(x, s, t)
+        x_higher = higher(x, s, t, **kw)
+        delta = torch.max(torch.ones_like(x) * atol, rtol * torch.max(torch.abs(x_lower), torch.abs(x_prev)))
+        norm_fn = lambda v: torch.sqrt(torch.square(v.reshape((v.shape[0], -1))).mean(dim=-1, keepdim=True))
+        E = norm_fn((x_higher - x_lower) / delta).max()
+        if torch.all(E <= 1.0):
+            x = x_higher
+            s = t
+            x_prev = x_lower
+            lam_s = ns.lam(s)
+        h = torch.min(theta * h * torch.float_power(E, -1.0 / order).float(), lam_0 - lam_s)
+        nfe += order
+    if denoise_to_zero:
+        x = data_pred(x, torch.ones(()) * t_0)
+    return (x, model_times, nfe) if return_model_times else x
 
 
 # ----------------------------------------------------------------------------- post-processing

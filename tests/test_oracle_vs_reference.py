@@ -194,6 +194,47 @@ def test_dynamic_thresholding_bit_exact_on_toy_net(algo):
     assert torch.equal(ref, mine)
 
 
+@pytest.mark.parametrize("algo", ["dpmsolver", "dpmsolver++"])
+@pytest.mark.parametrize("method,order,steps,skip,solver_type", [
+    ("singlestep", 1, 4, "time_uniform", "dpmsolver"), ("singlestep", 2, 6, "logSNR", "dpmsolver"),
+    ("singlestep", 2, 7, "logSNR", "taylor"), ("singlestep", 3, 9, "logSNR", "dpmsolver"),
+    ("singlestep", 3, 10, "time_uniform", "dpmsolver"), ("singlestep", 3, 11, "logSNR", "taylor"),
+    ("singlestep", 2, 5, "time_quadratic", "dpmsolver"), ("singlestep_fixed", 2, 6, "logSNR", "dpmsolver"),
+    ("singlestep_fixed", 3, 9, "time_uniform", "dpmsolver")])
+def test_dpm_singlestep_bit_exact_on_toy_net(algo, method, order, steps, skip, solver_type):
+    """DPM_Solver.sample(method='singlestep' / 'singlestep_fixed') (sampler.py:573-795,1216-1239).
+    The toy network ignores the conditioning, which the reference's singlestep branch does not forward."""
+    ns = ref_loader.load()
+    betas = samplers.betas_fp32()
+    x = torch.randn(1, 1, 16, 24, generator=torch.Generator().manual_seed(5))
+    nsv = ns.NoiseScheduleVP(schedule="discrete", betas=betas)
+    for mtype in ("x_start", "noise"):
+        mf = ns.model_wrapper(lambda x_, t_, img, **kw: _toy(x_, t_), nsv, model_type=mtype, model_kwargs={}, guidance_type="uncond")
+        ref = ns.DPM_Solver(mf, nsv, algorithm_type=algo).sample(x, None, steps=steps, order=order, skip_type=skip, method=method,
+                                                                  denoise_to_zero=True, solver_type=solver_type)
+        mine = samplers.sample_dpm_singlestep(_toy, x, betas, steps=steps, order=order, algorithm_type=algo, model_type=mtype,
+                                              skip_type=skip, method=method, denoise_to_zero=True, solver_type=solver_type)
+        assert torch.equal(ref, mine), (mtype, (ref - mine).abs().max().item())
+
+
+@pytest.mark.parametrize("algo", ["dpmsolver", "dpmsolver++"])
+@pytest.mark.parametrize("order,solver_type", [(2, "dpmsolver"), (3, "dpmsolver"), (3, "taylor")])
+def test_dpm_adaptive_bit_exact_on_toy_net(algo, order, solver_type):
+    """DPM_Solver.sample(method='adaptive') -> dpm_solver_adaptive (sampler.py:958-1009): same accepted / rejected steps,
+    same iterate, bit for bit."""
+    ns = ref_loader.load()
+    betas = samplers.betas_fp32()
+    x = torch.randn(2, 1, 16, 24, generator=torch.Generator().manual_seed(6))
+    nsv = ns.NoiseScheduleVP(schedule="discrete", betas=betas)
+    mf = ns.model_wrapper(lambda x_, t_, img, **kw: _toy(x_, t_), nsv, model_type="noise", model_kwargs={}, guidance_type="uncond")
+    ref = ns.DPM_Solver(mf, nsv, algorithm_type=algo).sample(x, None, order=order, method="adaptive", denoise_to_zero=False,
+                                                              solver_type=solver_type, atol=0.0078, rtol=0.05)
+    mine, times, nfe = samplers.sample_dpm_adaptive(_toy, x, betas, order=order, algorithm_type=algo, model_type="noise",
+                                                    solver_type=solver_type, return_model_times=True)
+    assert torch.equal(ref, mine), (ref - mine).abs().max().item()
+    assert nfe >= order and len(times) > order
+
+
 def test_ddpm_steps_bit_exact_on_toy_net(monkeypatch):
     """util/denoising.py:39-67.  The reference hard-codes .to('cuda') / .to('cpu') hops (:48,55,64); they are made
     no-ops for this CPU run (device plumbing only, no arithmetic)."""

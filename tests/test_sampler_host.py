@@ -24,7 +24,7 @@ def interpret(ops, x, net, noise=None):
     for op in ops:
         if op[0] == "eval":
             t = torch.full((x.shape[0],), op[1], dtype=torch.float32)
-            bufs[1] = net(bufs[0].float(), t).double()
+            bufs[1] = net(bufs[op[2] if len(op) > 2 else 0].float(), t).double()
         elif op[0] == "clamp":
             bufs[op[1]] = bufs[op[1]].clamp(op[2], op[3])
         elif op[0] == "thresh":
@@ -88,6 +88,29 @@ def test_dpm_program_matches_oracle(algo, mtype, order, steps, lof):
     assert (got - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("algo", ["dpmsolver", "dpmsolver++"])
+@pytest.mark.parametrize("mtype", ["x_start", "noise"])
+@pytest.mark.parametrize("method,order,steps,skip,solver_type", [
+    ("singlestep", 1, 4, "time_uniform", "dpmsolver"), ("singlestep", 2, 6, "logSNR", "dpmsolver"),
+    ("singlestep", 2, 7, "logSNR", "taylor"), ("singlestep", 3, 9, "logSNR", "dpmsolver"),
+    ("singlestep", 3, 10, "time_uniform", "dpmsolver"), ("singlestep", 3, 11, "logSNR", "taylor"),
+    ("singlestep", 2, 5, "time_quadratic", "dpmsolver"), ("singlestep_fixed", 3, 9, "logSNR", "dpmsolver")])
+def test_dpm_singlestep_program_matches_oracle(algo, mtype, method, order, steps, skip, solver_type):
+    """the singlestep solvers as EVAL/AXPY programs (intermediate evaluations read buffer 5)."""
+    betas = O.betas_fp32()
+    x = torch.randn(1, 1, 8, 8, generator=torch.Generator().manual_seed(13))
+    ns = S.NoiseScheduleVP("discrete", betas=betas)
+    ops, times = S.build_dpm_singlestep_program(ns, steps, order, algo, mtype, skip, method, True, solver_type)
+    ref, rtimes = O.sample_dpm_singlestep(_toy, x, betas, steps=steps, order=order, algorithm_type=algo, model_type=mtype,
+                                          skip_type=skip, method=method, denoise_to_zero=True, solver_type=solver_type,
+                                          return_model_times=True)
+    assert len(times) == len(rtimes)
+    for a, b in zip(times, rtimes):
+        assert abs(a - b) < 0.06
+    tol = 2e-4 * max(1.0, ref.abs().max().item())
+    assert (interpret(ops, x, _toy) - ref).abs().max().item() < tol
+
+
 @pytest.mark.parametrize("solver_type", ["dpmsolver", "taylor"])
 def test_dpm_program_taylor(solver_type):
     betas = O.betas_fp32()
@@ -119,8 +142,13 @@ def test_unsupported_paths_fail_loudly():
     with pytest.raises(NotImplementedError):
         S.model_wrapper(lambda *a: None, ns, guidance_type="classifier")
     mf = S.model_wrapper(lambda *a: None, ns, model_type="noise")
+    with pytest.raises(ValueError):
+        S.DPM_Solver(mf, ns).sample(torch.zeros(1, 1, 8, 8), method="no_such_method")
     with pytest.raises(NotImplementedError):
-        S.DPM_Solver(mf, ns).sample(torch.zeros(1, 1, 8, 8), method="singlestep")
+        S.DPM_Solver(mf, ns).sample(torch.zeros(1, 1, 8, 8), method="singlestep", return_intermediate=True)
+    with pytest.raises(IndexError):
+        # the reference's singlestep order 1 with logSNR spacing indexes past its K = 1 outer steps (sampler.py:536-540,1224)
+        S.build_dpm_singlestep_program(ns, 4, 1, skip_type="logSNR")
     with pytest.raises(AssertionError):
         S.build_dpm_program(ns, 1, 2)           # steps >= order (sampler.py:1174)
     with pytest.raises(RuntimeError):

@@ -256,3 +256,60 @@ def test_ddpm_steps_api():
     assert len(xs) == 5 and len(x0s) == 4
     for a, r in zip(xs + x0s, rxs + rx0):
         assert (a.cpu() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.parametrize("algo,order,steps", [("dpmsolver", 2, 4), ("dpmsolver++", 3, 6)])
+def test_dpm_singlestep_with_conditioning(nets, algo, order, steps):
+    """DPM_Solver.sample(method='singlestep') (sampler.py:573-795,1216-1239) in the fused loop, with the
+    conditioning forwarded to every (also the intermediate) network evaluation, against the fp32 oracle."""
+    from diff_sal_b200 import sampler as S
+    from oracle import salunet, samplers as O
+    net = nets("wide", True)
+    x, feats, aud = inputs(1, True)
+    ns = S.NoiseScheduleVP("discrete", betas=O.betas_fp32())
+    mf = S.model_wrapper(net, ns, model_type="x_start", model_kwargs={"audio_feat_list": aud}, guidance_type="uncond")
+    y = S.DPM_Solver(mf, ns, algorithm_type=algo).sample(x, feats, steps=steps, order=order, skip_type="logSNR",
+                                                        method="singlestep", denoise_to_zero=True).cpu()
+    sd = synth.make_state_dict("wide")
+    xc, fc, ac = synth.make_inputs(1, audio=True)
+    ref = O.sample_dpm_singlestep(lambda x_, t_: salunet.forward(sd, x_, t_, fc, ac), xc, steps=steps, order=order,
+                                  algorithm_type=algo, model_type="x_start", skip_type="logSNR", method="singlestep")
+    assert (minmax(y) - minmax(ref)).abs().max().item() <= TOL
+    # graph replay == eager for programs with intermediate evaluations
+    y2 = S.DPM_Solver(mf, ns, algorithm_type=algo).sample(x, feats, steps=steps, order=order, skip_type="logSNR",
+                                                         method="singlestep", denoise_to_zero=True, use_graph=False).cpu()
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("algo,order", [("dpmsolver", 2), ("dpmsolver++", 3)])
+def test_dpm_adaptive_on_toy_net(algo, order):
+    """DPM_Solver.sample(method='adaptive') (sampler.py:958-1009): host-driven step-size control over the fused update
+    kernels and the device error norm; same accepted / rejected steps (NFE) and the same iterate as the fp32 oracle."""
+    from diff_sal_b200 import sampler as S
+    from oracle import samplers as O
+    toy = lambda x_, t_: torch.tanh(0.7 * x_ + 0.001 * t_.float()[:, None, None, None]) * 0.5 + 0.1 * torch.roll(x_, 1, -1)
+    x = torch.randn(2, 1, 16, 24, generator=torch.Generator().manual_seed(6))
+    ns = S.NoiseScheduleVP("discrete", betas=O.betas_fp32())
+    mf = S.model_wrapper(lambda x_, t_, img, **kw: toy(x_, t_), ns, model_type="noise", model_kwargs={}, guidance_type="uncond")
+    y = S.DPM_Solver(mf, ns, algorithm_type=algo).sample(x.cuda(), None, order=order, method="adaptive",
+                                                        denoise_to_zero=False).cpu()
+    ref, times, nfe = O.sample_dpm_adaptive(toy, x, order=order, algorithm_type=algo, model_type="noise", return_model_times=True)
+    _, got_nfe = S.sample_dpm_adaptive(ns, x.cuda(), lambda x_, t_: toy(x_, t_), order, algo, "noise")
+    assert got_nfe == nfe
+    assert (y - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_dpm_adaptive_with_the_conditioned_denoiser(nets):
+    """The adaptive solver around SalUNetB200 (the reference's own adaptive branch cannot run a conditioned SalUNet: it
+    never passes ``img``): finite, in range, and -- with an x0 network -- close to the multistep solution."""
+    from diff_sal_b200 import sampler as S
+    from oracle import samplers as O
+    net = nets("wide", True)
+    x, feats, aud = inputs(1, True)
+    ns = S.NoiseScheduleVP("discrete", betas=O.betas_fp32())
+    mf = S.model_wrapper(net, ns, model_type="x_start", model_kwargs={"audio_feat_list": aud}, guidance_type="uncond")
+    solver = S.DPM_Solver(mf, ns, algorithm_type="dpmsolver++")
+    ya = solver.sample(x, feats, order=2, method="adaptive", denoise_to_zero=True, atol=0.05, rtol=0.2).cpu()
+    ym = solver.sample(x, feats, steps=9, order=2, skip_type="logSNR", method="multistep", denoise_to_zero=True).cpu()
+    assert torch.isfinite(ya).all() and ya.min().item() >= 0.0 and ya.max().item() <= 1.0
+    assert (minmax(ya) - minmax(ym)).abs().max().item() <= 5e-2
