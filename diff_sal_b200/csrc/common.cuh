@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -170,6 +171,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 __device__ __forceinline__ uint32_t umma_idesc_bf16_m256(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
+// A / B format bits of the kind::f16 instruction descriptor: 1 = bf16 (above), 0 = fp16
+constexpr uint32_t kIdescAbBf16 = (1u << 7) | (1u << 10);
 
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -279,6 +282,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float erf_abs = fmaf(-p * t, e, 1.0f);           // erf(|z|)
     const float hx = 0.5f * x;
     return fmaf(copysignf(erf_abs, x), hx, hx);             // 0.5 x (1 + erf(z))
+}
+// two fp16 values (saturated to the finite range) in one 32-bit word: operands of the GEMMs that run in kind::f16 with
+// fp16 inputs (GemmParams::ab_f16) -- same tensor-core rate as bf16, three more mantissa bits
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
+    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

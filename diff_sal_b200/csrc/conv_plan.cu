@@ -203,6 +203,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
 
     p.scale = op.scale; p.shift = op.shift; p.rowbias = op.rowbias; p.residual = op.residual;
     p.act = op.act;
+    p.ab_f16 = op.ab_f16;
     p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
     p.ldo = op.ldo ? op.ldo : op.N;
     p.out_fmul = op.out_fmul ? op.out_fmul : 1;

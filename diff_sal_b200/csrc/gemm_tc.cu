@@ -168,7 +168,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         // lane issues.  Descriptors are base + constant offsets: the issue loop must stay far shorter than the MMA
         // time of a K block (192 cycles at N = 96), or the tensor pipe starves on instruction issue.
         if (rank == 0) {                                    // in a pair only the leader issues
-            const uint32_t idesc = two ? umma_idesc_bf16_m256((uint32_t)p.bn) : umma_idesc_bf16((uint32_t)p.bn);
+            const uint32_t idesc = (two ? umma_idesc_bf16_m256((uint32_t)p.bn) : umma_idesc_bf16((uint32_t)p.bn)) &
+                                   (p.ab_f16 ? ~kIdescAbBf16 : ~0u);
             const uint32_t row_bytes = (uint32_t)p.bk * 2u;
             const uint64_t da0 = umma_smem_desc(smem_u32(smem), row_bytes);
             const uint64_t db0 = umma_smem_desc(smem_u32(smem) + a_bytes, row_bytes);

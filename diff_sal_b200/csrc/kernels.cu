@@ -268,6 +268,148 @@ int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, con
     DSB_LAUNCH_CHECK();
 }
 
+// GroupNorm + swish in ONE launch: a thread-block cluster of CL CTAs owns a frame.  Pass 1: every CTA reduces its pixel
+// slice to per-group (sum, sum of squares) in fp64; the partials meet through distributed shared memory (each CTA reads
+// all CL partial sets in rank order -> the same bits in every CTA, run to run); pass 2 re-reads the slice (L2-resident:
+// the encoder tensors are 2 - 33 MB) and writes bf16(swish(GN(x))) and, optionally, bf16(x).  Replaces the
+// gn_stats_kernel / gn_apply_kernel pair (two launches and a last-block fold per GroupNorm, six GroupNorms per evaluation).
+template <int CL>
+__global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__ x, int HW, int C,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      bf16* __restrict__ out_act, bf16* __restrict__ out_raw) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float ssum[4][768];
+    __shared__ float ssq[4][768];
+    __shared__ double part[32][2];
+    __shared__ float mean[32], rstd[32];
+    const unsigned rank = cluster_ctarank();
+    const int f = blockIdx.x / CL, tid = threadIdx.x;
+    const int cv_n = C >> 2, cg = C >> 5;
+    const int per = (HW + CL - 1) / CL;
+    const int p0 = (int)rank * per, p1 = min(HW, p0 + per);
+    const float4* base = reinterpret_cast<const float4*>(x + (size_t)f * HW * C);
+    // ---- pass 1: thread = (4-channel vector, pixel lane); 512 threads = P pixel lanes x cv_n vectors (P = 21 .. 2)
+    const int P = min(4, 512 / cv_n);                     // smem holds 4 lanes; more lanes fold into them below
+    const int PL = 512 / cv_n;                            // pixel lanes actually running
+    const int cv = tid % cv_n, pl = tid / cv_n;
+    float4 s4 = make_float4(0, 0, 0, 0), q4 = make_float4(0, 0, 0, 0);
+    if (pl < PL) {
+        for (int px = p0 + pl; px < p1; px += PL) {
+            const float4 v = base[(size_t)px * cv_n + cv];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
+        }
+    }
+    // fold the pixel lanes into <= 4 smem lanes in a fixed order (lane pl goes to slot pl % 4, rounds in sequence)
+    for (int round = 0; round * 4 < PL; ++round) {
+        if (pl < PL && pl / 4 == round) {
+            float* ps = &ssum[pl & 3][4 * cv];
+            float* pq = &ssq[pl & 3][4 * cv];
+            if (round == 0) {
+                ps[0] = s4.x; ps[1] = s4.y; ps[2] = s4.z; ps[3] = s4.w;
+                pq[0] = q4.x; pq[1] = q4.y; pq[2] = q4.z; pq[3] = q4.w;
+            } else {
+                ps[0] += s4.x; ps[1] += s4.y; ps[2] += s4.z; ps[3] += s4.w;
+                pq[0] += q4.x; pq[1] += q4.y; pq[2] += q4.z; pq[3] += q4.w;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 32) {
+        double sm = 0.0, sq = 0.0;
+        const int lanes = min(P, PL);
+        for (int l = 0; l < lanes; ++l)
+            for (int k = 0; k < cg; ++k) { sm += (double)ssum[l][tid * cg + k]; sq += (double)ssq[l][tid * cg + k]; }
+        part[tid][0] = sm;
+        part[tid][1] = sq;
+    }
+    cluster_sync_all();                                    // partials of all CL CTAs are visible cluster-wide
+    if (tid < 32) {
+        double sm = 0.0, sq = 0.0;
+        const uint32_t local = smem_u32(&part[tid][0]);
+        for (unsigned r = 0; r < CL; ++r) {                // rank order: identical bits in every CTA
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+            double a, b;
+            asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(remote));
+            sm += a;
+            sq += b;
+        }
+        const double n = (double)HW * cg;
+        const double m = sm / n;
+        double v = sq / n - m * m;
+        if (v < 0.0) v = 0.0;
+        mean[tid] = (float)m;
+        rstd[tid] = (float)(1.0 / sqrt(v + 1e-6));
+    }
+    cluster_sync_all();                                    // nobody leaves (or overwrites part) while peers still read it
+    // ---- pass 2: apply + swish over the same slice
+    const int total = (p1 - p0) * cv_n;
+    // 512 is not always a multiple of cv_n (C = 96: 24 | 512 ? no) -> recompute the vector index per element
+    const uint2* dummy = nullptr; (void)dummy;
+    const float4* xin = base + (size_t)p0 * cv_n;
+    uint2* oa = reinterpret_cast<uint2*>(out_act + (size_t)f * HW * C) + (size_t)p0 * cv_n;
+    uint2* orw = out_raw ? reinterpret_cast<uint2*>(out_raw + (size_t)f * HW * C) + (size_t)p0 * cv_n : nullptr;
+    const int stride = (512 / cv_n) * cv_n;                // threads beyond a whole number of channel periods idle
+    if (tid < stride) {
+        const int c = 4 * (tid % cv_n);
+        const float4 g = reinterpret_cast<const float4*>(gamma)[tid % cv_n];
+        const float4 bt = reinterpret_cast<const float4*>(beta)[tid % cv_n];
+        const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
+        const float ax = rstd[g0] * g.x, ay = rstd[g1] * g.y, az = rstd[g2] * g.z, aw = rstd[g3] * g.w;
+        const float bx = fmaf(-mean[g0], ax, bt.x), by = fmaf(-mean[g1], ay, bt.y), bz = fmaf(-mean[g2], az, bt.z),
+                    bw = fmaf(-mean[g3], aw, bt.w);
+#pragma unroll 4
+        for (int i = tid; i < total; i += stride) {
+            const float4 v = xin[i];
+            oa[i] = make_uint2(pack_bf16x2(swishf(fmaf(v.x, ax, bx)), swishf(fmaf(v.y, ay, by))),
+                               pack_bf16x2(swishf(fmaf(v.z, az, bz)), swishf(fmaf(v.w, aw, bw))));
+            if (orw) orw[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+    }
+}
+
+template <int CL>
+static int gn_fused_launch_cl(const float* x, int F, int HW, int C, const float* gamma, const float* beta, bf16* out_act,
+                              bf16* out_raw, cudaStream_t s) {
+    static int ok = -1;                                    // -1 unknown, 0 this cluster size cannot be launched, 1 fine
+    if (ok < 0) {
+        ok = 1;
+        if (CL > 8 && cudaFuncSetAttribute(gn_fused_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ok = 0;
+        }
+    }
+    if (!ok) return -1000;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(F * CL);
+    cfg.blockDim = dim3(512);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_use(false) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<CL>, x, HW, C, gamma, beta, out_act, out_raw);
+    if (e != cudaSuccess && CL > 8) { (void)cudaGetLastError(); ok = 0; return -1000; }
+    return (int)e;
+}
+
+// out_act = bf16(swish(GN(x))), out_raw = bf16(x) (optional); x: [F][HW][C] fp32
+int gn_fused_launch(const float* x, int F, int HW, int C, const float* gamma, const float* beta, bf16* out_act, bf16* out_raw,
+                    cudaStream_t s) {
+    if (C % 32 || C > 768 || C < 96) return -30;
+    int r = gn_fused_launch_cl<16>(x, F, HW, C, gamma, beta, out_act, out_raw, s);
+    if (r == -1000) r = gn_fused_launch_cl<8>(x, F, HW, C, gamma, beta, out_act, out_raw, s);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------ bilinear helpers
 // PyTorch area_pixel_compute_source_index (align_corners=False): src = scale*(dst+0.5)-0.5 clamped at 0.
 __device__ __forceinline__ void bil_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
@@ -376,7 +518,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int C, bool APPLY>
 __global__ void __launch_bounds__(256) ln_vec_kernel(const float* __restrict__ x, long tokens, float2* __restrict__ stats,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    bf16* __restrict__ out, int hw, int T, int tmax) {
+                                                    bf16* __restrict__ out, int hw, int T, int tmax, int f16) {
     pdl_trigger();
     pdl_wait();
     using G = LnGeom<C>;
@@ -408,8 +550,10 @@ __global__ void __launch_bounds__(256) ln_vec_kernel(const float* __restrict__ x
 #pragma unroll
         for (int i = 0; i < G::NVEC; ++i) {
             const float4 g = g4[l + G::LPT * i], b = b4[l + G::LPT * i];
-            o[l + G::LPT * i] = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
-                                           pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+            const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+            o[l + G::LPT * i] = f16 ? make_uint2(pack_f16x2(y0, y1), pack_f16x2(y2, y3))
+                                    : make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
         }
     } else {
         if (l == 0) stats[tok] = make_float2(mean, rstd);
@@ -418,11 +562,11 @@ __global__ void __launch_bounds__(256) ln_vec_kernel(const float* __restrict__ x
 
 template <bool APPLY>
 static int ln_vec_launch(const float* x, long tokens, int C, float2* stats, const float* gamma, const float* beta, bf16* out,
-                         int hw, int T, int tmax, cudaStream_t s) {
+                         int hw, int T, int tmax, cudaStream_t s, int f16 = 0) {
 #define DSB_LN_CASE(CC)                                                                                              \
     case CC: {                                                                                                       \
         const int g = (int)((tokens + 8 * LnGeom<CC>::TPW - 1) / (8 * LnGeom<CC>::TPW));                              \
-        DSB_PDL_LAUNCH((ln_vec_kernel<CC, APPLY>), g, 256, 0, s, x, tokens, stats, gamma, beta, out, hw, T, tmax);     \
+        DSB_PDL_LAUNCH((ln_vec_kernel<CC, APPLY>), g, 256, 0, s, x, tokens, stats, gamma, beta, out, hw, T, tmax, f16);     \
         break;                                                                                                       \
     }
     switch (C) {
@@ -442,8 +586,8 @@ int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, i
 }
 
 int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
-                    int T, int tmax, cudaStream_t s) {
-    return ln_vec_launch<true>(x, tokens, C, nullptr, gamma, beta, out, hw, T, tmax, s);
+                    int T, int tmax, cudaStream_t s, int f16) {
+    return ln_vec_launch<true>(x, tokens, C, nullptr, gamma, beta, out, hw, T, tmax, s, f16);
 }
 
 // ------------------------------------------------------------------------------------------ q = LN(dw3x3(LN(x)))
@@ -752,6 +896,236 @@ __global__ void __launch_bounds__(256, 2) q_dwln_tile2_kernel(const float* __res
     }
 }
 
+__device__ __forceinline__ void pooled_ln_store(const float* pre, int C, const float* __restrict__ g,
+                                                const float* __restrict__ b, bf16* __restrict__ o, float* red);
+
+// Q and V producers of a narrow stage in ONE pass over the stage input (audio-visual mode, C = 96 / 192):
+//   q = LN_q(dw3x3(LN(x)))  for every pixel,   v = LN_v(dw SxS stride S (LN(x)))  for the 18 pooling windows of the frame.
+// A block owns a TH x TW pixel tile made of whole pooling windows (16 x 16 = one window at C = 96, 8 x 16 = two windows
+// at C = 192).  Phase 1 computes the LayerNorm statistics of every staged token itself (a lane group holds the whole
+// token; same two-pass fp32 formula as ln_vec_kernel) and stages n = (x - mean) * rstd; phase 2 is q_dwln_tile2's column
+// walk (a lane group owns RS = 4 rows of one column); phase 3 pools the windows straight from the staged tile with the
+// LayerNorm affine folded into the tap table (wvg = w_v * g, wvbs = b * sum_p w_v).  Replaces ln_stats + q_dwln +
+// pool_ln(v): the stage input is read once (x 1.3 - 1.4 halo) instead of three times, and two launches disappear.
+template <int C, int TW, int TH, int S_>
+__global__ void __launch_bounds__(512, 1) qv_tile_kernel(const float* __restrict__ x, int H, int W,
+                                                        const float* __restrict__ wg, const float* __restrict__ wb,
+                                                        const float* __restrict__ wbs, const float* __restrict__ qg,
+                                                        const float* __restrict__ qb, const float* __restrict__ wvg,
+                                                        const float* __restrict__ wvbs, const float* __restrict__ vg,
+                                                        const float* __restrict__ vb, bf16* __restrict__ q_out,
+                                                        bf16* __restrict__ v_out, int T, int tmax) {
+    pdl_trigger();
+    pdl_wait();
+    using G = LnGeom<C>;
+    constexpr int RS = 4, NG = 512 / G::LPT, HWT = TW + 2, HHT = TH + 2, CV = C / 4, NT = HHT * HWT;
+    constexpr int NPASS = (NT + NG - 1) / NG, NWIN = (TW / S_) * (TH / S_), PG = 512 / CV;
+    static_assert(G::NVEC == 3 && NG == TW * (TH / RS) && TH % S_ == 0 && TW % S_ == 0, "tile geometry");
+    extern __shared__ float4 tile4[];                    // [HHT][HWT][CV] normalised tokens
+    __shared__ float pool[PG * C];
+    __shared__ float red[32];
+    const int nseg = W / TW, nrow = (H + TH - 1) / TH;
+    const int seg = blockIdx.x % nseg;
+    const int yb = (blockIdx.x / nseg) % nrow;
+    const int f = blockIdx.x / (nseg * nrow);
+    if (f % T >= tmax) return;
+    const int x0 = seg * TW, y0 = yb * TH;
+    const size_t fbase = (size_t)f * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / G::LPT, l = lane % G::LPT;
+    const int gidx = warp * G::TPW + sub;                // lane group, 0 .. NG-1
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    // ---- phase 1: statistics + normalised neighbourhood -> shared memory
+#pragma unroll 1
+    for (int p0 = 0; p0 < NPASS; p0 += 3) {
+        float4 v[3][3];
+        bool ok[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const int t = gidx + (p0 + p) * NG;
+            const int r = t / HWT, col = t - r * HWT;
+            const int yy = y0 + r - 1, xx = x0 + col - 1;
+            ok[p] = (p0 + p) < NPASS && t < NT && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const size_t tok = ok[p] ? fbase + (size_t)yy * W + xx : fbase;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[p][i] = x4[tok * CV + l + G::LPT * i];
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const int t = gidx + (p0 + p) * NG;
+            float s1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) s1 += (v[p][i].x + v[p][i].y) + (v[p][i].z + v[p][i].w);
+            const float mean = group_sum<G::LPT>(s1) * (1.0f / C);
+            float s2 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float a = v[p][i].x - mean, b = v[p][i].y - mean, c = v[p][i].z - mean, d = v[p][i].w - mean;
+                s2 = fmaf(a, a, s2); s2 = fmaf(b, b, s2); s2 = fmaf(c, c, s2); s2 = fmaf(d, d, s2);
+            }
+            const float rstd = rsqrtf(group_sum<G::LPT>(s2) * (1.0f / C) + 1e-5f);
+            if ((p0 + p) < NPASS && t < NT) {
+                const float rs = ok[p] ? rstd : 0.0f, c0 = -mean * rs;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tile4[t * CV + l + G::LPT * i] = make_float4(fmaf(v[p][i].x, rs, c0), fmaf(v[p][i].y, rs, c0),
+                                                                 fmaf(v[p][i].z, rs, c0), fmaf(v[p][i].w, rs, c0));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: q for RS rows of one tile column per lane group
+    {
+        const float4* wg4 = reinterpret_cast<const float4*>(wg);
+        const float4* wb4 = reinterpret_cast<const float4*>(wb);
+        const int col = gidx % TW, r0 = (gidx / TW) * RS;
+        const int xx = x0 + col;
+        float4 q[RS][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int cvi = l + G::LPT * i;
+            float4 w[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[k] = __ldg(wg4 + k * CV + cvi);
+            const float4 bs = __ldg(reinterpret_cast<const float4*>(wbs) + cvi);
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                float4 a = bs;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float4 tv = tile4[((r0 + r + dy) * HWT + col + dx) * CV + cvi];
+                        const float4 wv = w[dy * 3 + dx];
+                        a.x = fmaf(wv.x, tv.x, a.x); a.y = fmaf(wv.y, tv.y, a.y);
+                        a.z = fmaf(wv.z, tv.z, a.z); a.w = fmaf(wv.w, tv.w, a.w);
+                    }
+                const int yy = y0 + r0 + r;
+                if (yy == 0 || yy == H - 1 || xx == 0 || xx == W - 1) {      // border token: drop the out-of-image bias taps
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int y2 = yy + dy - 1, x2 = xx + dx - 1;
+                            if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) {
+                                const float4 t = __ldg(wb4 + (dy * 3 + dx) * CV + cvi);
+                                a.x -= t.x; a.y -= t.y; a.z -= t.z; a.w -= t.w;
+                            }
+                        }
+                }
+                q[r][i] = a;
+            }
+        }
+        float4 gq[3], bq[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            gq[i] = __ldg(reinterpret_cast<const float4*>(qg) + l + G::LPT * i);
+            bq[i] = __ldg(reinterpret_cast<const float4*>(qb) + l + G::LPT * i);
+        }
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            float s1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) s1 += (q[r][i].x + q[r][i].y) + (q[r][i].z + q[r][i].w);
+            const float mean = group_sum<G::LPT>(s1) * (1.0f / C);
+            float v2 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float a = q[r][i].x - mean, b = q[r][i].y - mean, c = q[r][i].z - mean, d = q[r][i].w - mean;
+                v2 = fmaf(a, a, v2); v2 = fmaf(b, b, v2); v2 = fmaf(c, c, v2); v2 = fmaf(d, d, v2);
+            }
+            const float rstd = rsqrtf(group_sum<G::LPT>(v2) * (1.0f / C) + 1e-5f);
+            const int yy = y0 + r0 + r;
+            if (yy < H) {
+                uint2* o = reinterpret_cast<uint2*>(q_out + (fbase + (size_t)yy * W + xx) * C);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    o[l + G::LPT * i] = make_uint2(
+                        pack_bf16x2((q[r][i].x - mean) * rstd * gq[i].x + bq[i].x, (q[r][i].y - mean) * rstd * gq[i].y + bq[i].y),
+                        pack_bf16x2((q[r][i].z - mean) * rstd * gq[i].z + bq[i].z, (q[r][i].w - mean) * rstd * gq[i].w + bq[i].w));
+            }
+        }
+    }
+    // ---- phase 3: the pooling windows of this tile (rows below the last whole window are not pooled: 3 x 6 windows)
+    if (y0 / S_ >= 3) return;                            // block-uniform
+    const int tid = threadIdx.x;
+    const int c4 = tid % CV, gq_ = tid / CV;
+    const float4* wv4 = reinterpret_cast<const float4*>(wvg) + c4;
+#pragma unroll 1
+    for (int wdw = 0; wdw < NWIN; ++wdw) {
+        const int wy = wdw / (TW / S_), wx = wdw % (TW / S_);
+        const int Y = y0 / S_ + wy, X = x0 / S_ + wx;
+        if (Y >= 3) break;                               // block-uniform
+        if (gq_ < PG) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int p = gq_; p < S_ * S_; p += PG) {
+                const int dy = p / S_, dx = p % S_;
+                const float4 tv = tile4[((wy * S_ + dy + 1) * HWT + wx * S_ + dx + 1) * CV + c4];
+                const float4 w = __ldg(wv4 + p * CV);
+                acc.x = fmaf(w.x, tv.x, acc.x); acc.y = fmaf(w.y, tv.y, acc.y);
+                acc.z = fmaf(w.z, tv.z, acc.z); acc.w = fmaf(w.w, tv.w, acc.w);
+            }
+            reinterpret_cast<float4*>(pool)[gq_ * CV + c4] = acc;
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += 512) {
+            float a = __ldg(wvbs + c);
+            for (int k = 0; k < PG; ++k) a += pool[k * C + c];
+            pool[c] = a;                                  // element c of row 0 is only touched by this thread
+        }
+        __syncthreads();
+        pooled_ln_store(pool, C, vg, vb, v_out + ((size_t)f * 18 + Y * 6 + X) * C, red);
+        __syncthreads();
+    }
+}
+
+// taps with the LayerNorm affine folded in for a depthwise SxS pooling: wg[p][c] = w[p][c] * g[c], wbs[c] = b[c] * sum_p w[p][c]
+__global__ void dw_affine_prep_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
+                                      int taps, int C, float* __restrict__ wg, float* __restrict__ wbs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.0f;
+    for (int k = 0; k < taps; ++k) {
+        const float wv = w[k * C + c];
+        wg[k * C + c] = wv * g[c];
+        s += wv;
+    }
+    wbs[c] = s * b[c];
+}
+
+int dw_affine_prep_launch(const float* w, const float* g, const float* b, int taps, int C, float* wg, float* wbs, cudaStream_t s) {
+    dw_affine_prep_kernel<<<(C + 127) / 128, 128, 0, s>>>(w, g, b, taps, C, wg, wbs);
+    DSB_LAUNCH_CHECK();
+}
+
+template <int C, int TW, int TH, int S_>
+static int qv_tile_launch_t(const float* x, int F, int H, int W, const QdwTables& tb, const float* qg, const float* qb,
+                            const float* wvg, const float* wvbs, const float* vg, const float* vb, bf16* q_out, bf16* v_out,
+                            int T, int tmax, cudaStream_t s) {
+    constexpr size_t smem = (size_t)(TH + 2) * (TW + 2) * C * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(qv_tile_kernel<C, TW, TH, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const int grid = F * ((H + TH - 1) / TH) * (W / TW);
+    DSB_PDL_LAUNCH((qv_tile_kernel<C, TW, TH, S_>), grid, 512, smem, s, x, H, W, tb.wg, tb.wb, tb.wbs, qg, qb, wvg, wvbs, vg, vb,
+                   q_out, v_out, T, tmax);
+    DSB_LAUNCH_CHECK();
+}
+
+int qv_tile_launch(const float* x, int F, int H, int W, int C, int s_, const QdwTables& tb, const float* qg, const float* qb,
+                   const float* wvg, const float* wvbs, const float* vg, const float* vb, bf16* q_out, bf16* v_out, int T,
+                   int tmax, cudaStream_t s) {
+    if (C == 96 && H == 56 && W == 96 && s_ == 16)
+        return qv_tile_launch_t<96, 16, 16, 16>(x, F, H, W, tb, qg, qb, wvg, wvbs, vg, vb, q_out, v_out, T, tmax, s);
+    if (C == 192 && H == 28 && W == 48 && s_ == 8)
+        return qv_tile_launch_t<192, 16, 8, 8>(x, F, H, W, tb, qg, qb, wvg, wvbs, vg, vb, q_out, v_out, T, tmax, s);
+    return -37;
+}
+
 // wg[k][c] = w[k][c] * g[c], wb[k][c] = w[k][c] * b[c], wbs[c] = sum_k wb[k][c]   (w: [9][C] depthwise taps)
 __global__ void q_dw_prep_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b, int C,
                                  float* __restrict__ wg, float* __restrict__ wb, float* __restrict__ wbs) {
@@ -867,7 +1241,7 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
         const float4 g = reinterpret_cast<const float4*>(ng)[c4], bb = reinterpret_cast<const float4*>(nb)[c4];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int npx = s_ * s_;
-#pragma unroll 4
+#pragma unroll 8
         for (int p = gq; p < npx; p += G) {
             const int t = (p >> sl) * W + (p & (s_ - 1));
             const float2 st = sw[t];
@@ -967,8 +1341,12 @@ int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int 
 // K source = raw reinterpretation of the contiguous [B][C][T][H][W] buffer (a*g) as [(B T)][H W][C]
 // (transformer.py:146) followed by 'b (h w) c -> b c h w' (attention.py:89): element (bt, pix', c') is the flat
 // element j = (bt % T)*HW*C + pix'*C + c' of clip b = bt / T, and flat j decodes to (c, t, pix) = [C][T][HW].
+// The audio map is read from its channel-major copy a_cm[b][c][t][7][12] (audio_cmajor_launch, once per conditioning):
+// for a fixed source channel the 1 / 2 / 4 audio values under 4 consecutive source pixels are then adjacent floats and the
+// lanes of a warp walk contiguous memory.  (Read from the token-major a_low[b][t][84][c] the same values were 4-byte
+// gathers 4*C bytes apart: one 32-byte sector per value, 8 % of the HBM rate in ncu.)
 template <int C, int H, int W, int S_, int T_>
-__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_low, int tmax,
+__global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_cm, int tmax,
                                 const float* __restrict__ wk, const float* __restrict__ kg,
                                 const float* __restrict__ kb, bf16* __restrict__ out) {
     pdl_trigger();
@@ -989,11 +1367,11 @@ __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __rest
     // upsample by R) as 1, 2 or 4 scalars.  All divisors are compile-time.
     const int G = blockDim.x / CV;
     const int c4 = tid % CV, gq = tid / CV;
-    const float* a_b = a_low + (size_t)b * T_ * 84 * C;
+    const float* a_b = a_cm + (size_t)b * C * T_ * 84;
     const float* g_b = g + (size_t)b * C * HW;
     if (gq < G) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll 8
         for (int p = gq; p < NPX; p += G) {
             const int dy = p / S_, dx = p % S_;
             const int j = clip_base + ((Y * S_ + dy) * W + X * S_ + dx) * C + 4 * c4;
@@ -1002,15 +1380,17 @@ __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __rest
             const int ys = pix / W, xs = pix % W;
             const float4 gv = *reinterpret_cast<const float4*>(g_b + (size_t)cs * HW + pix);
             const float4 w = __ldg(reinterpret_cast<const float4*>(wk) + p * CV + c4);
-            const float* ar = a_b + (((size_t)ts * 7 + (ys / R)) * 12) * C + cs;
+            const float* ar = a_b + (((size_t)cs * T_ + ts) * 7 + (ys / R)) * 12;
             float a0, a1, a2, a3;
             if constexpr (R >= 4) {
-                a0 = a1 = a2 = a3 = ar[(xs / R) * C];
+                a0 = a1 = a2 = a3 = __ldg(ar + xs / R);
             } else if constexpr (R == 2) {
-                a0 = a1 = ar[(xs / 2) * C];
-                a2 = a3 = ar[(xs / 2 + 1) * C];
+                const float2 t2 = __ldg(reinterpret_cast<const float2*>(ar + xs / 2));      // xs % 4 == 0
+                a0 = a1 = t2.x;
+                a2 = a3 = t2.y;
             } else {
-                a0 = ar[xs * C]; a1 = ar[(xs + 1) * C]; a2 = ar[(xs + 2) * C]; a3 = ar[(xs + 3) * C];
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(ar + xs));
+                a0 = t4.x; a1 = t4.y; a2 = t4.z; a3 = t4.w;
             }
             acc.x = fmaf(w.x, a0 * gv.x, acc.x);
             acc.y = fmaf(w.y, a1 * gv.y, acc.y);
@@ -1021,6 +1401,29 @@ __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __rest
     }
     pool_fold_groups(sm, C, G);
     pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
+}
+
+// a_low[(b*T + t)*84 + p][c]  ->  a_cm[b][c][t*84 + p]     (32 x 32 shared-memory transpose, coalesced on both sides)
+__global__ void __launch_bounds__(256) audio_cmajor_kernel(const float* __restrict__ a_low, int C, int TP,
+                                                          float* __restrict__ a_cm) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int p = p0 + k, c = c0 + tx;
+        tile[k][tx] = (p < TP && c < C) ? a_low[((size_t)b * TP + p) * C + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, p = p0 + tx;
+        if (p < TP && c < C) a_cm[((size_t)b * C + c) * TP + p] = tile[tx][k];
+    }
+}
+
+int audio_cmajor_launch(const float* a_low, int B, int T, int C, float* a_cm, cudaStream_t s) {
+    const int TP = T * 84;
+    audio_cmajor_kernel<<<dim3((TP + 31) / 32, (C + 31) / 32, B), 256, 0, s>>>(a_low, C, TP, a_cm);
+    DSB_LAUNCH_CHECK();
 }
 
 int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_, const float* wk,
@@ -1207,7 +1610,7 @@ __global__ void __launch_bounds__(256, 2) ms_sum_kernel(MsSrc src, bf16* __restr
     uint2* orow = reinterpret_cast<uint2*>(S) + (((size_t)b * OH + yo) * OW + xo0) * CV + cv;
 #pragma unroll
     for (int i = 0; i < kMsXT; ++i)
-        orow[(size_t)i * CV] = make_uint2(pack_bf16x2(acc[i].x, acc[i].y), pack_bf16x2(acc[i].z, acc[i].w));
+        orow[(size_t)i * CV] = make_uint2(pack_f16x2(acc[i].x, acc[i].y), pack_f16x2(acc[i].z, acc[i].w));   // fp16: mt_proj operand
 }
 
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s) {

@@ -5,6 +5,8 @@
 
 namespace dsb {
 
+struct QdwTables { const float* wg; const float* wb; const float* wbs; };     // [9][C], [9][C], [C]
+
 struct TembWeights {
     const float* w0; const float* b0;      // temb.dense.0  [384,96]
     const float* w1; const float* b1;      // temb.dense.1  [384,384]
@@ -26,6 +28,10 @@ int gn_stats_launch(const float* x, int F, int HW, int C, double* acc, cudaStrea
 int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, const float* gamma, const float* beta,
                     bf16* out_act, bf16* out_raw, cudaStream_t s);
 
+// the two passes above in one launch (a thread-block cluster per frame, statistics exchanged through DSMEM)
+int gn_fused_launch(const float* x, int F, int HW, int C, const float* gamma, const float* beta, bf16* out_act, bf16* out_raw,
+                    cudaStream_t s);
+
 // bilinear x2, align_corners=False: fp32 [F][H][W][C] -> bf16 [F][2H][2W][C]
 int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cudaStream_t s);
 
@@ -33,17 +39,27 @@ int upsample2x_launch(const float* x, int F, int H, int W, int C, bf16* out, cud
 // tokens of frames with (frame % T) >= tmax are skipped (hw = tokens per frame)
 int ln_stats_launch(const float* x, long tokens, int C, float2* stats, int hw, int T, int tmax, cudaStream_t s);
 // out = bf16(LN(x) * gamma + beta); tokens of frames with (frame % T) >= tmax are skipped (hw = tokens per frame)
+// f16 = 1: the output holds fp16 (not bf16) values -- the operand of a GEMM that runs with GemmParams::ab_f16
 int ln_apply_launch(const float* x, long tokens, int C, const float* gamma, const float* beta, bf16* out, int hw,
-                    int T, int tmax, cudaStream_t s);
+                    int T, int tmax, cudaStream_t s, int f16 = 0);
 
 // q = LN_q( depthwise3x3( LN_norm(x) ) )  -> bf16 [tokens][C]      (attention.py:36-48,92 ; transformer.py:151)
 // tb (optional): tap tables with the LayerNorm affine folded in (q_dw_prep_launch); with them the narrow stages
 // (C = 96, 192) take the second-generation tiled kernel.
-struct QdwTables { const float* wg; const float* wb; const float* wbs; };     // [9][C], [9][C], [C]
 int q_dw_prep_launch(const float* w9, const float* ng, const float* nb, int C, float* wg, float* wb, float* wbs, cudaStream_t s);
 int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int C, const float* ng, const float* nb,
                   const float* wq /*[9][C]*/, const QdwTables* tb, const float* qg, const float* qb, bf16* out, int T, int tmax,
                   cudaStream_t s);
+
+// taps of a depthwise SxS pooling with the pre-attention LayerNorm affine folded in: wg[p][c] = w[p][c] * g[c],
+// wbs[c] = b[c] * sum_p w[p][c]
+int dw_affine_prep_launch(const float* w, const float* g, const float* b, int taps, int C, float* wg, float* wbs, cudaStream_t s);
+// q and v of a narrow stage (C = 96 @ 56x96, C = 192 @ 28x48) in one pass over the stage input, LayerNorm statistics
+// computed in the kernel (replaces ln_stats + q_dwln + pool_ln for the audio-visual configuration); -37 if the geometry
+// is not one of the two
+int qv_tile_launch(const float* x, int F, int H, int W, int C, int s_, const QdwTables& tb, const float* qg, const float* qb,
+                   const float* wvg, const float* wvbs, const float* vg, const float* vb, bf16* q_out, bf16* v_out, int T,
+                   int tmax, cudaStream_t s);
 
 // v (or visual-only k) = LN( depthwise sxs stride s ( LN_norm(x) ) ) -> bf16 [F*18][C]   (attention.py:53-76,93)
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
@@ -52,8 +68,11 @@ int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int
 
 // audio gate: g[b][c][y][x] = softmax_x( mean_t( a[b,t,y/r,x/r,c] * x[b,t,y,x,c] ) )   (transformer.py:140-144)
 int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s);
+// channel-major copy of the aligned audio map: a_low[(b*T+t)*84 + p][c] -> a_cm[b][c][t*84 + p]
+int audio_cmajor_launch(const float* a_low, int B, int T, int C, float* a_cm, cudaStream_t s);
 // k = LN( depthwise sxs stride s ( scrambled (a*g) ) ) -> bf16 [B*T*18][C]   (transformer.py:145-146, attention.py:89-91)
-int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_,
+// a_cm: the CHANNEL-MAJOR audio map (audio_cmajor_launch)
+int kpool_av_launch(const float* g, const float* a_cm, int B, int T, int H, int W, int C, int s_,
                     const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s);
 
 // per-frame tensor-core operands of the 18-key, 2-head attention:
@@ -66,7 +85,7 @@ int attn_operands_launch(const float* kp, const float* vp, int F, int C, float s
 int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
                      float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s);
 
-// S[b][y][x][c] = sum_i bilinear(r_i -> 112x192)[b,y,x,c]  (bf16)   (sal_unet.py:482-487)
+// S[b][y][x][c] = sum_i bilinear(r_i -> 112x192)[b,y,x,c]  (fp16 bits: operand of the ab_f16 mt_proj GEMM)   (sal_unet.py:482-487)
 int ms_sum_launch(const float* const r[4], int B, bf16* S, cudaStream_t s);
 // bilinear x2 on a single-channel map: p[B][112][192] -> out[B][224][384]   (sal_unet.py:325-327)
 int final_up_launch(const float* p, int B, float* out, cudaStream_t s);

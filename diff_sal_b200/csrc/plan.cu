@@ -11,6 +11,7 @@
 #include <vector>
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -76,6 +77,7 @@ struct dsb_handle {
     float* enc_d[3] = {nullptr, nullptr, nullptr};
     float* back[3] = {nullptr, nullptr, nullptr};
     float* a_low[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* a_cm[4] = {nullptr, nullptr, nullptr, nullptr};     // channel-major copies for the K-source gather
     bf16* audio_tok = nullptr;
     float *X[4] = {}, *X1[4] = {}, *X2[4] = {};
     float* r[4] = {};
@@ -173,13 +175,13 @@ const float* W(dsb_handle* h, const std::string& key) {
 }
 
 // ------------------------------------------------------------------------------------------ finalize helpers
-int pack_gemm_weight(dsb_handle* h, const std::string& key, int N, int Cin, int taps) {
+int pack_gemm_weight(dsb_handle* h, const std::string& key, int N, int Cin, int taps, int f16 = 0) {
     const Weight* w = find_w(h, key);
     if (!w) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", key.c_str());
     if (w->numel != (long)N * Cin * taps) return fail(h, DSB_ERR_WEIGHT, "weight '%s' has the wrong size", key.c_str());
     bf16* dst = nullptr;
     if (int r = dev_alloc(h, &dst, (size_t)N * Cin * taps)) return r;
-    if (int r = pack_weight_launch(w->p, N, Cin, taps, dst, 0)) return fail(h, DSB_ERR_CUDA, "pack_weight launch %d", r);
+    if (int r = pack_weight_launch(w->p, N, Cin, taps, dst, 0, f16)) return fail(h, DSB_ERR_CUDA, "pack_weight launch %d", r);
     h->wpack[key] = dst;
     return 0;
 }
@@ -235,6 +237,8 @@ int alloc_workspace(dsb_handle* h) {
     if (h->cfg.audio_visual) {
         for (int i = 0; i < 4; ++i)
             if (int r = dev_alloc(h, &h->a_low[i], F * 84 * kStageC[i])) return r;
+        for (int i = 0; i < 4; ++i)
+            if (int r = dev_alloc(h, &h->a_cm[i], F * 84 * kStageC[i])) return r;
         if (int r = dev_alloc(h, &h->audio_tok, F * 84 * 512)) return r;
         if (int r = dev_alloc(h, &h->gate, B * kMaxFrame)) return r;
     }
@@ -357,6 +361,7 @@ int build_program(dsb_handle* h) {
     };
 
     // ------------------------------------------------------------ noise encoder (sal_unet.py:279-300)
+    static const bool gn_fused = [] { const char* e = getenv("DSB_GN_FUSED"); return !(e && e[0] == '0'); }();
     {
         TembWeights tw;
         tw.w0 = WF("temb.dense.0.weight.T"); tw.b0 = W(h, "temb.dense.0.bias");      // transposed [in][out]
@@ -387,8 +392,12 @@ int build_program(dsb_handle* h) {
             const float *g2 = W(h, rk + "norm2.weight"), *b2 = W(h, rk + "norm2.bias");
             bf16 *act = h->enc_act, *raw = h->enc_raw, *res = h->enc_res;
             float *c1 = h->enc_c1, *sc = h->enc_sc;
-            b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); }, "gn_stats", (double)B * HW * Cin * 4.0);
-            b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); }, "gn_apply", (double)B * HW * Cin * 8.0);
+            if (gn_fused) {
+                b.add([=](cudaStream_t s) { return gn_fused_launch(cur, B, HW, Cin, g1, b1, act, raw, s); }, "gn_fused", (double)B * HW * Cin * 8.0);
+            } else {
+                b.add([=](cudaStream_t s) { return gn_stats_launch(cur, B, HW, Cin, acc1, s); }, "gn_stats", (double)B * HW * Cin * 4.0);
+                b.add([=](cudaStream_t s) { return gn_apply_launch(cur, B, HW, Cin, acc1, g1, b1, act, raw, s); }, "gn_apply", (double)B * HW * Cin * 8.0);
+            }
             if (i == 0) b.depend(5, 1, 0);                  // timestep projections ready
             {   // 1x1 shortcut on the raw block input: only conv2's epilogue needs it, so it runs beside
                 // conv1 / GroupNorm 2 on the side stream
@@ -406,8 +415,12 @@ int build_program(dsb_handle* h) {
                 op.halo = 1;
                 b.conv(op, "res.conv1");
             }
-            b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); }, "gn_stats", (double)B * HW * Cout * 4.0);
-            b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); }, "gn_apply", (double)B * HW * Cout * 6.0);
+            if (gn_fused) {
+                b.add([=](cudaStream_t s) { return gn_fused_launch(c1, B, HW, Cout, g2, b2, act, nullptr, s); }, "gn_fused", (double)B * HW * Cout * 6.0);
+            } else {
+                b.add([=](cudaStream_t s) { return gn_stats_launch(c1, B, HW, Cout, acc2, s); }, "gn_stats", (double)B * HW * Cout * 4.0);
+                b.add([=](cudaStream_t s) { return gn_apply_launch(c1, B, HW, Cout, acc2, g2, b2, act, nullptr, s); }, "gn_apply", (double)B * HW * Cout * 6.0);
+            }
             b.depend(7, 1, 0);                              // shortcut ready
             {   // conv2 + bias + shortcut -> block output (only ever a GEMM operand: bf16)
                 ConvOp op = make_op(CONV_3X3, B, H, Wd, Cout, Cout, act, WP(rk + "conv2.weight"));
@@ -475,11 +488,6 @@ int build_program(dsb_handle* h) {
             return op;
         };
         float2* stats = h->lnstats;
-        // three independent producers read the stage input: K (audio gate -> scramble -> pool, side stream 2),
-        // V (side stream 1) and Q (caller's stream); they rejoin before the attention operands are built
-        b.depend(0, 0, 2);                                  // Xi is complete -> K branch may start
-        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, HW, kT, tmax, s); }, "ln_stats", (double)tokens * C * 4.0 * live);
-        b.depend(1, 0, 1);                                  // LayerNorm statistics ready -> V branch may start
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
         bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
         const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
@@ -487,13 +495,50 @@ int build_program(dsb_handle* h) {
         const float *qg = W(h, bk + "attn.conv_proj_q.bn.weight"), *qb = W(h, bk + "attn.conv_proj_q.bn.bias");
         const float *kg = W(h, bk + "attn.conv_proj_k.bn.weight"), *kb = W(h, bk + "attn.conv_proj_k.bn.bias");
         const float *vg = W(h, bk + "attn.conv_proj_v.bn.weight"), *vb = W(h, bk + "attn.conv_proj_v.bn.bias");
+        const QdwTables qtb = {WF(bk + "attn.conv_proj_q.wg"), WF(bk + "attn.conv_proj_q.wb"), WF(bk + "attn.conv_proj_q.wbs")};
+        static const bool qv_fused_on = [] { const char* e = getenv("DSB_QV_FUSED"); return !(e && e[0] == '0'); }();
+        const bool qv_fused = qv_fused_on && h->has_audio && C <= 192;
+        if (qv_fused) {
+            // narrow stages, audio-visual: Q and V come out of ONE pass over the stage input (LayerNorm statistics computed
+            // in the kernel) on the caller's stream; the K branch (audio gate -> scramble -> pool) runs beside it on stream 2
+            b.depend(0, 0, 2);                              // Xi is complete -> K branch may start
+            b.cur = 2;
+            {
+                const float* al = h->a_low[i];
+                const float* acm = h->a_cm[i];
+                float* gate = h->gate;
+                b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
+                b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
+                ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
+                op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
+                b.conv(op, "attn.proj_k");
+            }
+            b.cur = 0;
+            const float *wvg = WF(bk + "attn.conv_proj_v.wvg"), *wvbs = WF(bk + "attn.conv_proj_v.wvbs");
+            b.add([=](cudaStream_t s) { return qv_tile_launch(Xi, F, H, Wd, C, sk, qtb, qg, qb, wvg, wvbs, vg, vb, q_ln, v_ln, kT, tmax, s); },
+                  "qv_tile", (double)tokens * C * 6.0 * live);
+            b.depend(1, 0, 1);                              // V tokens ready -> their projection runs on stream 1
+            b.cur = 1;
+            {
+                ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
+                op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
+                b.conv(op, "attn.proj_v");
+            }
+            b.cur = 0;
+        } else {
+        // three independent producers read the stage input: K (audio gate -> scramble -> pool, side stream 2),
+        // V (side stream 1) and Q (caller's stream); they rejoin before the attention operands are built
+        b.depend(0, 0, 2);                                  // Xi is complete -> K branch may start
+        b.add([=](cudaStream_t s) { return ln_stats_launch(Xi, tokens, C, stats, HW, kT, tmax, s); }, "ln_stats", (double)tokens * C * 4.0 * live);
+        b.depend(1, 0, 1);                                  // LayerNorm statistics ready -> V branch may start
         b.cur = 2;
         if (!h->has_audio) b.depend(1, 0, 2);               // visual-only K also needs the statistics
         if (h->has_audio) {
             const float* al = h->a_low[i];
             float* gate = h->gate;
             b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
-            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, al, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
+            const float* acm = h->a_cm[i];
+            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
         } else {
             b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
         }
@@ -510,8 +555,8 @@ int build_program(dsb_handle* h) {
             b.conv(op, "attn.proj_v");
         }
         b.cur = 0;
-        const QdwTables qtb = {WF(bk + "attn.conv_proj_q.wg"), WF(bk + "attn.conv_proj_q.wb"), WF(bk + "attn.conv_proj_q.wbs")};
         b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, &qtb, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
+        }
         // algorithmic FLOPs are always the reference's (all 9 frames), also where dead frames are skipped
         const bool fused_attn = C <= 192;
         if (fused_attn) {
@@ -607,10 +652,10 @@ int build_program(dsb_handle* h) {
             const float *gm = W(h, nk + "weight"), *bm = W(h, nk + "bias");
             const float* x2 = h->X2[i];
             bf16* lnm = h->lnm;
-            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s); }, "ln_apply_mts", (double)tokens * C * 6.0 * 5.0 / 9.0);
+            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s, 1); }, "ln_apply_mts", (double)tokens * C * 6.0 * 5.0 / 9.0);
             ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
                                 WP("invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight"));
-            op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i];
+            op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i]; op.ab_f16 = 1;
             op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
                 b.conv(op, "reduce_temp");
         }
@@ -626,7 +671,7 @@ int build_program(dsb_handle* h) {
         }, "ms_sum", (double)B * (7140.0 * 768 * 4 + 21504.0 * 768 * 2));
         ConvOp op = make_op(CONV_3X3, B, 112, 192, 768, 96, h->S, WP("invpt_decoder.mt_proj.0.weight"));
         op.scale = WF("invpt_decoder.mt_proj.1.scale"); op.shift = WF("invpt_decoder.mt_proj.1.shift");
-        op.act = ACT_RELU; op.head_w = W(h, "logits.linear_pred.weight");
+        op.act = ACT_RELU; op.head_w = W(h, "logits.linear_pred.weight"); op.ab_f16 = 1;
         float hb = 0.0f;
         cudaMemcpy(&hb, W(h, "logits.linear_pred.bias"), sizeof(float), cudaMemcpyDeviceToHost);
         op.head_b = hb; op.out_head = h->p;
@@ -817,15 +862,26 @@ extern "C" int dsb_finalize_weights(dsb_handle* h) {
         }
         if (int r = pack_dw(h, bk + "attn.conv_proj_k.conv.weight", C, sk * sk, sk * sk, 0)) return r;
         if (int r = pack_dw(h, bk + "attn.conv_proj_v.conv.weight", C, sk * sk, sk * sk, 0)) return r;
+        {   // pooling taps of V with the pre-attention LayerNorm affine folded in (qv_tile_kernel)
+            float *wvg = nullptr, *wvbs = nullptr;
+            if (int r = dev_alloc(h, &wvg, (size_t)sk * sk * C)) return r;
+            if (int r = dev_alloc(h, &wvbs, (size_t)C)) return r;
+            if (int r = dw_affine_prep_launch(h->wf[bk + "attn.conv_proj_v.conv.weight"], W(h, bk + "norm.weight"),
+                                              W(h, bk + "norm.bias"), sk * sk, C, wvg, wvbs, 0))
+                return fail(h, DSB_ERR_CUDA, "dw_affine_prep launch %d", r);
+            h->wf[bk + "attn.conv_proj_v.wvg"] = wvg;
+            h->wf[bk + "attn.conv_proj_v.wvbs"] = wvbs;
+        }
         if (h->cfg.audio_visual) {
             if (!W(h, bk + "align_conv.bias")) return fail(h, DSB_ERR_WEIGHT, "missing weight '%salign_conv.bias'", bk.c_str());
             if (int r = pack_gemm_weight(h, bk + "align_conv.weight", C, 512, 1)) return r;
         }
         const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";
         if (!W(h, nk + "weight") || !W(h, nk + "bias")) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s*'", nk.c_str());
-        if (int r = pack_gemm_weight(h, "invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight", 768, C, kReduce)) return r;
+        // output-head chain (ReduceTemp, mt_proj): fp16 operands (precision policy)
+        if (int r = pack_gemm_weight(h, "invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight", 768, C, kReduce, 1)) return r;
     }
-    if (int r = pack_gemm_weight(h, "invpt_decoder.mt_proj.0.weight", 96, 768, 9)) return r;
+    if (int r = pack_gemm_weight(h, "invpt_decoder.mt_proj.0.weight", 96, 768, 9, 1)) return r;
     if (int r = fold_bn(h, "invpt_decoder.mt_proj.1", "invpt_decoder.mt_proj.0.bias", 96)) return r;
     CUDA_TRY(h, cudaDeviceSynchronize());
     h->weight_bytes = h->alloc_bytes;
@@ -862,6 +918,8 @@ extern "C" int dsb_set_condition(dsb_handle* h, const void* const feat[4], const
             ConvLaunch cl;
             if ((r = conv_lower(op, &cl))) return fail(h, DSB_ERR_CUDA, "conv_lower(align_conv) failed (%d)", r);
             if ((r = conv_run(cl, h->num_sms, s))) return fail(h, DSB_ERR_CUDA, "align_conv launch failed (%d)", r);
+            if ((r = audio_cmajor_launch(h->a_low[i], B, kT, kStageC[i], h->a_cm[i], s)))
+                return fail(h, DSB_ERR_CUDA, "audio_cmajor launch failed (%d)", r);
         }
     }
     if (rebuild) {
@@ -871,7 +929,7 @@ extern "C" int dsb_set_condition(dsb_handle* h, const void* const feat[4], const
         if (int r = build_program(h)) return r;
     }
     h->cond_epoch++;
-    h->cond_launches = 3 + (audio ? 5 : 0);
+    h->cond_launches = 3 + (audio ? 9 : 0);
     return DSB_OK;
 }
 

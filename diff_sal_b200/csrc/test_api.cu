@@ -22,6 +22,10 @@ static int g_test_two_cta = 0;
 // -1: never use CTA pairs, 0: automatic, 1: always (for the per-kernel tests)
 extern "C" void dsb_test_set_two_cta(int mode) { g_test_two_cta = mode; }
 
+static int g_test_ab_f16 = 0;
+// 1: A / Wt of dsb_test_conv hold fp16 values (GemmParams::ab_f16)
+extern "C" void dsb_test_set_ab_f16(int on) { g_test_ab_f16 = on; }
+
 static float* g_test_split_ws = nullptr;
 static long g_test_split_elems = 0;
 // split-K scratch for dsb_test_conv (NULL: never split); returns the slice count the LAST lowered op used
@@ -44,6 +48,7 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     op.two_cta = g_test_two_cta;
     op.split_ws = g_test_split_ws; op.split_ws_elems = g_test_split_elems;
     op.halo = g_test_halo;
+    op.ab_f16 = g_test_ab_f16;
     ConvLaunch l;
     int r = conv_lower(op, &l);
     if (r) return r;
@@ -60,6 +65,8 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
 extern "C" int dsb_test_groupnorm_swish(const float* x, int F, int HW, int C, const float* gamma, const float* beta,
                                         double* scratch /*[F*64*64]*/, void* out_act, void* out_raw, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    if (!scratch)                                       // NULL scratch: the one-launch cluster kernel the plan uses
+        return gn_fused_launch(x, F, HW, C, gamma, beta, (bf16*)out_act, (bf16*)out_raw, s);
     if (int r = gn_stats_launch(x, F, HW, C, scratch, s)) return r;
     return gn_apply_launch(x, F, HW, C, scratch, gamma, beta, (bf16*)out_act, (bf16*)out_raw, s);
 }
@@ -82,6 +89,20 @@ extern "C" int dsb_test_q_dwln(const float* x, int F, int H, int W, int C, const
     return q_dwln_launch(x, (const float2*)stats_scratch, F, H, W, C, ng, nb, wq9, &qt, qg, qb, (bf16*)out, T, tmax, s);
 }
 
+extern "C" int dsb_test_qv_tile(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
+                                const float* wq9, const float* qg, const float* qb, const float* wv, const float* vg,
+                                const float* vb, void* q_out, void* v_out, int T, int tmax, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    static float* tb = nullptr;                        // folded tap tables (prepared per weight set in the product)
+    const size_t cap = (size_t)(19 + 257) * 768;
+    if (!tb && cudaMalloc(&tb, cap * sizeof(float)) != cudaSuccess) return -1;
+    float *wg = tb, *wb = tb + 9 * 768, *wbs = tb + 18 * 768, *wvg = tb + 19 * 768, *wvbs = tb + (19 + 256) * 768;
+    if (int r = q_dw_prep_launch(wq9, ng, nb, C, wg, wb, wbs, s)) return r;
+    if (int r = dw_affine_prep_launch(wv, ng, nb, sk * sk, C, wvg, wvbs, s)) return r;
+    const QdwTables qt = {wg, wb, wbs};
+    return qv_tile_launch(x, F, H, W, C, sk, qt, qg, qb, wvg, wvbs, vg, vb, (bf16*)q_out, (bf16*)v_out, T, tmax, s);
+}
+
 extern "C" int dsb_test_pool_ln(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
                                 const float* w, const float* g, const float* b, void* stats_scratch, void* out, int T,
                                 int tmax, void* stream) {
@@ -95,7 +116,16 @@ extern "C" int dsb_test_av_key(const float* x, const float* a_low, int B, int T,
                                void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = av_gate_launch(x, a_low, B, T, H, W, C, gate, s)) return r;
-    return kpool_av_launch(gate, a_low, B, T, H, W, C, sk, wk, kg, kb, (bf16*)out_k, tmax, s);
+    static float* acm = nullptr;                      // channel-major audio map (prepared at conditioning time in the product)
+    static size_t acm_cap = 0;
+    const size_t need = (size_t)B * T * 84 * C;
+    if (need > acm_cap) {
+        if (acm) cudaFree(acm);
+        if (cudaMalloc(&acm, need * sizeof(float)) != cudaSuccess) return -1;
+        acm_cap = need;
+    }
+    if (int r = audio_cmajor_launch(a_low, B, T, C, acm, s)) return r;
+    return kpool_av_launch(gate, acm, B, T, H, W, C, sk, wk, kg, kb, (bf16*)out_k, tmax, s);
 }
 
 extern "C" int dsb_test_upsample2x(const float* x, int F, int H, int W, int C, void* out, void* stream) {

@@ -2,21 +2,23 @@
 
 namespace dsb {
 
-__global__ void pack_weight_kernel(const float* __restrict__ src, int N, int Cin, int taps, bf16* __restrict__ dst) {
+__global__ void pack_weight_kernel(const float* __restrict__ src, int N, int Cin, int taps, bf16* __restrict__ dst, int f16) {
     const long total = (long)N * Cin * taps;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cin);
         const int tap = (int)((i / Cin) % taps);
         const long n = i / ((long)Cin * taps);
-        dst[i] = __float2bfloat16(src[(n * Cin + c) * taps + tap]);
+        const float v = src[(n * Cin + c) * taps + tap];
+        if (f16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+        else dst[i] = __float2bfloat16(v);
     }
 }
 
-int pack_weight_launch(const float* src, int N, int Cin, int taps, bf16* dst, cudaStream_t s) {
+int pack_weight_launch(const float* src, int N, int Cin, int taps, bf16* dst, cudaStream_t s, int f16) {
     const long total = (long)N * Cin * taps;
     long g = (total + 255) / 256;
     if (g > 4096) g = 4096;
-    pack_weight_kernel<<<(int)g, 256, 0, s>>>(src, N, Cin, taps, dst);
+    pack_weight_kernel<<<(int)g, 256, 0, s>>>(src, N, Cin, taps, dst, f16);
     return (int)cudaGetLastError();
 }
 

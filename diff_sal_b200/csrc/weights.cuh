@@ -4,8 +4,8 @@
 
 namespace dsb {
 
-// src fp32 [N][Cin][taps] (conv weight, taps contiguous) -> dst bf16 [N][tap*Cin + c]
-int pack_weight_launch(const float* src, int N, int Cin, int taps, bf16* dst, cudaStream_t s);
+// src fp32 [N][Cin][taps] (conv weight, taps contiguous) -> dst bf16 (or, f16 = 1, fp16 bits) [N][tap*Cin + c]
+int pack_weight_launch(const float* src, int N, int Cin, int taps, bf16* dst, cudaStream_t s, int f16 = 0);
 // depthwise: dst[tap*C + c] = src[c*src_stride + src_off + tap]
 int pack_dw_launch(const float* src, int C, int taps, int src_stride, int src_off, float* dst, cudaStream_t s);
 // src [R][Cc] -> dst [Cc][R]

@@ -216,6 +216,9 @@ int dsb_test_layernorm(const float* x, long tokens, int C, const float* gamma, c
                        int T, int tmax, void* stream);
 int dsb_test_q_dwln(const float* x, int F, int H, int W, int C, const float* ng, const float* nb, const float* wq9,
                     const float* qg, const float* qb, void* stats_scratch, void* out, int T, int tmax, void* stream);
+int dsb_test_qv_tile(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb, const float* wq9,
+                     const float* qg, const float* qb, const float* wv, const float* vg, const float* vb, void* q_out,
+                     void* v_out, int T, int tmax, void* stream);
 int dsb_test_pool_ln(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
                      const float* w, const float* g, const float* b, void* stats_scratch, void* out, int T, int tmax,
                      void* stream);
@@ -239,6 +242,8 @@ void dsb_test_set_two_cta(int mode);
 /* split-K scratch of dsb_test_conv (NULL: never split) and the slice count its last call used (0: not split) */
 void dsb_test_set_split_ws(float* ws, long elems);
 int dsb_test_last_ksplit(void);
+/* 1: the A / Wt buffers of dsb_test_conv hold fp16 (not bf16) values -- the operand type of the output-head GEMMs */
+void dsb_test_set_ab_f16(int on);
 /* request the halo-tile 3x3 path in dsb_test_conv, and whether its last call took it */
 void dsb_test_set_halo(int on);
 int dsb_test_last_halo(void);

@@ -70,6 +70,39 @@ def test_linear(L, M, Cin, N, act, resid):
     close(out.reshape(M, N), ref, 2e-3)
 
 
+@pytest.mark.parametrize("halo,two", [(0, -1), (1, 1)])
+def test_fp16_operands(L, halo, two):
+    """GemmParams::ab_f16: the output-head GEMMs (ReduceTemp, mt_proj) take fp16 instead of bf16 operands -- same
+    kind::f16 instruction, A / B format bits of the instruction descriptor cleared.  Values are chosen so that an fp16
+    buffer misread as bf16 (or the reverse) is wrong by orders of magnitude."""
+    lib = L.lib()
+    lib.dsb_test_set_ab_f16(1)
+    lib.dsb_test_set_halo(halo)
+    lib.dsb_test_set_two_cta(two)
+    try:
+        Fr, H, W, Cin, N = 2, 32, 48, 128, 96
+        x = _rand(Fr, Cin, H, W, seed=71).to(torch.float16)
+        w = _rand(N, Cin, 3, 3, seed=72, scale=(9 * Cin) ** -0.5).to(torch.float16)
+        a = x.permute(0, 2, 3, 1).contiguous()
+        wt = w.permute(0, 2, 3, 1).reshape(N, -1).contiguous()
+        out = run_conv(L, CONV_3X3, a, wt, N, Fr, H, W, Cin, act=ACT_RELU, want="f32")
+        ref = F.relu(F.conv2d(x.float(), w.float(), padding=1)).permute(0, 2, 3, 1)
+        close(out, ref, 1e-3)
+        # temporal (5,1,1) reduction, the other fp16 GEMM of the plan
+        T, kt, C2 = 9, 5, 192
+        xt = _rand(2 * T, 10, 12, C2, seed=73).to(torch.float16)
+        w3 = _rand(768, C2, kt, seed=74, scale=(kt * C2) ** -0.5).to(torch.float16)
+        wt3 = w3.permute(0, 2, 1).reshape(768, -1).contiguous()
+        o = run_conv(L, CONV_TEMPORAL, xt, wt3, 768, 2, 10, 12, C2, T=T, kt=kt, act=ACT_RELU, want="f32")
+        xr = xt.float().reshape(2, T, 10, 12, C2)[:, :kt]
+        ref3 = F.relu(torch.einsum("bthwc,nct->bhwn", xr, w3.float()))
+        close(o, ref3, 1e-3)
+    finally:
+        lib.dsb_test_set_ab_f16(0)
+        lib.dsb_test_set_halo(0)
+        lib.dsb_test_set_two_cta(0)
+
+
 @pytest.mark.parametrize("Fr,H,W,Cin,N,dil", [(2, 28, 48, 192, 384, 1), (3, 14, 24, 768, 384, 2), (1, 56, 96, 96, 192, 1),
                                               (9, 56, 96, 96, 96, 2), (4, 7, 12, 768, 768, 1)])
 def test_conv3x3(L, Fr, H, W, Cin, N, dil):

@@ -52,6 +52,26 @@ def test_groupnorm_swish(L, Fr, H, W, C):
     assert torch.equal(raw, a.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("Fr,H,W,C", [(2, 56, 96, 96), (3, 56, 96, 192), (3, 28, 48, 192), (2, 28, 48, 384), (8, 14, 24, 384),
+                                       (2, 14, 24, 768), (1, 7, 9, 96)])
+def test_groupnorm_swish_one_launch(L, Fr, H, W, C):
+    """gn_fused_kernel: a thread-block cluster per frame, statistics exchanged through distributed shared memory (every
+    GroupNorm of the noise encoder runs through it); reproducible bit for bit run to run."""
+    x = rnd(Fr, C, H, W, seed=41, scale=1.5, shift=0.3)
+    g, b = rnd(C, seed=42, scale=0.2, shift=1.0), rnd(C, seed=43, scale=0.1)
+    a = nhwc(x)
+    act = torch.empty(Fr, H, W, C, device="cuda", dtype=torch.bfloat16)
+    raw = torch.empty_like(act)
+    check(L.lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act), L.ptr(raw), L.stream_ptr()))
+    ref = F.group_norm(x, 32, g, b, eps=1e-6)
+    ref = nhwc(ref * torch.sigmoid(ref))
+    assert (act.float() - ref).abs().max().item() <= BF * max(1.0, ref.abs().max().item())
+    assert torch.equal(raw, a.to(torch.bfloat16))
+    act2 = torch.empty_like(act)
+    check(L.lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act2), None, L.stream_ptr()))
+    assert torch.equal(act, act2)
+
+
 @pytest.mark.parametrize("C", [96, 192, 384, 768])
 def test_layernorm_with_frame_filter(L, C):
     T, hw, B = 9, 20, 2
@@ -82,6 +102,37 @@ def test_q_depthwise_layernorm(L, Fr, H, W, C):
     q = F.conv3d(xn.unsqueeze(2), w3, None, padding=1, groups=C).squeeze(2)     # the reference's Conv3d on depth 1
     ref = F.layer_norm(nhwc(q), (C,), qg, qb, eps=1e-5).reshape(Fr * H * W, C)
     assert (out.float() - ref).abs().max().item() <= BF * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("Fr,T,tmax,H,W,C,s", [(2, 1, 1, 56, 96, 96, 16), (3, 1, 1, 28, 48, 192, 8), (9, 9, 5, 28, 48, 192, 8)])
+def test_fused_q_and_v_producer(L, Fr, T, tmax, H, W, C, s):
+    """qv_tile_kernel (narrow stages, audio-visual): q = LN(dw3x3(LN(x))) and the 18 pooled v = LN(dw sxs(LN(x))) tokens
+    of every live frame from one pass over x, LayerNorm statistics computed in the kernel."""
+    x = rnd(Fr, C, H, W, seed=51, scale=1.3)
+    ng, nb = rnd(C, seed=52, scale=0.2, shift=1.0), rnd(C, seed=53, scale=0.1)
+    w3 = rnd(C, 1, 3, 3, 3, seed=54, scale=0.3)
+    qg, qb = rnd(C, seed=55, scale=0.2, shift=1.0), rnd(C, seed=56, scale=0.1)
+    wv = rnd(C, 1, 1, s, s, seed=57, scale=1.0 / s)
+    vg, vb = rnd(C, seed=58, scale=0.2, shift=1.0), rnd(C, seed=59, scale=0.1)
+    w9 = w3[:, 0, 1].reshape(C, 9).t().contiguous()
+    wt = wv.reshape(C, s * s).t().contiguous()
+    q_out = torch.full((Fr * H * W, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    v_out = torch.full((Fr * 18, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    xl = nhwc(x)
+    check(L.lib().dsb_test_qv_tile(L.ptr(xl), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(w9), L.ptr(qg), L.ptr(qb), L.ptr(wt),
+                                   L.ptr(vg), L.ptr(vb), L.ptr(q_out), L.ptr(v_out), T, tmax, L.stream_ptr()))
+    xn = F.layer_norm(nhwc(x), (C,), ng, nb, eps=1e-5).permute(0, 3, 1, 2)
+    q = F.conv3d(xn.unsqueeze(2), w3, None, padding=1, groups=C).squeeze(2)
+    qref = F.layer_norm(nhwc(q), (C,), qg, qb, eps=1e-5).reshape(Fr, H * W, C)
+    v = F.conv2d(xn, wv[:, :, 0], None, stride=s, groups=C)
+    vref = F.layer_norm(nhwc(v), (C,), vg, vb, eps=1e-5).reshape(Fr, 18, C)
+    qo, vo = q_out.float().reshape(Fr, H * W, C), v_out.float().reshape(Fr, 18, C)
+    live = [f for f in range(Fr) if f % T < tmax]
+    dead = [f for f in range(Fr) if f % T >= tmax]
+    assert (qo[live] - qref[live]).abs().max().item() <= BF * max(1.0, qref.abs().max().item())
+    assert (vo[live] - vref[live]).abs().max().item() <= BF * max(1.0, vref.abs().max().item())
+    if dead:
+        assert (qo[dead] == 7.0).all() and (vo[dead] == 7.0).all()          # dead frames untouched
 
 
 @pytest.mark.parametrize("Fr,H,W,C,s", [(2, 7, 12, 768, 2), (2, 14, 24, 384, 4), (2, 28, 48, 192, 8), (1, 56, 96, 96, 16)])
@@ -140,11 +191,11 @@ def test_upsample2x(L, Fr, H, W, C):
 def test_multi_scale_sum_and_final_upsample(L):
     B = 2
     rs = [rnd(B, 768, 7 << k, 12 << k, seed=25 + k) for k in range(4)]
-    out = torch.empty(B, 112, 192, 768, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, 112, 192, 768, device="cuda", dtype=torch.float16)     # fp16: operand of the mt_proj GEMM
     rl = [nhwc(r) for r in rs]                      # keep the channels-last copies alive across the launch
     check(L.lib().dsb_test_ms_sum(*[L.ptr(r) for r in rl], B, L.ptr(out), L.stream_ptr()))
     ref = sum(F.interpolate(r, size=(112, 192), mode="bilinear", align_corners=False) for r in rs)
-    assert (out.float() - nhwc(ref)).abs().max().item() <= BF * max(1.0, ref.abs().max().item())
+    assert (out.float() - nhwc(ref)).abs().max().item() <= BF / 8 * max(1.0, ref.abs().max().item())
     p = rnd(B, 1, 112, 192, seed=30)
     o2 = torch.empty(B, 1, 224, 384, device="cuda")
     check(L.lib().dsb_test_final_up(L.ptr(p), B, L.ptr(o2), L.stream_ptr()))
