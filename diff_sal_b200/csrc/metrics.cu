@@ -154,7 +154,62 @@ __global__ void __launch_bounds__(kThreads) metrics_kernel(const float* __restri
     }
 }
 
+// Validation losses of the reference's sampling loop (models/sal_losses.py:14-176, get_kl_cc_sim_loss_wo_weight :207-233,
+// called on every validated batch at diffusion_trainer.py:741,797,868): per clip
+//   kl  = sum g' log(eps + g' / (s' + eps)),   s' = s / sum s, g' = g / sum g,  eps = 2.2204e-16         (kldiv2)
+//   cc  = sum a b / sqrt(sum a^2 sum b^2),     a, b = maps standardised with the UNBIASED std (torch.std) (cc_s2)
+//   sim = sum min(s~, g~),                     s~, g~ = min-max normalised maps divided by their sums      (similarity2)
+//   nss = sum ((s - mean s) / (std s + eps)) g / sum g                                                     (nss2)
+// One block per clip, two passes (moments / extrema, then the four sums), fp64 accumulation; the batch mean of each
+// column is what the reference returns.
+__global__ void __launch_bounds__(kThreads) val_losses_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                              int n, double* __restrict__ out) {
+    __shared__ double scratch[32 * 8];
+    const int b = blockIdx.x;
+    const float* p = pred + (size_t)b * n;
+    const float* g = gt + (size_t)b * n;
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 1e300, -1e300, 1e300, -1e300};      // sum s, sum g, (unused), (unused), min/max s, min/max g
+    const int op1[8] = {0, 0, 0, 0, 1, 2, 1, 2};
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const double a = p[i], c = g[i];
+        v[0] += a; v[1] += c;
+        v[4] = fmin(v[4], a); v[5] = fmax(v[5], a); v[6] = fmin(v[6], c); v[7] = fmax(v[7], c);
+    }
+    block_reduce<8>(v, op1, scratch);
+    const double N = (double)n, sum_s = v[0], sum_g = v[1], mean_s = sum_s / N, mean_g = sum_g / N;
+    const double min_s = v[4], max_s = v[5], min_g = v[6], max_g = v[7];
+    const double rng_s = max_s - min_s, rng_g = max_g - min_g;
+    const double nsum_s = (sum_s - N * min_s) / rng_s, nsum_g = (sum_g - N * min_g) / rng_g;   // sums of the min-max maps
+    const double eps = 2.2204e-16;
+    double w[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // kl, sum ds^2, sum dg^2, sum ds dg, sim, sum ds g, -, -
+    const int op2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const double a = p[i], c = g[i];
+        const double sp = a / sum_s, gp = c / sum_g;
+        w[0] += gp * log(eps + gp / (sp + eps));
+        const double ds = a - mean_s, dg = c - mean_g;
+        w[1] += ds * ds; w[2] += dg * dg; w[3] += ds * dg;
+        w[4] += fmin(((a - min_s) / rng_s) / nsum_s, ((c - min_g) / rng_g) / nsum_g);
+        w[5] += ds * c;
+    }
+    block_reduce<8>(w, op2, scratch);
+    if (threadIdx.x == 0) {
+        const double std_s = sqrt(w[1] / (N - 1.0));                       // torch.std: unbiased
+        out[b * 4 + 0] = w[0];
+        out[b * 4 + 1] = w[3] / sqrt(w[1] * w[2]);                         // the standard deviations cancel
+        out[b * 4 + 2] = w[4];
+        out[b * 4 + 3] = (w[5] / (std_s + eps)) / sum_g;
+    }
+}
+
 }  // namespace
+
+extern "C" int dsb_val_losses(const float* pred, const float* gt, int B, int64_t elems_per_clip, double* out4, void* stream) {
+    if (!pred || !gt || !out4 || B < 1 || elems_per_clip < 2 || elems_per_clip > (1 << 30)) return DSB_ERR_ARG;
+    val_losses_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(pred, gt, (int)elems_per_clip, out4);
+    return cudaGetLastError() == cudaSuccess ? DSB_OK : DSB_ERR_CUDA;
+}
 
 extern "C" int dsb_metrics(const float* pred, const float* density, const float* fixations, const double* jitter_or_null,
                            int B, int64_t pixels_per_map, double* out4, void* stream) {

@@ -496,7 +496,7 @@ int build_program(dsb_handle* h) {
         const float *kg = W(h, bk + "attn.conv_proj_k.bn.weight"), *kb = W(h, bk + "attn.conv_proj_k.bn.bias");
         const float *vg = W(h, bk + "attn.conv_proj_v.bn.weight"), *vb = W(h, bk + "attn.conv_proj_v.bn.bias");
         const QdwTables qtb = {WF(bk + "attn.conv_proj_q.wg"), WF(bk + "attn.conv_proj_q.wb"), WF(bk + "attn.conv_proj_q.wbs")};
-        static const bool qv_fused_on = [] { const char* e = getenv("DSB_QV_FUSED"); return !(e && e[0] == '0'); }();
+        static const bool qv_fused_on = [] { const char* e = getenv("DSB_QV_FUSED"); return e && e[0] == '1'; }();   // measured: no faster than the three-kernel form (DESIGN.md negative results)
         const bool qv_fused = qv_fused_on && h->has_audio && C <= 192;
         if (qv_fused) {
             // narrow stages, audio-visual: Q and V come out of ONE pass over the stage input (LayerNorm statistics computed

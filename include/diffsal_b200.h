@@ -31,6 +31,9 @@
  *        VGGish.__init__ + load_state_dict + forward_feat (models/vggish.py:87-124) -- SURVEY.md 8f row N2 (audio half)
  *   dsb_metrics
  *        metrics.metrics.{CC, SIM, NSS, AUC_Judd} (metrics/metrics.py:7-64,178-252) -- SURVEY.md 8f row N3
+ *   dsb_val_losses
+ *        models.sal_losses.{kldiv2, cc_s2, similarity2, nss2} behind get_kl_cc_sim_loss_wo_weight
+ *        (models/sal_losses.py:14-176,207-233) -- SURVEY.md 8f row N3
  */
 #ifndef DIFFSAL_B200_H
 #define DIFFSAL_B200_H
@@ -145,6 +148,12 @@ int dsb_postprocess(const float* x, int B, int64_t pixels_per_map, float* clampe
  * out4: device fp64 [B][4] = CC, SIM, NSS, AUC_J. */
 int dsb_metrics(const float* pred, const float* density, const float* fixations, const double* jitter_or_null, int B,
                 int64_t pixels_per_map, double* out4, void* stream);
+
+/* validation losses of the reference's sampling loop on the device: kldiv2 / cc_s2 / similarity2 /
+ * nss2 of models/sal_losses.py:14-176 (get_kl_cc_sim_loss_wo_weight :207-233, diffusion_trainer.py:741,797,868), PER CLIP:
+ * pred / gt: device fp32 [B][elems_per_clip]; out4: device fp64 [B][4] = kl, cc, sim, nss (the reference returns their
+ * batch means). */
+int dsb_val_losses(const float* pred, const float* gt, int B, int64_t elems_per_clip, double* out4, void* stream);
 
 /* number of kernel launches enqueued by the last dsb_denoise / dsb_sample call (for bench.py's gpu_launches) */
 int64_t dsb_last_launch_count(const dsb_handle* h);

@@ -57,3 +57,29 @@ def test_reference_named_functions_and_errors():
     assert np.isnan(G.AUC_Judd(pt, torch.zeros_like(ft)).item())       # no fixation: NaN like the reference
     with pytest.raises(DsbError):
         G.CC(pt.cpu(), dt.cpu())
+
+
+def test_validation_losses_on_device():
+    """dsb_val_losses (models/sal_losses.py:14-176,207-233) against the fp32 oracle restatement, batch of maps from the
+    sampler's value range plus a sparse ground truth."""
+    import types
+    from diff_sal_b200 import sal_losses as S
+    from oracle import sal_losses as O
+    g = torch.Generator().manual_seed(21)
+    pred = torch.rand(4, 1, 224, 384, generator=g) * 0.3 + 0.1
+    gt = torch.rand(4, 1, 224, 384, generator=g) ** 6
+    per = S.per_clip_losses(pred.cuda(), gt.cuda()).cpu()
+    for b in range(4):
+        want = [O.kldiv2(pred[b:b + 1], gt[b:b + 1]), O.cc_s2(pred[b:b + 1], gt[b:b + 1]), O.similarity2(pred[b:b + 1], gt[b:b + 1]),
+                O.nss2(pred[b:b + 1], gt[b:b + 1])]
+        for k in range(4):
+            assert abs(per[b, k].item() - want[k].item()) <= 2e-5 * max(1.0, abs(want[k].item())), (b, k)
+    for kl in (True, False):
+        cfg = types.SimpleNamespace(loss=types.SimpleNamespace(loss_kl=kl))
+        got, want = S.get_kl_cc_sim_loss_wo_weight(cfg, pred.cuda(), gt.cuda()), O.get_kl_cc_sim_loss_wo_weight(kl, pred, gt)
+        assert set(got) == set(want)
+        for k in got:
+            assert abs(float(got[k]) - float(want[k])) <= 2e-5 * max(1.0, abs(float(want[k]))), k
+    from diff_sal_b200.engine import DsbError
+    with pytest.raises(DsbError):
+        S.per_clip_losses(pred, gt)                       # CPU tensors: no fallback

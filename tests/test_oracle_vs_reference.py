@@ -275,3 +275,23 @@ def test_vggish_matches_reference():
     with torch.no_grad():
         ref = net.forward_feat(x)
     assert (vggish.forward_feat(sd, x) - ref).abs().max().item() < 1e-4
+
+
+def test_validation_losses_match_reference():
+    """models/sal_losses.py kldiv2 / cc_s2 / similarity2 / nss2 behind get_kl_cc_sim_loss_wo_weight."""
+    import types
+    ref_loader.load()
+    import models.sal_losses as ref
+    from oracle import sal_losses as mine
+    g = torch.Generator().manual_seed(12)
+    pred = torch.rand(3, 1, 56, 96, generator=g) * 0.8 + 0.05
+    gt = torch.rand(3, 1, 56, 96, generator=g) ** 4
+    for name in ("kldiv2", "cc_s2", "similarity2", "nss2"):
+        a, b = getattr(ref, name)(pred, gt), getattr(mine, name)(pred, gt)
+        assert abs(a.item() - b.item()) <= 2e-6 * max(1.0, abs(a.item())), name
+    for kl in (True, False):
+        cfg = types.SimpleNamespace(loss=types.SimpleNamespace(loss_kl=kl, loss_cc=True, loss_sim=True, loss_nss=True))
+        ra, mb = ref.get_kl_cc_sim_loss_wo_weight(cfg, pred, gt), mine.get_kl_cc_sim_loss_wo_weight(kl, pred, gt)
+        assert set(ra) == set(mb)
+        for k in ra:
+            assert abs(float(ra[k]) - float(mb[k])) <= 2e-6 * max(1.0, abs(float(ra[k]))), k
