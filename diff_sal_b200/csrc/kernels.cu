@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
     const int cv = tid % cv_n, pl = tid / cv_n;
     float4 s4 = make_float4(0, 0, 0, 0), q4 = make_float4(0, 0, 0, 0);
     if (pl < PL) {
+#pragma unroll 8
         for (int px = p0 + pl; px < p1; px += PL) {
             const float4 v = base[(size_t)px * cv_n + cv];
             s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
         const float ax = rstd[g0] * g.x, ay = rstd[g1] * g.y, az = rstd[g2] * g.z, aw = rstd[g3] * g.w;
         const float bx = fmaf(-mean[g0], ax, bt.x), by = fmaf(-mean[g1], ay, bt.y), bz = fmaf(-mean[g2], az, bt.z),
                     bw = fmaf(-mean[g3], aw, bt.w);
-#pragma unroll 4
+#pragma unroll 8
         for (int i = tid; i < total; i += stride) {
             const float4 v = xin[i];
             oa[i] = make_uint2(pack_bf16x2(swishf(fmaf(v.x, ax, bx)), swishf(fmaf(v.y, ay, by))),
@@ -775,8 +776,8 @@ __global__ void __launch_bounds__(256) q_dwln_tiled_kernel(const float* __restri
 //    amortised over TH tokens; the out-of-image taps of border tokens are subtracted from wbs.
 // Against the first version (one token per lane group and block row: 3.2 staged tokens and 27 tap loads per output token,
 // three FP operations per staged element) this stages 1.6 - 2.1 tokens per output token at a third of the arithmetic.
-template <int C, int TW, int TH>
-__global__ void __launch_bounds__(256, 2) q_dwln_tile2_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+template <int C, int TW, int TH, int MINB, int PB>
+__global__ void __launch_bounds__(256, MINB) q_dwln_tile2_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
                                                              int H, int W, const float* __restrict__ wg,
                                                              const float* __restrict__ wb, const float* __restrict__ wbs,
                                                              const float* __restrict__ qg, const float* __restrict__ qb,
@@ -798,14 +799,14 @@ __global__ void __launch_bounds__(256, 2) q_dwln_tile2_kernel(const float* __res
     const int sub = lane / G::LPT, l = lane % G::LPT;
     const int slot = warp * G::TPW + sub;                // tile column of this lane group, 0 .. TW-1
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    // ---- phase 1: normalised neighbourhood -> shared memory (batches of 4 tokens per lane group keep 12 loads in flight)
+    // ---- phase 1: normalised neighbourhood -> shared memory (batches of PB tokens per lane group keep 3 PB loads in flight)
 #pragma unroll 1
-    for (int p0 = 0; p0 < NPASS; p0 += 4) {
-        float4 v[4][3];
-        float2 st[4];
-        bool ok[4];
+    for (int p0 = 0; p0 < NPASS; p0 += PB) {
+        float4 v[PB][3];
+        float2 st[PB];
+        bool ok[PB];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < PB; ++p) {
             const int t = slot + (p0 + p) * PER;
             const int r = t / HWT, col = t - r * HWT;
             const int yy = y0 + r - 1, xx = x0 + col - 1;
@@ -816,7 +817,7 @@ __global__ void __launch_bounds__(256, 2) q_dwln_tile2_kernel(const float* __res
             for (int i = 0; i < 3; ++i) v[p][i] = x4[tok * CV + l + G::LPT * i];
         }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < PB; ++p) {
             const int t = slot + (p0 + p) * PER;
             if (t < NT) {
                 const float rs = ok[p] ? st[p].y : 0.0f, c0 = -st[p].x * rs;
@@ -1147,17 +1148,17 @@ int q_dw_prep_launch(const float* w9, const float* ng, const float* nb, int C, f
     DSB_LAUNCH_CHECK();
 }
 
-template <int C, int TW, int TH>
+template <int C, int TW, int TH, int MINB, int PB>
 static int q_dwln_tile2_launch(const float* x, const float2* stats, int F, int H, int W, const QdwTables& tb, const float* qg,
                                const float* qb, bf16* out, int T, int tmax, cudaStream_t s) {
     constexpr size_t smem = (size_t)(TH + 2) * (TW + 2) * C * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(q_dwln_tile2_kernel<C, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(q_dwln_tile2_kernel<C, TW, TH, MINB, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    DSB_PDL_LAUNCH((q_dwln_tile2_kernel<C, TW, TH>), F * (H / TH) * (W / TW), 256, smem, s, x, stats, H, W, tb.wg, tb.wb, tb.wbs, qg,
+    DSB_PDL_LAUNCH((q_dwln_tile2_kernel<C, TW, TH, MINB, PB>), F * (H / TH) * (W / TW), 256, smem, s, x, stats, H, W, tb.wg, tb.wb, tb.wbs, qg,
                    qb, out, T, tmax);
     DSB_LAUNCH_CHECK();
 }
@@ -1169,12 +1170,12 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
     const int g = (int)((tokens + 7) / 8);
     static const int th = [] { const char* e = getenv("DSB_QDW_TH"); return e ? atoi(e) : 4; }();
     if (tb && tb->wg && C == 96 && W % 32 == 0 && H % 4 == 0) {
-        if (th == 2) return q_dwln_tile2_launch<96, 32, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
-        if (th == 4) return q_dwln_tile2_launch<96, 32, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 2) return q_dwln_tile2_launch<96, 32, 2, 3, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 4) return q_dwln_tile2_launch<96, 32, 4, 2, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
     }
     if (tb && tb->wg && C == 192 && W % 16 == 0 && H % 4 == 0) {
-        if (th == 2) return q_dwln_tile2_launch<192, 16, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
-        if (th == 4) return q_dwln_tile2_launch<192, 16, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 2) return q_dwln_tile2_launch<192, 16, 2, 3, 2>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
+        if (th == 4) return q_dwln_tile2_launch<192, 16, 4, 2, 4>(x, stats, F, H, W, *tb, qg, qb, out, T, tmax, s);
     }
     if (C == 96 && W % 32 == 0) {
         DSB_PDL_LAUNCH((q_dwln_tiled_kernel<96, 32>), F * H * (W / 32), 256, 3 * 34 * 96 * sizeof(float), s, x, stats, H, W, ng, nb, wq, qg, qb, out, T, tmax);
