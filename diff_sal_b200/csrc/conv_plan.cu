@@ -8,7 +8,9 @@ namespace dsb {
 static int pick_bn(int N) {
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
-    for (int bn = 256; bn >= 16; bn -= 16)
+    for (int bn = 256; bn >= 32; bn -= 32)               // the general epilogues work on 32-column chunks
+        if (N % bn == 0) return bn;
+    for (int bn = 240; bn >= 16; bn -= 16)               // 48-column attention-score tiles
         if (N % bn == 0) return bn;
     return 0;
 }
@@ -204,6 +206,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.scale = op.scale; p.shift = op.shift; p.rowbias = op.rowbias; p.residual = op.residual;
     p.act = op.act;
     p.ab_f16 = op.ab_f16;
+    p.out_f16 = op.out_f16;
     p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
     p.ldo = op.ldo ? op.ldo : op.N;
     p.out_fmul = op.out_fmul ? op.out_fmul : 1;

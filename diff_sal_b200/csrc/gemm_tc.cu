@@ -408,10 +408,17 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         }
                         if (p.out_bf16) {
                             uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
-                            op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                               pack_bf16x2(v[6], v[7]));
-                            op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                               pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            if (p.out_f16) {
+                                op[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                                   pack_f16x2(v[6], v[7]));
+                                op[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                                                   pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+                            } else {
+                                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                   pack_bf16x2(v[6], v[7]));
+                                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                   pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            }
                         }
                     }
                 }
@@ -479,7 +486,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         if (p.out2_f32) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)rowtab[96 + row] * p.ldo + n) = v;
                         if (p.out_bf16)
                             *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po * p.ldo + n) =
-                                make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                                p.out_f16 ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w))
+                                          : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                     }
                 }
             }
@@ -574,6 +582,7 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (p.f_group && (p.f_used < 1 || p.f_used > p.f_group)) return -19;
     if (p.two_cta && (p.b_rows_per_frame || p.out_softmax || (p.bn / 2) % 8)) return -20;
     if (p.ksub < 1 || (p.taps * p.cin_blocks) % p.ksub) return -21;
+    if (p.out_f16 && (p.out_softmax || p.ksplit > 1)) return -25;
     if (p.ksplit > 1) {
         if (p.two_cta || p.epi_transposed || p.head_w || p.out_softmax || p.out_bf16 || p.out2_f32 || p.scale || p.shift ||
             p.rowbias || p.residual || p.act != ACT_NONE || !p.out_f32 || p.f_group)

@@ -31,6 +31,7 @@ struct GemmParams {
     int N, bn;                      // N % bn == 0, bn % 16 == 0, bn <= 256
     int two_cta;                    // 1: CTA pairs (cluster of 2) issue cta_group::2 MMAs with M = 256
     int ab_f16;                     // 1: both operands hold fp16 (not bf16) values -- the output-head GEMMs (DESIGN.md precision policy)
+    int out_f16;                    // 1: out_bf16 receives fp16 (not bf16) values (it feeds a GEMM that runs with ab_f16)
     int b_rows_per_frame;           // 0: shared weights; else B rows of frame f start at f * b_rows_per_frame
                                     //    (per-frame attention operands; requires single-frame tiles)
     // frame remap (dead-frame elimination): tile frame tf reads / adds the residual of source frame

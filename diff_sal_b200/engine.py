@@ -110,6 +110,20 @@ def _bind(lib):
     lib.dsb_vggish_forward_feat.restype = ci
     lib.dsb_vggish_last_launch_count.argtypes = [vp]
     lib.dsb_vggish_last_launch_count.restype = ci
+    lib.dsb_mvit_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.dsb_mvit_create.restype = ci
+    lib.dsb_mvit_destroy.argtypes = [vp]
+    lib.dsb_mvit_destroy.restype = None
+    lib.dsb_mvit_last_error.argtypes = [vp]
+    lib.dsb_mvit_last_error.restype = ctypes.c_char_p
+    lib.dsb_mvit_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.dsb_mvit_load_weight.restype = ci
+    lib.dsb_mvit_finalize.argtypes = [vp]
+    lib.dsb_mvit_finalize.restype = ci
+    lib.dsb_mvit_forward.argtypes = [vp, vp, ctypes.POINTER(vp), ci, vp]
+    lib.dsb_mvit_forward.restype = ci
+    lib.dsb_mvit_last_launch_count.argtypes = [vp]
+    lib.dsb_mvit_last_launch_count.restype = ci
     lib._dsb_bound = True
     return lib
 
@@ -459,3 +473,71 @@ class VggishEngine:
     @property
     def last_launch_count(self):
         return int(self.lib.dsb_vggish_last_launch_count(self._h))
+
+
+class MvitEngine:
+    """Handle of the MViTv2-S video encoder (dsb_mvit_*; models/mvit.py:796-1152)."""
+
+    SHAPES = [(768, 8, 7, 12), (384, 8, 14, 24), (192, 8, 28, 48), (96, 8, 56, 96)]
+
+    def __init__(self, max_batch=2, device=None):
+        if not torch.cuda.is_available():
+            raise DsbError("diff_sal_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _bind(_lib.lib())
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_batch = int(max_batch)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.dsb_mvit_create(self.max_batch, ctypes.byref(self._h))
+        if rc != 0:
+            raise DsbError("dsb_mvit_create failed with %d (needs an sm_100 GPU)" % rc)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dsb_mvit_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.dsb_mvit_last_error(self._h)
+            raise DsbError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def load_state_dict(self, state_dict, prefix=""):
+        with torch.cuda.device(self.device):
+            for key, val in state_dict.items():
+                if prefix:
+                    if not key.startswith(prefix):
+                        continue
+                    key = key[len(prefix):]
+                t = val.detach().to(dtype=torch.float32).contiguous()
+                shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                self._check(self.lib.dsb_mvit_load_weight(self._h, key.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()),
+                            "dsb_mvit_load_weight(%s)" % key)
+            self._check(self.lib.dsb_mvit_finalize(self._h), "dsb_mvit_finalize")
+
+    def forward(self, video):
+        """video [B, 3, 16, 224, 384] (or the loader's raw 4-D view [B*16, 3, 224, 384], mvit.py:1110-1111) -> the four
+        feature tensors, coarsest first, fp32 on this engine's device."""
+        if video.dim() == 4:
+            video = video.reshape(-1, video.shape[-3], 16, video.shape[-2], video.shape[-1])
+        if video.dim() != 5 or tuple(video.shape[1:]) != (3, 16, 224, 384):
+            raise DsbError("video must be [B, 3, 16, 224, 384], got %s" % (tuple(video.shape),))
+        B = video.shape[0]
+        if B < 1 or B > self.max_batch:
+            raise DsbError("batch %d outside [1, %d]" % (B, self.max_batch))
+        v = video.to(device=self.device, dtype=torch.float32).contiguous()
+        outs = [torch.empty((B,) + s, dtype=torch.float32, device=self.device) for s in self.SHAPES]
+        ptrs = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dsb_mvit_forward(self._h, ctypes.c_void_p(v.data_ptr()), ptrs, B, _stream()), "dsb_mvit_forward")
+        return outs
+
+    @property
+    def last_launch_count(self):
+        return int(self.lib.dsb_mvit_last_launch_count(self._h))

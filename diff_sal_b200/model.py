@@ -12,14 +12,14 @@ its sampling driver reaches them as ``model.module.forward_vggish`` / ``.visual_
 * or use ``VideoSaliencyModelB200`` below, the same container without the reference tree: same constructor arguments,
   same ``forward_vggish(audio)`` / ``forward(data, t)``.
 
-The video encoder (MViT) is not part of this package: ``visual_net`` may be any module returning the
-four feature tensors (e.g. the reference's ``MViT``); with ``visual_net=None`` the container draws random placeholder
-features exactly like the reference does (diff_model.py:105-111).
+``visual_net=dict(type="MViT", arch="small", out_scales=[0, 1, 2, 3])`` builds the B200 video encoder (``MViTB200``); with
+``visual_net=None`` the container draws random placeholder features exactly like the reference does (diff_model.py:105-111).
 """
 import torch
 import torch.nn as nn
 
 from .audio_attention import AudioAttnNetB200
+from .mvit import MViTB200
 from .salunet import SalUNetB200
 from .vggish import VGGishB200
 
@@ -55,10 +55,11 @@ OBJECT_REGISTRY = Registry("object")
 
 
 def register_b200_modules(registry, force=True):
-    """Registers the drop-in modules under the reference's class names (cfgs/audio_visual.py:34-82)."""
+    """Registers the drop-in modules under the reference's class names (cfgs/audio_visual.py:27-82)."""
     registry.register_module(name="SalUNet", force=force, module=SalUNetB200)
     registry.register_module(name="AudioAttnNet", force=force, module=AudioAttnNetB200)
     registry.register_module(name="VGGish", force=force, module=VGGishB200)
+    registry.register_module(name="MViT", force=force, module=MViTB200)
     return registry
 
 

@@ -202,6 +202,69 @@ def make_vggish_state_dict(seed=0, with_embeddings=False):
     return sd
 
 
+# (in_dims, out_dims, heads, stride_q, stride_kv, rel_pos length) of the 16 blocks of the reference's MViTv2-S
+# (models/mvit.py:898-903,1024-1066; rel_pos tables are sized for a square 56 x 56 token grid, :586-592)
+MVIT_BLOCKS = ([(96, 96, 1, 1, 8, 111), (96, 192, 2, 2, 4, 55), (192, 192, 2, 1, 4, 55), (192, 384, 4, 2, 2, 27)] +
+               [(384, 384, 4, 1, 2, 27)] * 10 + [(384, 768, 8, 2, 1, 27), (768, 768, 8, 1, 1, 13)])
+
+
+def mvit_state_dict_spec():
+    """(key, shape) of ``MViT(arch="small", out_scales=[0, 1, 2, 3])`` (models/mvit.py:796-1105) in registration order."""
+    spec = [("cls_token", (1, 1, 96)), ("patch_embed.projection.weight", (96, 3, 3, 7, 7)), ("patch_embed.projection.bias", (96,))]
+    for i, (cin, cout, heads, sq, skv, rel) in enumerate(MVIT_BLOCKS):
+        b = "blocks.%d." % i
+        spec += [(b + "norm1.weight", (cin,)), (b + "norm1.bias", (cin,)),
+                 (b + "attn.rel_pos_h", (rel, 96)), (b + "attn.rel_pos_w", (rel, 96)), (b + "attn.rel_pos_t", (15, 96)),
+                 (b + "attn.qkv.weight", (3 * cout, cin)), (b + "attn.qkv.bias", (3 * cout,)),
+                 (b + "attn.proj.weight", (cout, cout)), (b + "attn.proj.bias", (cout,))]
+        for n in ("q", "k", "v"):
+            spec += [(b + "attn.pool_%s.weight" % n, (96, 1, 3, 3, 3)), (b + "attn.norm_%s.weight" % n, (96,)),
+                     (b + "attn.norm_%s.bias" % n, (96,))]
+        spec += [(b + "norm2.weight", (cout,)), (b + "norm2.bias", (cout,)),
+                 (b + "mlp.fc1.weight", (4 * cout, cout)), (b + "mlp.fc1.bias", (4 * cout,)),
+                 (b + "mlp.fc2.weight", (cout, 4 * cout)), (b + "mlp.fc2.bias", (cout,))]
+        if cin != cout:
+            spec += [(b + "proj.weight", (cout, cin)), (b + "proj.bias", (cout,))]
+    for s_, c in enumerate((96, 192, 384, 768)):
+        spec += [("norm%d.weight" % s_, (c,)), ("norm%d.bias" % s_, (c,))]
+    return spec
+
+
+def make_mvit_state_dict(seed=0):
+    """'wide' random weights for the video encoder: fan-in scaled linears / convolutions, non-zero biases, randomised
+    LayerNorm affines, O(0.3) relative-position tables and depthwise pooling taps (so that every term matters)."""
+    g = torch.Generator().manual_seed(seed + 1013)
+    sd = {}
+    for key, shape in mvit_state_dict_spec():
+        leaf = key.rsplit(".", 1)[-1]
+        if key == "cls_token":
+            v = 0.5 * torch.randn(shape, generator=g)
+        elif "rel_pos" in key:
+            v = 0.3 * torch.randn(shape, generator=g)
+        elif "norm" in key and len(shape) == 1:
+            v = (1.0 + 0.2 * torch.randn(shape, generator=g)) if leaf == "weight" else 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "bias":
+            v = 0.05 * torch.randn(shape, generator=g)
+        elif ".pool_" in key:
+            v = torch.randn(shape, generator=g) * 0.25
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            v = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+        sd[key] = v.float().contiguous()
+    return sd
+
+
+def make_video_input(batch, seed=7321, hw=IMG_HW):
+    """ImageNet-normalised-range video clips as the loader hands them to the video encoder: [B, 3, 16, 224, 384]."""
+    out = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed + i)
+        out.append(torch.randn((1, 3, 16) + tuple(hw), generator=g))
+    return torch.cat(out, 0)
+
+
 def make_audio_input(batch, seed=4321, frames=9, hw=(112, 192)):
     """Log-mel-like audio patches as the loader hands them to forward_vggish (datasets/saliency_db.py:303-305,457):
     [B, 1, 9, 112, 192], values ~ N(-2, 1.5)."""

@@ -29,6 +29,8 @@
  *        (models/diff_model.py:70-81,97-113) -- SURVEY.md 8f row N1
  *   dsb_vggish_create / dsb_vggish_load_weight / dsb_vggish_finalize / dsb_vggish_forward_feat
  *        VGGish.__init__ + load_state_dict + forward_feat (models/vggish.py:87-124) -- SURVEY.md 8f row N2 (audio half)
+ *   dsb_mvit_create / dsb_mvit_load_weight / dsb_mvit_finalize / dsb_mvit_forward
+ *        MViT.__init__ + load_state_dict + forward (models/mvit.py:796-1152) -- SURVEY.md 8f row N2 (video half)
  *   dsb_metrics
  *        metrics.metrics.{CC, SIM, NSS, AUC_Judd} (metrics/metrics.py:7-64,178-252) -- SURVEY.md 8f row N3
  *   dsb_val_losses
@@ -211,6 +213,21 @@ int dsb_vggish_load_weight(dsb_vggish* h, const char* ref_key, const void* data,
 int dsb_vggish_finalize(dsb_vggish* h);
 int dsb_vggish_forward_feat(dsb_vggish* h, const float* audio, float* out, int frames, void* stream);
 int dsb_vggish_last_launch_count(const dsb_vggish* h);
+
+/* ---- MViTv2-S video encoder (models/mvit.py:796-1152 `MViT(arch="small", out_scales=[0,1,2,3])`, called once per clip as
+ * `visual_net(imgs)` by VideoSaliencyModel.forward / DiffusionTrainer.sample_image, models/diff_model.py:103-104,
+ * diffusion_trainer.py:559-562) -- SURVEY.md 8f row N2, video half --------------------------------------------------------
+ * Weight keys are MViT.state_dict()'s ("blocks.3.attn.rel_pos_h", ...; 401 tensors).  video: device fp32
+ * [B][3][16][224][384] (the only geometry accepted); out[0..3]: device fp32 feature tensors in the order the reference
+ * returns them: [B,768,8,7,12], [B,384,8,14,24], [B,192,8,28,48], [B,96,8,56,96]. */
+typedef struct dsb_mvit dsb_mvit;
+int dsb_mvit_create(int max_batch, dsb_mvit** out);
+void dsb_mvit_destroy(dsb_mvit* h);
+const char* dsb_mvit_last_error(const dsb_mvit* h);
+int dsb_mvit_load_weight(dsb_mvit* h, const char* ref_key, const void* data, const int64_t* shape, int ndim);
+int dsb_mvit_finalize(dsb_mvit* h);
+int dsb_mvit_forward(dsb_mvit* h, const float* video, float* const out[4], int B, void* stream);
+int dsb_mvit_last_launch_count(const dsb_mvit* h);
 
 /* ---- single-kernel test entry (tests/test_kernels_gpu.py) ------------------------------------------------- */
 int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int dilation, int T, int kt, const void* A,

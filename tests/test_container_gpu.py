@@ -215,3 +215,40 @@ def test_product_container_matches_reference_container(ref, container):
     assert torch.equal(ya, yb)
     for sub in (m.decoder_net, m.spatiotemp_net, m.audio_net):
         sub.engine.close()
+
+
+def test_full_model_video_and_audio_in_map_out(ref):
+    """The reference's VideoSaliencyModel with ALL four sub-networks built from the B200 classes (MViTB200, VGGishB200,
+    AudioAttnNetB200, SalUNetB200): raw video + log-mel audio in, map out, against the fp32 oracle chain."""
+    from diff_sal_b200.audio_attention import AudioAttnNetB200
+    from diff_sal_b200.mvit import MViTB200
+    from diff_sal_b200.salunet import SalUNetB200
+    from diff_sal_b200.vggish import VGGishB200
+    from oracle import audio_attention, mvit, salunet, samplers, vggish
+    model = ref.VideoSaliencyModel(
+        channel_list=None,
+        visual_net=dict(type=MViTB200, arch="small", pretrained=None, out_scales=[0, 1, 2, 3]),
+        spatiotemp_net=dict(type=AudioAttnNetB200, **audio_cfg()),
+        audio_net=dict(type=VGGishB200, pretrained=False),
+        decoder_net=dict(type=SalUNetB200, **decoder_cfg()))
+    wrapped = FakeDDP(model).cuda().eval()
+    ck = checkpoint()
+    for k, v in synth.make_mvit_state_dict().items():
+        ck["module.visual_net." + k] = v
+    msg = wrapped.load_state_dict(ck, strict=False)
+    assert all(k.startswith("module.fc.") for k in msg.missing_keys) and not msg.unexpected_keys
+    video, audio = synth.make_video_input(1), synth.make_audio_input(1)
+    x, _, _ = synth.make_inputs(1, audio=False)
+    t = torch.tensor([500.0])
+    # the loader hands the clip over as [B*16, 3, H, W] (diffusion_trainer.py:101-105; MViT.forward re-views it)
+    data = {"img": video.reshape(-1, 3, 224, 384).cuda(), "input": x.cuda(), "audio": audio.cuda()}
+    with torch.no_grad():
+        y = wrapped.module(data, t.cuda()).cpu()
+    vis = mvit.forward(synth.make_mvit_state_dict(), video)
+    feat = vggish.forward_feat(synth.make_vggish_state_dict(), audio.view(-1, 1, 112, 192))
+    feat = feat.reshape(1, 9, 512, 7, 12).permute(0, 2, 1, 3, 4).contiguous()
+    emb = audio_attention.forward(synth.make_audio_attn_state_dict(), feat)
+    refy = salunet.forward(synth.make_state_dict("wide"), x, t, vis, emb)
+    for m in (model.decoder_net, model.spatiotemp_net, model.audio_net, model.visual_net):
+        m.engine.close()
+    assert (samplers.minmax_map(y) - samplers.minmax_map(refy)).abs().max().item() <= 1e-2

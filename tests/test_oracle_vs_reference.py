@@ -295,3 +295,28 @@ def test_validation_losses_match_reference():
         assert set(ra) == set(mb)
         for k in ra:
             assert abs(float(ra[k]) - float(mb[k])) <= 2e-6 * max(1.0, abs(float(ra[k]))), k
+
+
+def test_mvit_matches_reference():
+    """SURVEY 8f row N2 (video half): MViTv2-S (models/mvit.py:796-1152) -- key list, shapes, and one clip through the
+    oracle restatement against the unmodified reference on seeded 'wide' weights."""
+    from oracle import mvit
+    ref_loader.load()
+    from models.mvit import MViT
+    net = MViT(arch="small", pretrained=None, out_scales=[0, 1, 2, 3]).eval()
+    ref_sd = net.state_dict()
+    spec = synth.mvit_state_dict_spec()
+    assert [k for k, _ in spec] == list(ref_sd.keys())
+    for k, s in spec:
+        assert tuple(ref_sd[k].shape) == tuple(s), k
+    sd = synth.make_mvit_state_dict()
+    net.load_state_dict(sd, strict=True)
+    x = synth.make_video_input(1)
+    with torch.no_grad():
+        ref = net(x)
+        raw4d = net(x.reshape(-1, 3, 224, 384))              # the loader's raw 4-D view (mvit.py:1110-1111)
+    mine = mvit.forward(sd, x)
+    assert [tuple(a.shape) for a in mine] == [(1, 768, 8, 7, 12), (1, 384, 8, 14, 24), (1, 192, 8, 28, 48), (1, 96, 8, 56, 96)]
+    for a, b, c in zip(ref, mine, raw4d):
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item())
+        assert torch.equal(a, c)
