@@ -175,55 +175,63 @@ __global__ void __launch_bounds__(256) mvit_softmax_kernel(const float* __restri
                                                           int Lk, int Lpad, int qh, int qw, int kh, int kw,
                                                           const float* __restrict__ Rt, const float* __restrict__ Rh,
                                                           const float* __restrict__ Rw, bf16* __restrict__ P) {
+    extern __shared__ uint32_t kidx[];                     // [Lk]: key k -> (kt | kh << 8 | kw << 16) offsets into rel[]; cls: none
     __shared__ float rel[8][64];                           // per warp: kt (8) | kh (<= 14) | kw (<= 24)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int q = blockIdx.x * 8 + wid, f = blockIdx.y;
+    // the key -> (t, y, x) decode is the same for every query row: done once per block (8 rows), not per element
+    for (int k = threadIdx.x; k < Lk; k += 256) {
+        uint32_t v = 0xFFFFFFFFu;
+        if (k > 0) {
+            const int r = k - 1, t = r / (kh * kw), y = (r / kw) % kh, x = r % kw;
+            v = (uint32_t)t | ((uint32_t)(kT + y) << 8) | ((uint32_t)(kT + kh + x) << 16);
+        }
+        kidx[k] = v;
+    }
+    __syncthreads();
     if (q >= Lq) return;
     const float* row = sc + ((size_t)f * Lq + q) * Lpad;
     bf16* prow = P + ((size_t)f * Lq + q) * Lpad;
     const int nrel = kT + kh + kw;
-    if (q > 0) {
+    const bool biased = q > 0;
+    if (biased) {
         const int r = q - 1, t = r / (qh * qw), y = (r / qw) % qh, x = r % qw;
-        const float* qv = qres + ((size_t)f * Lq + q) * 96;
+        const float4* qv = reinterpret_cast<const float4*>(qres + ((size_t)f * Lq + q) * 96);
         for (int j = lane; j < nrel; j += 32) {
             const float* R = j < kT ? Rt + ((size_t)t * kT + j) * 96
                                     : (j < kT + kh ? Rh + ((size_t)y * kh + (j - kT)) * 96 : Rw + ((size_t)x * kw + (j - kT - kh)) * 96);
+            const float4* R4 = reinterpret_cast<const float4*>(R);
             float a = 0.0f;
-#pragma unroll 8
-            for (int c = 0; c < 96; ++c) a = fmaf(qv[c], __ldg(R + c), a);
+#pragma unroll 6
+            for (int c = 0; c < 24; ++c) {
+                const float4 u = qv[c], w = __ldg(R4 + c);
+                a = fmaf(u.x, w.x, a); a = fmaf(u.y, w.y, a); a = fmaf(u.z, w.z, a); a = fmaf(u.w, w.w, a);
+            }
             rel[wid][j] = a;
         }
     }
     __syncwarp();
-    float mx = -INFINITY;
+    const float* rl = rel[wid];
+    // pass 1: online maximum / sum
+    float mx = -INFINITY, sum = 0.0f;
     for (int k = lane; k < Lk; k += 32) {
         float v = row[k];
-        if (q > 0 && k > 0) {
-            const int r = k - 1, t = r / (kh * kw), y = (r / kw) % kh, x = r % kw;
-            v += rel[wid][t] + rel[wid][kT + y] + rel[wid][kT + kh + x];
-        }
-        mx = fmaxf(mx, v);
-    }
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int k = lane; k < Lk; k += 32) {
-        float v = row[k];
-        if (q > 0 && k > 0) {
-            const int r = k - 1, t = r / (kh * kw), y = (r / kw) % kh, x = r % kw;
-            v += rel[wid][t] + rel[wid][kT + y] + rel[wid][kT + kh + x];
-        }
+        const uint32_t id = kidx[k];
+        if (biased && id != 0xFFFFFFFFu) v += rl[id & 255u] + rl[(id >> 8) & 255u] + rl[id >> 16];
+        if (v > mx) { sum *= __expf(mx - v); mx = v; }
         sum += __expf(v - mx);
     }
-    const float inv = 1.0f / warp_sum(sum);
+    const float gmx = warp_max(mx);
+    sum *= __expf(mx - gmx);                                // lanes without any element hold mx = -inf, sum = 0 -> 0 * 0
+    const float inv = 1.0f / warp_sum(mx == -INFINITY ? 0.0f : sum);
+    // pass 2: probabilities (the key padding is written as zeros)
     for (int k = lane; k < Lpad; k += 32) {
         float pv = 0.0f;
         if (k < Lk) {
             float v = row[k];
-            if (q > 0 && k > 0) {
-                const int r = k - 1, t = r / (kh * kw), y = (r / kw) % kh, x = r % kw;
-                v += rel[wid][t] + rel[wid][kT + y] + rel[wid][kT + kh + x];
-            }
-            pv = __expf(v - mx) * inv;
+            const uint32_t id = kidx[k];
+            if (biased && id != 0xFFFFFFFFu) v += rl[id & 255u] + rl[(id >> 8) & 255u] + rl[id >> 16];
+            pv = __expf(v - gmx) * inv;
         }
         prow[k] = h16(pv);
     }
@@ -600,7 +608,7 @@ extern "C" int dsb_mvit_forward(dsb_mvit* h, const float* video, float* const ou
             op.out_f32 = h->sc;
             if (int r = mrun(h, op, "attention scores", i, s)) return r;
         }
-        mvit_softmax_kernel<<<dim3((Lq + 7) / 8, FH), 256, 0, s>>>(h->sc, h->qres, Lq, Lk, Lpad, qh, qw, kh, kw, h->wf[a + ".Rt"],
+        mvit_softmax_kernel<<<dim3((Lq + 7) / 8, FH), 256, (size_t)Lk * sizeof(uint32_t), s>>>(h->sc, h->qres, Lq, Lk, Lpad, qh, qw, kh, kw, h->wf[a + ".Rt"],
                                                                    h->wf[a + ".Rh"], h->wf[a + ".Rw"], h->P);
         MVIT_KERNEL("relative-position softmax");
         // ---- out[:, head] = P_head . V_head + q_head (residual pooling, cls row excluded)  (mvit.py:634-646)

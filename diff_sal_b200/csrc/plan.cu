@@ -104,6 +104,7 @@ struct dsb_handle {
     // Independent branches of an evaluation (the q / k / v token producers of a block) run on side streams:
     // kind 0 = launch on stream prog_stream[i]; 1 = record event prog_ev[i] on that stream; 2 = that stream waits for it
     std::vector<int> prog_kind, prog_stream, prog_ev;
+    std::vector<int> prog_pdl;                    // per launch: programmatic-dependent-launch mode of its zone (0 off, 2 all kernels)
     int prog_launches = 0;
     std::vector<int> profile_idx;
     cudaStream_t side[2] = {nullptr, nullptr};
@@ -288,8 +289,16 @@ struct Builder {
     int err = 0;
 
     int cur = 0;                                  // stream index subsequent launches go to (0 = caller's stream)
+    // Programmatic dependent launch is applied by ZONE: only in single-stream stretches of the program (nothing runs on the
+    // side streams), where a kernel that is scheduled early and waits in pdl_wait() cannot take SMs away from another
+    // stream.  Measured whole-program PDL was a loss; DSB_PDL_ZONES is a bit mask for experiments:
+    // 1 encoder, 2 up-embedding, 4 token path after the K / V join, 8 multi-scale head.
+    int zones = [] { const char* e = getenv("DSB_PDL_ZONES"); return e ? atoi(e) : 0; }();
+    int zone = 0;                                 // PDL mode of the launches added from now on (0 or 2)
+    void set_zone(int bit) { zone = (zones & bit) ? 2 : 0; }
 
     void meta(int kind, int ev) {
+        h->prog_pdl.push_back(cur == 0 ? zone : 0);
         h->prog_kind.push_back(kind);
         h->prog_stream.push_back(cur);
         h->prog_ev.push_back(ev);
@@ -346,6 +355,7 @@ int build_program(dsb_handle* h) {
     h->prog_flops.clear();
     h->prog_bytes.clear();
     h->prog_kind.clear();
+    h->prog_pdl.clear();
     h->prog_stream.clear();
     h->prog_ev.clear();
     h->prog_launches = 0;
@@ -373,6 +383,7 @@ int build_program(dsb_handle* h) {
         }
         float* tp[3] = {h->tp[0], h->tp[1], h->tp[2]};
         // the timestep MLP only feeds the conv1 epilogues: it runs beside the stem / first GroupNorm on a side stream
+        b.set_zone(1);
         b.depend(4, 0, 1);
         b.cur = 1;
         b.add([h, tw, tp, B](cudaStream_t s) { return temb_launch(h->cur_t, B, tw, tp, s); }, "temb");
@@ -449,6 +460,7 @@ int build_program(dsb_handle* h) {
         const int C = kStageC[i], H = kStageH[i], Wd = kStageW[i], HW = H * Wd, sk = kStageS[i];
         const std::string st = stage_key(i), bk = st + "blocks.0.";
         const float* Xi;
+        b.set_zone(2);
         if (i == 0) {
             Xi = h->back[0];
         } else {
@@ -474,6 +486,7 @@ int build_program(dsb_handle* h) {
             }
             Xi = h->X[i];
         }
+        b.set_zone(0);                                      // Q / K / V producers: three streams
         const long tokens = (long)F * HW;
         // Stage 3 is the last stage and ReduceTemp reads frames 0..4 only (sal_unet.py:449-454,469-481): its
         // attention / MLP for frames 5..8 of every clip is dead work and is skipped (the gate still sees all 9).
@@ -564,6 +577,7 @@ int build_program(dsb_handle* h) {
             // kernel does  q_ln . K'^T -> +bias -> per-head softmax -> P . V'' -> + proj bias + residual
             b.depend(2, 1, 0);                                  // join V
             b.depend(3, 2, 0);                                  // join K
+            b.set_zone(4);                                      // from the K / V join to ReduceTemp: one stream
             const float *Kp = h->Kp, *Vp = h->Vp;
             const float *wqf = W(h, bk + "attn.proj_q.weight"), *bqf = W(h, bk + "attn.proj_q.bias");
             const float* wpT = WF(bk + "attn.proj.weight.T");
@@ -591,6 +605,7 @@ int build_program(dsb_handle* h) {
         }
         b.depend(2, 1, 0);                                  // join V
         b.depend(3, 2, 0);                                  // join K
+        b.set_zone(4);                                      // from the K / V join to ReduceTemp: one stream
         {
             const float *Kp = h->Kp, *Vp = h->Vp;
             bf16 *KB = h->KB, *VB = h->VB;
@@ -662,6 +677,7 @@ int build_program(dsb_handle* h) {
     }
 
     // ------------------------------------------------------------ multi-scale head (sal_unet.py:482-489,320-327)
+    b.set_zone(8);
     {
         const float* rr[4] = {h->r[0], h->r[1], h->r[2], h->r[3]};
         bf16* S = h->S;
@@ -694,7 +710,10 @@ int run_program(dsb_handle* h, cudaStream_t s, bool serial = false) {
         if (kind == 0) {
             pdl_allow_next() = !after_wait[si] || serial;
             after_wait[si] = false;
+            const int keep = pdl_mode();
+            if (h->prog_pdl[i] > keep) pdl_mode() = h->prog_pdl[i];
             r = h->prog[i](st);
+            pdl_mode() = keep;
             pdl_allow_next() = true;
         }
         else if (serial) continue;
