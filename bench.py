@@ -417,6 +417,9 @@ def run_b200(args):
             "metric": "saliency clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "dtype_note": "16-bit tensor-core operands, fp32 accumulate / epilogues / residual streams / norm statistics; bf16 "
+                          "operands everywhere except the two GEMMs of the output-head chain (ReduceTemp, mt_proj), which take "
+                          "fp16 operands at the same kind::f16 rate (DESIGN.md section 2, precision policy)",
             "config": {"workload": WORKLOAD, "clips_per_gpu": B, "nfe": NFE, "parallelism": "clip-sharded x%d" % world,
                        "l2": "two input sets alternate between steps and the per-evaluation working set (~2 GB) exceeds "
                              "the 126 MB L2; no explicit flush", "cuda_graph": True},
