@@ -5,7 +5,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffsal_b200.so")
+TEST_LIB_PATH = os.path.join(_HERE, "libdiffsal_b200_test.so")
 _lib = None
+_test_lib = None
 
 
 class LibraryMissing(RuntimeError):
@@ -19,8 +21,19 @@ def lib():
             raise LibraryMissing(
                 "%s not built: run `python -m diff_sal_b200.build` (or __graft_entry__.build()). "
                 "There is no CPU / PyTorch fallback for the denoiser." % LIB_PATH)
-        _lib = ctypes.CDLL(LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     return _lib
+
+
+def test_lib():
+    """The per-kernel test entries (include/diffsal_b200_test.h); used by tests/ only, never by the product path."""
+    global _test_lib
+    if _test_lib is None:
+        lib()
+        if not os.path.exists(TEST_LIB_PATH):
+            raise LibraryMissing("%s not built: run `python -m diff_sal_b200.build`" % TEST_LIB_PATH)
+        _test_lib = ctypes.CDLL(TEST_LIB_PATH)
+    return _test_lib
 
 
 def ptr(t):

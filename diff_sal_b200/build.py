@@ -10,6 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffsal_b200.so")
+TEST_LIB = os.path.join(HERE, "libdiffsal_b200_test.so")       # per-kernel test entries: NOT part of the product library
+TEST_SRCS = ("test_api.cu", "probe.cu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -20,7 +22,7 @@ def _flags():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(TEST_LIB):
         return True
     t = os.path.getmtime(LIB)
     srcs = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
@@ -52,8 +54,12 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs
-    subprocess.check_call(cmd)
+    test_objs = [o for o in objs if os.path.basename(o)[:-2] + ".cu" in TEST_SRCS]
+    prod_objs = [o for o in objs if o not in test_objs]
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + prod_objs)
+    # the test library resolves the internal launchers (dsb::conv_lower ...) from the product library next to it
+    subprocess.check_call([NVCC, "-shared", "-o", TEST_LIB] + test_objs +
+                          ["-L" + HERE, "-l:libdiffsal_b200.so", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     return LIB
 
 

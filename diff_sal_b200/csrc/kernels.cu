@@ -1441,6 +1441,126 @@ int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int
     DSB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------ projections folded into K / V
+// The 18 keys / values of a frame only ever meet the queries through  q_ln Wq^T K^T  and  P V Wp^T  (attention.py:97-113), so
+// the query projection folds into the keys and the output projection into the values, and -- because K = k_ln Wk^T + bk and
+// V = v_ln Wv^T + bv are themselves linear -- both fold into the WEIGHTS once per weight set:
+//   K1[h*18+j][c] = scale sum_{c' in head h} K[j,c'] Wq[c',c] = k_ln[j,:] . MK_h[c,:] + cK_h[c]
+//   sb[h*18+j]    = scale sum_{c' in head h} K[j,c'] bq[c']   = k_ln[j,:] . mb_h[:]   + cb_h
+//   V2[c][h*18+j] = sum_{c' in head h} Wp[c,c'] V[j,c']       = v_ln[j,:] . MV_h[c,:] + cV_h[c]
+// with MK_h = scale Wq_h^T Wk_h, MV_h = Wp[:,h] Wv_h (C x C per head).  One GEMM per branch (N = 2C) then yields the
+// per-frame operands of the score and P.V products directly; proj_q, proj and the per-evaluation fold kernel disappear.
+// grid (C/16, C/16, 2 heads), block (16, 16): out[h][c][e]
+__global__ void __launch_bounds__(256) fold_weights_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
+                                                          const float* __restrict__ wp, const float* __restrict__ wv, int C,
+                                                          float scale, float* __restrict__ MK, float* __restrict__ MV) {
+    const int e = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y, h = blockIdx.z;
+    const int d = C >> 1, d0 = h * d;
+    float ak = 0.0f, av = 0.0f;
+    for (int i = 0; i < d; ++i) {
+        const int cp = d0 + i;
+        ak = fmaf(wq[(size_t)cp * C + c], wk[(size_t)cp * C + e], ak);
+        av = fmaf(wp[(size_t)c * C + cp], wv[(size_t)cp * C + e], av);
+    }
+    MK[((size_t)h * C + c) * C + e] = ak * scale;
+    MV[((size_t)h * C + c) * C + e] = av;
+}
+
+// cK[h*C+c] = scale sum Wq[c',c] bk[c'];  cV[h*C+c] = sum Wp[c,c'] bv[c'];  mb[h*C+e] = scale sum bq[c'] Wk[c',e];
+// cb[h] = scale sum bq[c'] bk[c']          (sums over c' in head h)
+__global__ void __launch_bounds__(256) fold_bias_kernel(const float* __restrict__ wq, const float* __restrict__ bq,
+                                                       const float* __restrict__ wk, const float* __restrict__ bk,
+                                                       const float* __restrict__ wp, const float* __restrict__ bv, int C, float scale,
+                                                       float* __restrict__ cK, float* __restrict__ cV, float* __restrict__ mb,
+                                                       float* __restrict__ cb) {
+    const int c = blockIdx.x * 256 + threadIdx.x, h = blockIdx.y;
+    const int d = C >> 1, d0 = h * d;
+    if (c < C) {
+        float a = 0.0f, v = 0.0f, m = 0.0f;
+        for (int i = 0; i < d; ++i) {
+            const int cp = d0 + i;
+            a = fmaf(wq[(size_t)cp * C + c], bk[cp], a);
+            v = fmaf(wp[(size_t)c * C + cp], bv[cp], v);
+            m = fmaf(bq[cp], wk[(size_t)cp * C + c], m);
+        }
+        cK[h * C + c] = a * scale;
+        cV[h * C + c] = v;
+        mb[h * C + c] = m * scale;
+    }
+    if (c == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < d; ++i) t = fmaf(bq[d0 + i], bk[d0 + i], t);
+        cb[h] = t * scale;
+    }
+}
+
+int fold_weights_launch(const float* wq, const float* bq, const float* wk, const float* bk, const float* wp, const float* wv,
+                        const float* bv, int C, float scale, float* MK, float* MV, float* cK, float* cV, float* mb, float* cb,
+                        cudaStream_t s) {
+    if (C % 16) return -38;
+    fold_weights_kernel<<<dim3(C / 16, C / 16, 2), dim3(16, 16), 0, s>>>(wq, wk, wp, wv, C, scale, MK, MV);
+    fold_bias_kernel<<<dim3((C + 255) / 256, 2), 256, 0, s>>>(wq, bq, wk, bk, wp, bv, C, scale, cK, cV, mb, cb);
+    DSB_LAUNCH_CHECK();
+}
+
+// Per frame: the folded GEMM outputs Kf / Vf [F*18][2C] fp32 (column h*C + c) -> the operand layouts of the score and P.V
+// products:  K1 bf16 [F][R][C] (row h*18+j; rows 36..R-1 zero), sb fp32 [F][R], V2 bf16 [F][C][64] (column h*18+j; 36..63 zero)
+__global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ Kf, const float* __restrict__ Vf,
+                                                     const bf16* __restrict__ k_ln, const float* __restrict__ mb,
+                                                     const float* __restrict__ cb, int C, int R, int T, int tmax,
+                                                     bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
+    pdl_trigger();
+    pdl_wait();
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (f % T >= tmax) return;
+    const int c8n = C >> 3, ld = 2 * C;
+    for (int it = tid; it < R * c8n; it += 256) {
+        const int r = it / c8n, c = (it - r * c8n) * 8;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (r < 36) {
+            const float4* src = reinterpret_cast<const float4*>(Kf + ((size_t)f * 18 + r % 18) * ld + (r / 18) * C + c);
+            const float4 a = src[0], b = src[1];
+            o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        }
+        reinterpret_cast<uint4*>(K1 + ((size_t)f * R + r) * C + c)[0] = o;
+    }
+    {   // folded score bias: one warp per key row
+        const int lane = tid & 31;
+        for (int r = tid >> 5; r < R; r += 8) {
+            float a = 0.0f;
+            if (r < 36) {
+                const bf16* kr = k_ln + ((size_t)f * 18 + r % 18) * C;
+                const float* m = mb + (r / 18) * C;
+                for (int c = lane; c < C; c += 32) a = fmaf(__bfloat162float(kr[c]), __ldg(m + c), a);
+                a = warp_sum(a) + __ldg(cb + r / 18);
+            }
+            if (lane == 0) sb[(size_t)f * R + r] = a;
+        }
+    }
+    for (int c = tid; c < C; c += 256) {
+        uint32_t w[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) w[k] = 0u;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float v0 = Vf[((size_t)f * 18 + 2 * k) * ld + hh * C + c], v1 = Vf[((size_t)f * 18 + 2 * k + 1) * ld + hh * C + c];
+                w[hh * 9 + k] = pack_bf16x2(v0, v1);
+            }
+        uint4* dst = reinterpret_cast<uint4*>(V2 + ((size_t)f * C + c) * 64);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+}
+
+int kv_pack_launch(const float* Kf, const float* Vf, const bf16* k_ln, const float* mb, const float* cb, int F, int C, int R,
+                   int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s) {
+    if (C % 8 || R < 36) return -38;
+    DSB_PDL_LAUNCH(kv_pack_kernel, F, 256, 0, s, Kf, Vf, k_ln, mb, cb, C, R, T, tmax, K1, sb, V2);
+    DSB_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------ attention operands
 __global__ void __launch_bounds__(256) attn_operands_kernel(const float* __restrict__ kp, const float* __restrict__ vp,
                                                            int C, float scale, bf16* __restrict__ KB,

@@ -81,6 +81,15 @@ int kpool_av_launch(const float* g, const float* a_cm, int B, int T, int H, int 
 int attn_operands_launch(const float* kp, const float* vp, int F, int C, float scale, bf16* KB, bf16* VB,
                          cudaStream_t s);
 
+// query / output projections folded into the key / value projection WEIGHTS (once per weight set; see kernels.cu):
+// MK, MV fp32 [2][C][C] (row h*C + c, K-major), cK, cV, mb fp32 [2*C], cb fp32 [2]
+int fold_weights_launch(const float* wq, const float* bq, const float* wk, const float* bk, const float* wp, const float* wv,
+                        const float* bv, int C, float scale, float* MK, float* MV, float* cK, float* cV, float* mb, float* cb,
+                        cudaStream_t s);
+// folded GEMM outputs Kf / Vf [F*18][2C] -> K1 bf16 [F][R][C], sb fp32 [F][R], V2 bf16 [F][C][64] (R = 48 or 64 key rows)
+int kv_pack_launch(const float* Kf, const float* Vf, const bf16* k_ln, const float* mb, const float* cb, int F, int C, int R,
+                   int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s);
+
 // folded per-frame attention operands for the fused attention chain (Wq folded into K, Wp into V; see kernels.cu)
 int attn_fold_launch(const float* kp, const float* vp, const float* wq, const float* bq, const float* wpT, int F, int C,
                      float scale, int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s);

@@ -176,6 +176,9 @@ const float* W(dsb_handle* h, const std::string& key) {
 }
 
 // ------------------------------------------------------------------------------------------ finalize helpers
+// query / output projections folded into the K / V projection weights (DSB_FOLD_PROJ=0: the separate-GEMM form)
+static const bool kFoldProj = [] { const char* e = getenv("DSB_FOLD_PROJ"); return !(e && e[0] == '0'); }();
+
 int pack_gemm_weight(dsb_handle* h, const std::string& key, int N, int Cin, int taps, int f16 = 0) {
     const Weight* w = find_w(h, key);
     if (!w) return fail(h, DSB_ERR_WEIGHT, "missing weight '%s'", key.c_str());
@@ -256,8 +259,8 @@ int alloc_workspace(dsb_handle* h) {
     if (int r = dev_alloc(h, &h->Qp, F * kMaxFrame)) return r;
     if (int r = dev_alloc(h, &h->k_ln, F * 18 * 768)) return r;
     if (int r = dev_alloc(h, &h->v_ln, F * 18 * 768)) return r;
-    if (int r = dev_alloc(h, &h->Kp, F * 18 * 768)) return r;
-    if (int r = dev_alloc(h, &h->Vp, F * 18 * 768)) return r;
+    if (int r = dev_alloc(h, &h->Kp, F * 18 * 1536)) return r;      // folded projections: [F*18][2C]
+    if (int r = dev_alloc(h, &h->Vp, F * 18 * 1536)) return r;
     if (int r = dev_alloc(h, &h->KB, F * 48 * 768)) return r;
     if (int r = dev_alloc(h, &h->VB, F * 768 * 64)) return r;
     if (int r = dev_alloc(h, &h->P, F * 5376 * 64)) return r;
@@ -501,6 +504,15 @@ int build_program(dsb_handle* h) {
             return op;
         };
         float2* stats = h->lnstats;
+        // K / V projections; with the query / output projections folded into their weights (kFoldProj) N = 2C and the
+        // output is already "keys seen through Wq" / "values seen through Wp" per head
+        auto kv_proj = [&](const char* which, const bf16* A_, float* out_) {
+            const std::string w = bk + (kFoldProj ? std::string("attn.fold_") + which : std::string("attn.proj_") + which);
+            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, kFoldProj ? 2 * C : C, A_, WP(w + ".weight"));
+            op.shift = kFoldProj ? WF(w + ".shift") : W(h, w + ".bias");
+            op.out_f32 = out_;
+            b.conv(op, which[0] == 'k' ? "attn.proj_k" : "attn.proj_v", 2.0 * (double)F * 18 * C * C);
+        };
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
         bf16 *q_ln = h->q_ln, *k_ln = h->k_ln, *v_ln = h->v_ln;
         const float *wq = WF(bk + "attn.conv_proj_q.conv.weight"), *wk = WF(bk + "attn.conv_proj_k.conv.weight"),
@@ -522,9 +534,7 @@ int build_program(dsb_handle* h) {
                 float* gate = h->gate;
                 b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
                 b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
-                ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
-                op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
-                b.conv(op, "attn.proj_k");
+                kv_proj("k", k_ln, h->Kp);
             }
             b.cur = 0;
             const float *wvg = WF(bk + "attn.conv_proj_v.wvg"), *wvbs = WF(bk + "attn.conv_proj_v.wvbs");
@@ -532,11 +542,7 @@ int build_program(dsb_handle* h) {
                   "qv_tile", (double)tokens * C * 6.0 * live);
             b.depend(1, 0, 1);                              // V tokens ready -> their projection runs on stream 1
             b.cur = 1;
-            {
-                ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
-                op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
-                b.conv(op, "attn.proj_v");
-            }
+            kv_proj("v", v_ln, h->Vp);
             b.cur = 0;
         } else {
         // three independent producers read the stage input: K (audio gate -> scramble -> pool, side stream 2),
@@ -555,18 +561,10 @@ int build_program(dsb_handle* h) {
         } else {
             b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
         }
-        {
-            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, k_ln, WP(bk + "attn.proj_k.weight"));
-            op.shift = W(h, bk + "attn.proj_k.bias"); op.out_f32 = h->Kp;
-            b.conv(op, "attn.proj_k");
-        }
+        kv_proj("k", k_ln, h->Kp);
         b.cur = 1;
         b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wv, vg, vb, v_ln, kT, tmax, s); }, "pool_ln_v", (double)tokens * C * 4.0 * live);
-        {
-            ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, C, v_ln, WP(bk + "attn.proj_v.weight"));
-            op.shift = W(h, bk + "attn.proj_v.bias"); op.out_f32 = h->Vp;
-            b.conv(op, "attn.proj_v");
-        }
+        kv_proj("v", v_ln, h->Vp);
         b.cur = 0;
         b.add([=](cudaStream_t s) { return q_dwln_launch(Xi, stats, F, H, Wd, C, ng, nb, wq, &qtb, qg, qb, q_ln, kT, tmax, s); }, "q_dwln", (double)tokens * C * 6.0 * live);
         }
@@ -584,7 +582,12 @@ int build_program(dsb_handle* h) {
             bf16 *K1 = h->K1, *V2 = h->V2;
             float* sb = h->sbias;
             const float scale = 1.0f / sqrtf((float)C);
-            b.add([=](cudaStream_t s) { return attn_fold_launch(Kp, Vp, wqf, bqf, wpT, F, C, scale, kT, tmax, K1, sb, V2, s); }, "attn_fold");
+            if (kFoldProj) {
+                const float *mb = WF(bk + "attn.fold_k.mb"), *cb = WF(bk + "attn.fold_k.cb");
+                b.add([=](cudaStream_t s) { return kv_pack_launch(Kp, Vp, k_ln, mb, cb, F, C, 64, kT, tmax, K1, sb, V2, s); }, "kv_pack");
+            } else {
+                b.add([=](cudaStream_t s) { return attn_fold_launch(Kp, Vp, wqf, bqf, wpT, F, C, scale, kT, tmax, K1, sb, V2, s); }, "attn_fold");
+            }
             MlpOp mo;
             memset(&mo, 0, sizeof(mo));
             mo.mode = 1;
@@ -597,6 +600,31 @@ int build_program(dsb_handle* h) {
             const int sms = h->num_sms;
             b.add([ml, sms](cudaStream_t s) { return mlp_fused_run(ml, sms, s); }, "gemm:attn.fused");
             h->prog_flops.back() = 4.0 * (double)tokens * C * C + 4.0 * (double)tokens * 18 * C;   // q, proj, QK^T, PV
+        } else if (kFoldProj) {
+            // wide stages: the same folding, three launches -- pack, scores + softmax straight off the query tokens,
+            // P . V'' with the projection bias and the residual in its epilogue
+            b.depend(2, 1, 0);                                  // join V
+            b.depend(3, 2, 0);                                  // join K
+            b.set_zone(4);
+            {
+                const float *Kp = h->Kp, *Vp = h->Vp;
+                const float *mb = WF(bk + "attn.fold_k.mb"), *cb = WF(bk + "attn.fold_k.cb");
+                bf16 *KB = h->KB, *VB = h->VB;
+                float* sb = h->sbias;
+                b.add([=](cudaStream_t s) { return kv_pack_launch(Kp, Vp, k_ln, mb, cb, F, C, 48, kT, tmax, KB, sb, VB, s); }, "kv_pack");
+            }
+            {   // scores (query projection inside the keys) + per-head softmax over the 18 keys
+                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, C, 48, q_ln, h->KB);
+                op.b_rows_per_frame = 48; op.rowbias = h->sbias; op.out_softmax = h->P;
+                if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
+                b.conv(op, "attn.qk_softmax", 2.0 * (double)tokens * C * C + 2.0 * (double)tokens * 18 * C);   // proj_q + bmm
+            }
+            {   // P . V'' (output projection inside the values) + bias + residual
+                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, 64, C, h->P, h->VB);
+                op.b_rows_per_frame = C; op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
+                if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
+                b.conv(op, "attn.pv_proj", 2.0 * (double)tokens * 18 * C + 2.0 * (double)tokens * C * C);      // bmm + proj
+            }
         } else {
         {
             ConvOp op = token_op(C, C, q_ln, WP(bk + "attn.proj_q.weight"));
@@ -863,6 +891,32 @@ extern "C" int dsb_finalize_weights(dsb_handle* h) {
             if (int r = pack_gemm_weight(h, bk + k, C, C, 1)) return r;
         if (C <= 192)
             if (int r = transposed(bk + "attn.proj.weight", C, C)) return r;
+        if (kFoldProj) {
+            // proj_q folded into proj_k, proj into proj_v (kernels.cu "projections folded into K / V"): fp32 products,
+            // rounded to bf16 once
+            float *MK = nullptr, *MV = nullptr, *cK = nullptr, *cV = nullptr, *mb = nullptr, *cb = nullptr;
+            if (int r = dev_alloc(h, &MK, (size_t)2 * C * C)) return r;
+            if (int r = dev_alloc(h, &MV, (size_t)2 * C * C)) return r;
+            if (int r = dev_alloc(h, &cK, (size_t)2 * C)) return r;
+            if (int r = dev_alloc(h, &cV, (size_t)2 * C)) return r;
+            if (int r = dev_alloc(h, &mb, (size_t)2 * C)) return r;
+            if (int r = dev_alloc(h, &cb, (size_t)2)) return r;
+            if (int r = fold_weights_launch(W(h, bk + "attn.proj_q.weight"), W(h, bk + "attn.proj_q.bias"), W(h, bk + "attn.proj_k.weight"),
+                                            W(h, bk + "attn.proj_k.bias"), W(h, bk + "attn.proj.weight"), W(h, bk + "attn.proj_v.weight"),
+                                            W(h, bk + "attn.proj_v.bias"), C, 1.0f / sqrtf((float)C), MK, MV, cK, cV, mb, cb, 0))
+                return fail(h, DSB_ERR_CUDA, "fold_weights launch %d", r);
+            bf16 *pk = nullptr, *pv = nullptr;
+            if (int r = dev_alloc(h, &pk, (size_t)2 * C * C)) return r;
+            if (int r = dev_alloc(h, &pv, (size_t)2 * C * C)) return r;
+            if (int r = pack_weight_launch(MK, 2 * C, C, 1, pk, 0)) return fail(h, DSB_ERR_CUDA, "pack_weight launch %d", r);
+            if (int r = pack_weight_launch(MV, 2 * C, C, 1, pv, 0)) return fail(h, DSB_ERR_CUDA, "pack_weight launch %d", r);
+            h->wpack[bk + "attn.fold_k.weight"] = pk;
+            h->wpack[bk + "attn.fold_v.weight"] = pv;
+            h->wf[bk + "attn.fold_k.shift"] = cK;
+            h->wf[bk + "attn.fold_v.shift"] = cV;
+            h->wf[bk + "attn.fold_k.mb"] = mb;
+            h->wf[bk + "attn.fold_k.cb"] = cb;
+        }
         if (int r = pack_gemm_weight(h, bk + "mlp.fc1.weight", 2 * C, C, 1)) return r;
         if (int r = pack_gemm_weight(h, bk + "mlp.fc2.weight", C, 2 * C, 1)) return r;
         // depthwise Conv3d(3,3,3) on a depth-1 volume: only the middle temporal tap touches data (attention.py:36-44)

@@ -28,7 +28,7 @@ def _rand(*shape, seed=0, scale=1.0):
 
 def run_conv(L, kind, A_nhwc, Wt, N, F_, H, W, Cin, dilation=1, T=1, kt=1, scale=None, shift=None, rowbias=None,
              residual=None, act=0, want="f32", out_frames=None, out_fmul=1, out_fadd=0, head_w=None, head_b=0.0):
-    lib = L.lib()
+    lib = L.test_lib()
     out_frames = out_frames or F_
     o32 = torch.zeros(out_frames, H, W, N, device="cuda") if want == "f32" else None
     o16 = torch.zeros(out_frames, H, W, N, device="cuda", dtype=torch.bfloat16) if want == "bf16" else None
@@ -75,7 +75,7 @@ def test_fp16_operands(L, halo, two):
     """GemmParams::ab_f16: the output-head GEMMs (ReduceTemp, mt_proj) take fp16 instead of bf16 operands -- same
     kind::f16 instruction, A / B format bits of the instruction descriptor cleared.  Values are chosen so that an fp16
     buffer misread as bf16 (or the reverse) is wrong by orders of magnitude."""
-    lib = L.lib()
+    lib = L.test_lib()
     lib.dsb_test_set_ab_f16(1)
     lib.dsb_test_set_halo(halo)
     lib.dsb_test_set_two_cta(two)
@@ -161,7 +161,7 @@ def test_head_epilogue(L):
 
 @pytest.fixture
 def two_cta(L):
-    lib = L.lib()
+    lib = L.test_lib()
     lib.dsb_test_set_two_cta(1)
     yield
     lib.dsb_test_set_two_cta(0)
@@ -194,7 +194,7 @@ def test_fused_mlp(L, C, HW, F_, fg, fu):
     b1, b2 = _rand(2 * C, seed=4, scale=0.2), _rand(C, seed=5, scale=0.2)
     res = _rand(src_frames, HW, C, seed=6)
     out = torch.full((src_frames, HW, C), 7.0, device="cuda")
-    r = L.lib().dsb_test_mlp_fused(C, HW, F_, fg, fu, L.ptr(a), L.ptr(w1), L.ptr(w2), L.ptr(b1), L.ptr(b2), L.ptr(res),
+    r = L.test_lib().dsb_test_mlp_fused(C, HW, F_, fg, fu, L.ptr(a), L.ptr(w1), L.ptr(w2), L.ptr(b1), L.ptr(b2), L.ptr(res),
                                    L.ptr(out), L.stream_ptr())
     assert r == 0, r
     torch.cuda.synchronize()
@@ -209,7 +209,7 @@ def test_fused_mlp(L, C, HW, F_, fg, fu):
 
 @pytest.fixture
 def split_ws(L):
-    lib = L.lib()
+    lib = L.test_lib()
     ws = torch.zeros(148 * 128 * 256, device="cuda")
     lib.dsb_test_set_split_ws.argtypes = [ctypes.c_void_p, ctypes.c_long]
     lib.dsb_test_set_split_ws(L.ptr(ws), ws.numel())
@@ -261,7 +261,7 @@ def test_umma_row_shifted_descriptor(L):
     """Hardware-semantics probe behind the halo-tile convolution: a SWIZZLE_128B K-major operand descriptor
     may start at any 128-byte row of a TMA-written tile and space its 8-row groups by any multiple of 128 bytes (the
     swizzle is a function of the shared-memory address; the descriptor's base-offset field must stay 0)."""
-    lib = L.lib()
+    lib = L.test_lib()
     g = torch.Generator().manual_seed(0)
     A = torch.randn(512, 64, generator=g).to(torch.bfloat16).cuda()
     B = torch.randn(32, 64, generator=g).to(torch.bfloat16).cuda()
@@ -278,7 +278,7 @@ def test_umma_row_shifted_descriptor(L):
 
 @pytest.fixture
 def halo(L):
-    lib = L.lib()
+    lib = L.test_lib()
     lib.dsb_test_set_halo(1)
     yield lib
     lib.dsb_test_set_halo(0)

@@ -16,7 +16,7 @@ def L():
     from diff_sal_b200 import _lib
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    lib = _lib.lib()
+    lib = _lib.test_lib()
     lib.dsb_test_layernorm.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     return _lib
@@ -44,7 +44,7 @@ def test_groupnorm_swish(L, Fr, H, W, C):
     act = torch.empty(Fr, H, W, C, device="cuda", dtype=torch.bfloat16)
     raw = torch.empty_like(act)
     scratch = torch.zeros(Fr * 64 * 64, device="cuda", dtype=torch.float64)
-    check(L.lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), L.ptr(scratch), L.ptr(act),
+    check(L.test_lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), L.ptr(scratch), L.ptr(act),
                                            L.ptr(raw), L.stream_ptr()))
     ref = F.group_norm(x, 32, g, b, eps=1e-6)
     ref = nhwc(ref * torch.sigmoid(ref))
@@ -62,13 +62,13 @@ def test_groupnorm_swish_one_launch(L, Fr, H, W, C):
     a = nhwc(x)
     act = torch.empty(Fr, H, W, C, device="cuda", dtype=torch.bfloat16)
     raw = torch.empty_like(act)
-    check(L.lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act), L.ptr(raw), L.stream_ptr()))
+    check(L.test_lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act), L.ptr(raw), L.stream_ptr()))
     ref = F.group_norm(x, 32, g, b, eps=1e-6)
     ref = nhwc(ref * torch.sigmoid(ref))
     assert (act.float() - ref).abs().max().item() <= BF * max(1.0, ref.abs().max().item())
     assert torch.equal(raw, a.to(torch.bfloat16))
     act2 = torch.empty_like(act)
-    check(L.lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act2), None, L.stream_ptr()))
+    check(L.test_lib().dsb_test_groupnorm_swish(L.ptr(a), Fr, H * W, C, L.ptr(g), L.ptr(b), None, L.ptr(act2), None, L.stream_ptr()))
     assert torch.equal(act, act2)
 
 
@@ -78,7 +78,7 @@ def test_layernorm_with_frame_filter(L, C):
     x = rnd(B * T * hw, C, seed=4, scale=2.0, shift=0.5)
     g, b = rnd(C, seed=5, scale=0.2, shift=1.0), rnd(C, seed=6, scale=0.1)
     out = torch.full((B * T * hw, C), 7.0, device="cuda", dtype=torch.bfloat16)
-    check(L.lib().dsb_test_layernorm(L.ptr(x), B * T * hw, C, L.ptr(g), L.ptr(b), L.ptr(out), hw, T, 5, L.stream_ptr()))
+    check(L.test_lib().dsb_test_layernorm(L.ptr(x), B * T * hw, C, L.ptr(g), L.ptr(b), L.ptr(out), hw, T, 5, L.stream_ptr()))
     ref = F.layer_norm(x, (C,), g, b, eps=1e-5)
     o = out.float().reshape(B, T, hw, C)
     r = ref.reshape(B, T, hw, C)
@@ -96,7 +96,7 @@ def test_q_depthwise_layernorm(L, Fr, H, W, C):
     out = torch.empty(Fr * H * W, C, device="cuda", dtype=torch.bfloat16)
     stats = torch.empty(Fr * H * W, 2, device="cuda")
     xl = nhwc(x)
-    check(L.lib().dsb_test_q_dwln(L.ptr(xl), Fr, H, W, C, L.ptr(ng), L.ptr(nb), L.ptr(w9), L.ptr(qg), L.ptr(qb),
+    check(L.test_lib().dsb_test_q_dwln(L.ptr(xl), Fr, H, W, C, L.ptr(ng), L.ptr(nb), L.ptr(w9), L.ptr(qg), L.ptr(qb),
                                   L.ptr(stats), L.ptr(out), 1, 1, L.stream_ptr()))
     xn = F.layer_norm(nhwc(x), (C,), ng, nb, eps=1e-5).permute(0, 3, 1, 2)
     q = F.conv3d(xn.unsqueeze(2), w3, None, padding=1, groups=C).squeeze(2)     # the reference's Conv3d on depth 1
@@ -119,7 +119,7 @@ def test_fused_q_and_v_producer(L, Fr, T, tmax, H, W, C, s):
     q_out = torch.full((Fr * H * W, C), 7.0, device="cuda", dtype=torch.bfloat16)
     v_out = torch.full((Fr * 18, C), 7.0, device="cuda", dtype=torch.bfloat16)
     xl = nhwc(x)
-    check(L.lib().dsb_test_qv_tile(L.ptr(xl), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(w9), L.ptr(qg), L.ptr(qb), L.ptr(wt),
+    check(L.test_lib().dsb_test_qv_tile(L.ptr(xl), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(w9), L.ptr(qg), L.ptr(qb), L.ptr(wt),
                                    L.ptr(vg), L.ptr(vb), L.ptr(q_out), L.ptr(v_out), T, tmax, L.stream_ptr()))
     xn = F.layer_norm(nhwc(x), (C,), ng, nb, eps=1e-5).permute(0, 3, 1, 2)
     q = F.conv3d(xn.unsqueeze(2), w3, None, padding=1, groups=C).squeeze(2)
@@ -145,7 +145,7 @@ def test_pooled_tokens(L, Fr, H, W, C, s):
     out = torch.empty(Fr * 18, C, device="cuda", dtype=torch.bfloat16)
     stats = torch.empty(Fr * H * W, 2, device="cuda")
     xl = nhwc(x)
-    check(L.lib().dsb_test_pool_ln(L.ptr(xl), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(wt), L.ptr(vg), L.ptr(vb),
+    check(L.test_lib().dsb_test_pool_ln(L.ptr(xl), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(wt), L.ptr(vg), L.ptr(vb),
                                    L.ptr(stats), L.ptr(out), 1, 1, L.stream_ptr()))
     xn = F.layer_norm(nhwc(x), (C,), ng, nb, eps=1e-5).permute(0, 3, 1, 2)
     v = F.conv2d(xn, wv[:, :, 0], None, stride=s, groups=C)
@@ -166,7 +166,7 @@ def test_audio_gate_and_scrambled_key(L, B, H, W, C, s):
     gate = torch.empty(B, C, H, W, device="cuda")
     out = torch.empty(B * T * 18, C, device="cuda", dtype=torch.bfloat16)
     wkt = wk.reshape(C, s * s).t().contiguous()
-    check(L.lib().dsb_test_av_key(L.ptr(xf), L.ptr(a_low), B, T, H, W, C, s, L.ptr(wkt), L.ptr(kg), L.ptr(kb), L.ptr(gate),
+    check(L.test_lib().dsb_test_av_key(L.ptr(xf), L.ptr(a_low), B, T, H, W, C, s, L.ptr(wkt), L.ptr(kg), L.ptr(kb), L.ptr(gate),
                                   L.ptr(out), T, L.stream_ptr()))
     au = a if H == 7 else F.interpolate(a, scale_factor=H // 7, mode="nearest")
     a5 = au.reshape(B, T, C, H, W).permute(0, 2, 1, 3, 4)
@@ -183,7 +183,7 @@ def test_upsample2x(L, Fr, H, W, C):
     x = rnd(Fr, C, H, W, seed=24)
     out = torch.empty(Fr, 2 * H, 2 * W, C, device="cuda", dtype=torch.bfloat16)
     xl = nhwc(x)
-    check(L.lib().dsb_test_upsample2x(L.ptr(xl), Fr, H, W, C, L.ptr(out), L.stream_ptr()))
+    check(L.test_lib().dsb_test_upsample2x(L.ptr(xl), Fr, H, W, C, L.ptr(out), L.stream_ptr()))
     ref = nhwc(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
     assert (out.float() - ref).abs().max().item() <= BF * max(1.0, ref.abs().max().item())
 
@@ -193,12 +193,12 @@ def test_multi_scale_sum_and_final_upsample(L):
     rs = [rnd(B, 768, 7 << k, 12 << k, seed=25 + k) for k in range(4)]
     out = torch.empty(B, 112, 192, 768, device="cuda", dtype=torch.float16)     # fp16: operand of the mt_proj GEMM
     rl = [nhwc(r) for r in rs]                      # keep the channels-last copies alive across the launch
-    check(L.lib().dsb_test_ms_sum(*[L.ptr(r) for r in rl], B, L.ptr(out), L.stream_ptr()))
+    check(L.test_lib().dsb_test_ms_sum(*[L.ptr(r) for r in rl], B, L.ptr(out), L.stream_ptr()))
     ref = sum(F.interpolate(r, size=(112, 192), mode="bilinear", align_corners=False) for r in rs)
     assert (out.float() - nhwc(ref)).abs().max().item() <= BF / 8 * max(1.0, ref.abs().max().item())
     p = rnd(B, 1, 112, 192, seed=30)
     o2 = torch.empty(B, 1, 224, 384, device="cuda")
-    check(L.lib().dsb_test_final_up(L.ptr(p), B, L.ptr(o2), L.stream_ptr()))
+    check(L.test_lib().dsb_test_final_up(L.ptr(p), B, L.ptr(o2), L.stream_ptr()))
     assert (o2 - F.interpolate(p, size=(224, 384), mode="bilinear", align_corners=False)).abs().max().item() < 1e-6
 
 
@@ -210,7 +210,7 @@ def test_stem_composition(L):
     w_d, b_d = rnd(96, 96, 3, 3, seed=34, scale=0.05), rnd(96, seed=35, scale=0.1)
     w5, b5 = torch.empty(2400, device="cuda"), torch.empty(96, device="cuda")
     h0 = torch.empty(B, 56, 96, 96, device="cuda")
-    check(L.lib().dsb_test_stem(L.ptr(x), B, L.ptr(w_in), L.ptr(b_in), L.ptr(w_d), L.ptr(b_d), L.ptr(w5), L.ptr(b5),
+    check(L.test_lib().dsb_test_stem(L.ptr(x), B, L.ptr(w_in), L.ptr(b_in), L.ptr(w_d), L.ptr(b_d), L.ptr(w5), L.ptr(b5),
                                 L.ptr(h0), L.stream_ptr()))
     ref = F.conv2d(F.pad(F.conv2d(x, w_in, b_in, padding=1), (0, 1, 0, 1)), w_d, b_d, stride=4)
     assert (h0 - nhwc(ref)).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
@@ -227,7 +227,7 @@ def test_timestep_embedding_mlp(L, tvals):
     outs = [torch.empty(B, c, device="cuda") for c in (192, 384, 768)]
     w0t, w1t = w0.t().contiguous(), w1.t().contiguous()          # [in][out], kept alive across the launch
     wpt = [w.t().contiguous() for w in wps]
-    check(L.lib().dsb_test_temb(L.ptr(t), B, L.ptr(w0t), L.ptr(b0), L.ptr(w1t), L.ptr(b1), L.ptr(wpt[0]), L.ptr(bps[0]),
+    check(L.test_lib().dsb_test_temb(L.ptr(t), B, L.ptr(w0t), L.ptr(b0), L.ptr(w1t), L.ptr(b1), L.ptr(wpt[0]), L.ptr(bps[0]),
                                 L.ptr(wpt[1]), L.ptr(bps[1]), L.ptr(wpt[2]), L.ptr(bps[2]), L.ptr(outs[0]), L.ptr(outs[1]),
                                 L.ptr(outs[2]), L.stream_ptr()))
     half = 48

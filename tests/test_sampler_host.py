@@ -1,6 +1,7 @@
 """CPU: host-side sampler logic of the product (schedules, step coefficients, sampler programs) against the
 oracle, plus the C-ABI export check.  No compute call touches the GPU here."""
 import ctypes
+import subprocess
 import os
 import re
 
@@ -166,6 +167,16 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 12
     for n in names:
         assert hasattr(lib, n), "libdiffsal_b200.so does not export %s" % n
+    assert not any(n.startswith("dsb_test_") for n in names)
+    # the per-kernel test entries live in their own library and are not exported by the product library
+    tlib = ctypes.CDLL(_lib.TEST_LIB_PATH)
+    thdr = open(os.path.join(ROOT, "include", "diffsal_b200_test.h")).read()
+    tnames = sorted(set(re.findall(r"\b(dsb_test_[a-z_0-9]+)\s*\(", thdr)))
+    assert len(tnames) >= 15
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for n in tnames:
+        assert hasattr(tlib, n), "libdiffsal_b200_test.so does not export %s" % n
+        assert (" T " + n) not in out, "product library exports the test entry %s" % n
 
 
 def test_product_fails_loudly_without_gpu():
