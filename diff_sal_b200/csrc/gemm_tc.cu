@@ -406,7 +406,23 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
 #pragma unroll
                             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-                        if (p.out_bf16) {
+                        if (p.kv_mode) {
+                            // attention operands: row = frame * 18 + key, 16 columns of one head (kv_C % 16 == 0)
+                            const int fr = (int)pix_out / 18, j = (int)pix_out - fr * 18;
+                            const int hh = n / p.kv_C, cc = n - hh * p.kv_C;
+                            if (p.kv_mode == 1) {
+                                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + ((size_t)fr * p.kv_R + hh * 18 + j) * p.kv_C + cc);
+                                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                   pack_bf16x2(v[6], v[7]));
+                                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                   pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                            } else {
+                                // transposed: the lanes of a warp (consecutive keys) write neighbouring 2-byte elements
+                                bf16* op = p.out_bf16 + ((size_t)fr * p.kv_C + cc) * 64 + hh * 18 + j;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) op[k * 64] = __float2bfloat16(v[k]);
+                            }
+                        } else if (p.out_bf16) {
                             uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
                             if (p.out_f16) {
                                 op[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),

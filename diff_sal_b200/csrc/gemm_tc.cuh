@@ -62,6 +62,10 @@ struct GemmParams {
     // attention scores: N == bn == 48 = 2 heads x 18 keys (+12 zero rows); per-head softmax over the 18 keys,
     // written as bf16 probabilities [pix][64] (columns 36..63 zero) -- the A operand of the P.V GEMM
     bf16* out_softmax;
+    // folded K / V projections (plan.cu, kernels.cu "projections folded into K / V"): GEMM row m = frame*18 + key j, column
+    // n = head*kv_C + c.  kv_mode 1 writes out_bf16 as the score operand [frame][kv_R][kv_C] (row head*18 + j), kv_mode 2
+    // as the transposed P.V operand [frame][kv_C][64] (column head*18 + j); padding rows / columns are never written.
+    int kv_mode, kv_R, kv_C;
 };
 
 // One-time per-process kernel attribute setup (safe to call repeatedly; called outside stream capture).

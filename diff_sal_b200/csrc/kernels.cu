@@ -898,7 +898,8 @@ __global__ void __launch_bounds__(256, MINB) q_dwln_tile2_kernel(const float* __
 }
 
 __device__ __forceinline__ void pooled_ln_store(const float* pre, int C, const float* __restrict__ g,
-                                                const float* __restrict__ b, bf16* __restrict__ o, float* red);
+                                                const float* __restrict__ b, bf16* __restrict__ o, float* red,
+                                                const ScoreBias* sbp = nullptr, int tokv = 0);
 
 // Q and V producers of a narrow stage in ONE pass over the stage input (audio-visual mode, C = 96 / 192):
 //   q = LN_q(dw3x3(LN(x)))  for every pixel,   v = LN_v(dw SxS stride S (LN(x)))  for the 18 pooling windows of the frame.
@@ -1196,14 +1197,33 @@ int q_dwln_launch(const float* x, const float2* stats, int F, int H, int W, int 
 // ------------------------------------------------------------------------------------------ pooled K / V tokens
 // Tail shared by both pooling kernels: pre[C] (smem) -> LayerNorm -> bf16 row.
 __device__ __forceinline__ void pooled_ln_store(const float* pre, int C, const float* __restrict__ g,
-                                                const float* __restrict__ b, bf16* __restrict__ o, float* red) {
+                                                const float* __restrict__ b, bf16* __restrict__ o, float* red,
+                                                const ScoreBias* sbp, int tokv) {
     float s = 0.0f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) s += pre[c];
     const float mean = block_sum(s, red) / (float)C;
     float q = 0.0f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) { const float d = pre[c] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(block_sum(q, red) / (float)C + 1e-5f);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2bfloat16((pre[c] - mean) * rstd * g[c] + b[c]);
+    float d0 = 0.0f, d1 = 0.0f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bf16 y = __float2bfloat16((pre[c] - mean) * rstd * g[c] + b[c]);
+        o[c] = y;
+        if (sbp && sbp->sb) {                             // folded score bias of this key (see "projections folded into K / V")
+            const float yf = __bfloat162float(y);
+            d0 = fmaf(yf, __ldg(sbp->mb + c), d0);
+            d1 = fmaf(yf, __ldg(sbp->mb + C + c), d1);
+        }
+    }
+    if (sbp && sbp->sb) {
+        d0 = block_sum(d0, red);
+        d1 = block_sum(d1, red);
+        if (threadIdx.x == 0) {
+            const int f = tokv / 18, j = tokv - f * 18;
+            sbp->sb[(size_t)f * sbp->R + j] = d0 + __ldg(sbp->cb);
+            sbp->sb[(size_t)f * sbp->R + 18 + j] = d1 + __ldg(sbp->cb + 1);
+        }
+    }
 }
 
 // part[G][C] (one partial row per pixel group) -> pre[C] in part[0], groups added in index order
@@ -1222,7 +1242,7 @@ __device__ __forceinline__ void pool_fold_groups(float* sm, int C, int G) {
 __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __restrict__ stats, int H, int W, int C,
                                int s_, const float* __restrict__ ng, const float* __restrict__ nb,
                                const float* __restrict__ wv, const float* __restrict__ vg,
-                               const float* __restrict__ vb, bf16* __restrict__ out, int T, int tmax) {
+                               const float* __restrict__ vb, bf16* __restrict__ out, int T, int tmax, const ScoreBias sbv) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float sm[];          // part[G][C]; pre[C] aliases part[0]
@@ -1256,7 +1276,7 @@ __global__ void pool_ln_kernel(const float* __restrict__ x, const float2* __rest
         reinterpret_cast<float4*>(sm)[gq * CV + c4] = acc;
     }
     pool_fold_groups(sm, C, G);
-    pooled_ln_store(sm, C, vg, vb, out + (size_t)tokv * C, red);
+    pooled_ln_store(sm, C, vg, vb, out + (size_t)tokv * C, red, &sbv, tokv);
 }
 
 // (C / 4) channel vectors x pixel groups; 256-thread blocks keep >= 5 blocks resident per SM (768-thread blocks were
@@ -1265,11 +1285,11 @@ static int pool_threads(int C) { (void)C; return 256; }
 
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
                    const float* nb, const float* wv, const float* vg, const float* vb, bf16* out, int T, int tmax,
-                   cudaStream_t s) {
+                   cudaStream_t s, ScoreBias sbv) {
     const int nthr = pool_threads(C);
     if (C % 4 || C / 4 > nthr) return -34;
     const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
-    DSB_PDL_LAUNCH(pool_ln_kernel, F * 18, nthr, smem, s, x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax);
+    DSB_PDL_LAUNCH(pool_ln_kernel, F * 18, nthr, smem, s, x, stats, H, W, C, s_, ng, nb, wv, vg, vb, out, T, tmax, sbv);
     DSB_LAUNCH_CHECK();
 }
 
@@ -1349,7 +1369,7 @@ int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int 
 template <int C, int H, int W, int S_, int T_>
 __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __restrict__ a_cm, int tmax,
                                 const float* __restrict__ wk, const float* __restrict__ kg,
-                                const float* __restrict__ kb, bf16* __restrict__ out) {
+                                const float* __restrict__ kb, bf16* __restrict__ out, const ScoreBias sbv) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float sm[];
@@ -1401,7 +1421,7 @@ __global__ void kpool_av_kernel(const float* __restrict__ g, const float* __rest
         reinterpret_cast<float4*>(sm)[gq * CV + c4] = acc;
     }
     pool_fold_groups(sm, C, G);
-    pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red);
+    pooled_ln_store(sm, C, kg, kb, out + (size_t)tokv * C, red, &sbv, tokv);
 }
 
 // a_low[(b*T + t)*84 + p][c]  ->  a_cm[b][c][t*84 + p]     (32 x 32 shared-memory transpose, coalesced on both sides)
@@ -1428,15 +1448,15 @@ int audio_cmajor_launch(const float* a_low, int B, int T, int C, float* a_cm, cu
 }
 
 int kpool_av_launch(const float* g, const float* a_low, int B, int T, int H, int W, int C, int s_, const float* wk,
-                    const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s) {
+                    const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s, ScoreBias sbv) {
     const int nthr = pool_threads(C);
     if (T != 9 || C / 4 > nthr) return -34;
     const size_t smem = (size_t)(nthr / (C / 4)) * C * sizeof(float);
     const int grid = B * T * 18;
-    if (C == 768 && H == 7 && W == 12 && s_ == 2) DSB_PDL_LAUNCH((kpool_av_kernel<768, 7, 12, 2, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 384 && H == 14 && W == 24 && s_ == 4) DSB_PDL_LAUNCH((kpool_av_kernel<384, 14, 24, 4, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 192 && H == 28 && W == 48 && s_ == 8) DSB_PDL_LAUNCH((kpool_av_kernel<192, 28, 48, 8, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
-    else if (C == 96 && H == 56 && W == 96 && s_ == 16) DSB_PDL_LAUNCH((kpool_av_kernel<96, 56, 96, 16, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out);
+    if (C == 768 && H == 7 && W == 12 && s_ == 2) DSB_PDL_LAUNCH((kpool_av_kernel<768, 7, 12, 2, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out, sbv);
+    else if (C == 384 && H == 14 && W == 24 && s_ == 4) DSB_PDL_LAUNCH((kpool_av_kernel<384, 14, 24, 4, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out, sbv);
+    else if (C == 192 && H == 28 && W == 48 && s_ == 8) DSB_PDL_LAUNCH((kpool_av_kernel<192, 28, 48, 8, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out, sbv);
+    else if (C == 96 && H == 56 && W == 96 && s_ == 16) DSB_PDL_LAUNCH((kpool_av_kernel<96, 56, 96, 16, 9>), grid, nthr, smem, s, g, a_low, tmax, wk, kg, kb, out, sbv);
     else return -34;
     DSB_LAUNCH_CHECK();
 }
@@ -1511,10 +1531,12 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
                                                      bf16* __restrict__ K1, float* __restrict__ sb, bf16* __restrict__ V2) {
     pdl_trigger();
     pdl_wait();
-    const int f = blockIdx.x, tid = threadIdx.x;
+    // grid (frame, part): part p owns the 8-channel groups p, p + P, ... of K1, the channels p*256/P.. of V2 and the
+    // key rows r = p (mod P) of the score bias
+    const int f = blockIdx.x, part = blockIdx.y, P = gridDim.y, tid = threadIdx.x;
     if (f % T >= tmax) return;
     const int c8n = C >> 3, ld = 2 * C;
-    for (int it = tid; it < R * c8n; it += 256) {
+    for (int it = part * 256 + tid; it < R * c8n; it += 256 * P) {
         const int r = it / c8n, c = (it - r * c8n) * 8;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (r < 36) {
@@ -1526,7 +1548,7 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
     }
     {   // folded score bias: one warp per key row
         const int lane = tid & 31;
-        for (int r = tid >> 5; r < R; r += 8) {
+        for (int r = part * 8 + (tid >> 5); r < R; r += 8 * P) {
             float a = 0.0f;
             if (r < 36) {
                 const bf16* kr = k_ln + ((size_t)f * 18 + r % 18) * C;
@@ -1537,7 +1559,7 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
             if (lane == 0) sb[(size_t)f * R + r] = a;
         }
     }
-    for (int c = tid; c < C; c += 256) {
+    for (int c = part * 256 + tid; c < C; c += 256 * P) {
         uint32_t w[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) w[k] = 0u;
@@ -1557,7 +1579,8 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
 int kv_pack_launch(const float* Kf, const float* Vf, const bf16* k_ln, const float* mb, const float* cb, int F, int C, int R,
                    int T, int tmax, bf16* K1, float* sb, bf16* V2, cudaStream_t s) {
     if (C % 8 || R < 36) return -38;
-    DSB_PDL_LAUNCH(kv_pack_kernel, F, 256, 0, s, Kf, Vf, k_ln, mb, cb, C, R, T, tmax, K1, sb, V2);
+    const int P = C >= 768 ? 6 : C >= 384 ? 4 : 2;           // >= 2 blocks per SM at 72 frames
+    DSB_PDL_LAUNCH(kv_pack_kernel, dim3(F, P), 256, 0, s, Kf, Vf, k_ln, mb, cb, C, R, T, tmax, K1, sb, V2);
     DSB_LAUNCH_CHECK();
 }
 

@@ -62,9 +62,17 @@ int qv_tile_launch(const float* x, int F, int H, int W, int C, int s_, const Qdw
                    int tmax, cudaStream_t s);
 
 // v (or visual-only k) = LN( depthwise sxs stride s ( LN_norm(x) ) ) -> bf16 [F*18][C]   (attention.py:53-76,93)
+// optional by-product of the K pooling kernels: the folded score bias of every key ("projections folded into K / V"),
+// sb[frame][R] at row head*18 + key = k_ln . mb[head] + cb[head]; sb == null: not produced
+struct ScoreBias {
+    const float* mb;   // [2][C]
+    const float* cb;   // [2]
+    float* sb;         // [frames][R]
+    int R;
+};
 int pool_ln_launch(const float* x, const float2* stats, int F, int H, int W, int C, int s_, const float* ng,
                    const float* nb, const float* wv /*[s*s][C]*/, const float* vg, const float* vb, bf16* out, int T,
-                   int tmax, cudaStream_t s);
+                   int tmax, cudaStream_t s, ScoreBias sbv = ScoreBias{nullptr, nullptr, nullptr, 0});
 
 // audio gate: g[b][c][y][x] = softmax_x( mean_t( a[b,t,y/r,x/r,c] * x[b,t,y,x,c] ) )   (transformer.py:140-144)
 int av_gate_launch(const float* x, const float* a_low, int B, int T, int H, int W, int C, float* g, cudaStream_t s);
@@ -73,7 +81,7 @@ int audio_cmajor_launch(const float* a_low, int B, int T, int C, float* a_cm, cu
 // k = LN( depthwise sxs stride s ( scrambled (a*g) ) ) -> bf16 [B*T*18][C]   (transformer.py:145-146, attention.py:89-91)
 // a_cm: the CHANNEL-MAJOR audio map (audio_cmajor_launch)
 int kpool_av_launch(const float* g, const float* a_cm, int B, int T, int H, int W, int C, int s_,
-                    const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s);
+                    const float* wk /*[s*s][C]*/, const float* kg, const float* kb, bf16* out, int tmax, cudaStream_t s, ScoreBias sbv = ScoreBias{nullptr, nullptr, nullptr, 0});
 
 // per-frame tensor-core operands of the 18-key, 2-head attention:
 //   KB[f][h*18+j][c] = scale * K[f,j,c] if c in head h else 0        ([F][48][C], rows 36..47 zero)

@@ -84,13 +84,16 @@ struct dsb_handle {
     bf16 *up = nullptr, *mid = nullptr, *q_ln = nullptr, *Qp = nullptr, *k_ln = nullptr, *v_ln = nullptr;
     float *Kp = nullptr, *Vp = nullptr, *gate = nullptr;
     bf16 *K1 = nullptr, *V2 = nullptr;            // folded attention operands (narrow stages)
+    bf16 *Ks[4] = {}, *Vs[4] = {};                // per-stage attention operands written by the K / V projection epilogues
+    float* sbs[4] = {};                           //   (padding rows / columns stay zero from allocation) + folded score bias
     float* sbias = nullptr;
     bf16 *KB = nullptr, *VB = nullptr, *P = nullptr, *o = nullptr, *ln2 = nullptr, *hid = nullptr, *lnm = nullptr;
     float2* lnstats = nullptr;
     bf16* S = nullptr;
     float* p = nullptr;
     float* sbuf[8] = {};                          // sampler buffers
-    float* splitws = nullptr;                     // split-K partial sums (main-stream GEMMs only, so one buffer suffices)
+    float* splitws = nullptr;                     // split-K partial sums of the main-stream GEMMs
+    float* splitws_head = nullptr;                // ... and of the ReduceTemp GEMMs, which run on the head stream
     float* t_all = nullptr;                       // [max evals][B]
     int t_all_cap = 0;
 
@@ -107,7 +110,7 @@ struct dsb_handle {
     std::vector<int> prog_pdl;                    // per launch: programmatic-dependent-launch mode of its zone (0 off, 2 all kernels)
     int prog_launches = 0;
     std::vector<int> profile_idx;
-    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // V branch, K branch, output-head branch
     cudaEvent_t ev[8] = {};
     int64_t cond_launches = 0;
     const float* cur_x = nullptr;
@@ -178,6 +181,8 @@ const float* W(dsb_handle* h, const std::string& key) {
 // ------------------------------------------------------------------------------------------ finalize helpers
 // query / output projections folded into the K / V projection weights (DSB_FOLD_PROJ=0: the separate-GEMM form)
 static const bool kFoldProj = [] { const char* e = getenv("DSB_FOLD_PROJ"); return !(e && e[0] == '0'); }();
+// ... and their GEMM epilogues write the score / P.V operand layouts directly (DSB_KV_EPI=0: fp32 outputs + kv_pack kernel)
+static const bool kKvEpi = kFoldProj && [] { const char* e = getenv("DSB_KV_EPI"); return !(e && e[0] == '0'); }();
 
 int pack_gemm_weight(dsb_handle* h, const std::string& key, int N, int Cin, int taps, int f16 = 0) {
     const Weight* w = find_w(h, key);
@@ -267,6 +272,12 @@ int alloc_workspace(dsb_handle* h) {
     if (int r = dev_alloc(h, &h->K1, F * 64 * 192)) return r;
     if (int r = dev_alloc(h, &h->V2, F * 192 * 64)) return r;
     if (int r = dev_alloc(h, &h->sbias, F * 64)) return r;
+    for (int i = 0; i < 4; ++i) {
+        const size_t C = kStageC[i], R = C <= 192 ? 64 : 48;
+        if (int r = dev_alloc(h, &h->Ks[i], F * R * C)) return r;
+        if (int r = dev_alloc(h, &h->Vs[i], F * C * 64)) return r;
+        if (int r = dev_alloc(h, &h->sbs[i], F * R)) return r;
+    }
     if (int r = dev_alloc(h, &h->o, F * kMaxFrame)) return r;
     if (int r = dev_alloc(h, &h->ln2, F * kMaxFrame)) return r;
     if (int r = dev_alloc(h, &h->hid, F * kMaxFrame * 2)) return r;
@@ -277,6 +288,7 @@ int alloc_workspace(dsb_handle* h) {
     for (int i = 0; i < 8; ++i)
         if (int r = dev_alloc(h, &h->sbuf[i], B * kMapElems)) return r;
     if (int r = dev_alloc(h, &h->splitws, (size_t)kSplitWsPerClip * B)) return r;
+    if (int r = dev_alloc(h, &h->splitws_head, (size_t)kSplitWsPerClip * B)) return r;
     h->t_all_cap = 1024;
     if (int r = dev_alloc(h, &h->t_all, (size_t)h->t_all_cap * B)) return r;
     if (int r = dev_alloc(h, &h->u8_stage, B * kMapElems)) return r;
@@ -458,6 +470,27 @@ int build_program(dsb_handle* h) {
         }
     }
 
+    // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU of stage j.
+    // Nothing before the multi-scale sum reads r_j, so for stages 0..2 this pair can leave the critical path and run on the
+    // head stream (3).  DSB_HEAD_STREAM: 0 = in line; 1 = forked right after the stage's MLP (beside the next up-embedding);
+    // 2 = forked after the next stage's up-embedding (beside its memory-bound Q / K / V producers).
+    static const int head_mode = [] { const char* e = getenv("DSB_HEAD_STREAM"); return e ? atoi(e) : 1; }();   // measured: 1 best (24.76 / 24.97 / 25.2 ms per step for 1 / 0 / 2)
+    auto emit_head = [&](int j) {
+        const int C = kStageC[j], H = kStageH[j], Wd = kStageW[j], HW = H * Wd;
+        const long tokens = (long)F * HW;
+        const std::string nk = "invpt_decoder.norm_mts." + std::to_string(j) + ".";
+        const float *gm = W(h, nk + "weight"), *bm = W(h, nk + "bias");
+        const float* x2 = h->X2[j];
+        bf16* lnm = h->lnm;
+        b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s, 1); }, "ln_apply_mts", (double)tokens * C * 6.0 * 5.0 / 9.0);
+        ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
+                            WP("invpt_decoder.redu_chan_up." + std::to_string(j) + ".proj.0.weight"));
+        op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[j]; op.ab_f16 = 1;
+        op.split_ws = head_mode ? h->splitws_head : h->splitws;
+        op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
+        b.conv(op, "reduce_temp");
+    };
+
     // ------------------------------------------------------------ decoder stages (sal_unet.py:457-491)
     for (int i = 0; i < 4; ++i) {
         const int C = kStageC[i], H = kStageH[i], Wd = kStageW[i], HW = H * Wd, sk = kStageS[i];
@@ -488,6 +521,12 @@ int build_program(dsb_handle* h) {
                 b.conv(op, "upembed.conv2");
             }
             Xi = h->X[i];
+            if (head_mode == 2) {                               // the previous stage's ReduceTemp pair starts here
+                b.depend(4, 0, 3);
+                b.cur = 3;
+                emit_head(i - 1);
+                b.cur = 0;
+            }
         }
         b.set_zone(0);                                      // Q / K / V producers: three streams
         const long tokens = (long)F * HW;
@@ -504,6 +543,9 @@ int build_program(dsb_handle* h) {
             return op;
         };
         float2* stats = h->lnstats;
+        const int kvR = C <= 192 ? 64 : 48;                 // key rows per frame of the score operand
+        ScoreBias sbv = {nullptr, nullptr, nullptr, 0};
+        if (kKvEpi) sbv = ScoreBias{WF(bk + "attn.fold_k.mb"), WF(bk + "attn.fold_k.cb"), h->sbs[i], kvR};
         // K / V projections; with the query / output projections folded into their weights (kFoldProj) N = 2C and the
         // output is already "keys seen through Wq" / "values seen through Wp" per head
         auto kv_proj = [&](const char* which, const bf16* A_, float* out_) {
@@ -511,6 +553,11 @@ int build_program(dsb_handle* h) {
             ConvOp op = make_op(CONV_1X1, 1, 1, F * 18, C, kFoldProj ? 2 * C : C, A_, WP(w + ".weight"));
             op.shift = kFoldProj ? WF(w + ".shift") : W(h, w + ".bias");
             op.out_f32 = out_;
+            if (kKvEpi) {
+                op.out_f32 = nullptr;
+                op.out_bf16 = which[0] == 'k' ? h->Ks[i] : h->Vs[i];
+                op.kv_mode = which[0] == 'k' ? 1 : 2; op.kv_R = kvR; op.kv_C = C;
+            }
             b.conv(op, which[0] == 'k' ? "attn.proj_k" : "attn.proj_v", 2.0 * (double)F * 18 * C * C);
         };
         const float *ng = W(h, bk + "norm.weight"), *nb = W(h, bk + "norm.bias");
@@ -533,7 +580,7 @@ int build_program(dsb_handle* h) {
                 const float* acm = h->a_cm[i];
                 float* gate = h->gate;
                 b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
-                b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
+                b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s, sbv); }, "kpool_av", (double)B * HW * C * 4.0 * live);
                 kv_proj("k", k_ln, h->Kp);
             }
             b.cur = 0;
@@ -557,9 +604,9 @@ int build_program(dsb_handle* h) {
             float* gate = h->gate;
             b.add([=](cudaStream_t s) { return av_gate_launch(Xi, al, B, kT, H, Wd, C, gate, s); }, "av_gate", (double)tokens * C * 4.0 + (double)B * HW * C * 4.0);
             const float* acm = h->a_cm[i];
-            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s); }, "kpool_av", (double)B * HW * C * 4.0 * live);
+            b.add([=](cudaStream_t s) { return kpool_av_launch(gate, acm, B, kT, H, Wd, C, sk, wk, kg, kb, k_ln, tmax, s, sbv); }, "kpool_av", (double)B * HW * C * 4.0 * live);
         } else {
-            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
+            b.add([=](cudaStream_t s) { return pool_ln_launch(Xi, stats, F, H, Wd, C, sk, ng, nb, wk, kg, kb, k_ln, kT, tmax, s, sbv); }, "pool_ln_k", (double)tokens * C * 4.0 * live);
         }
         kv_proj("k", k_ln, h->Kp);
         b.cur = 1;
@@ -582,7 +629,9 @@ int build_program(dsb_handle* h) {
             bf16 *K1 = h->K1, *V2 = h->V2;
             float* sb = h->sbias;
             const float scale = 1.0f / sqrtf((float)C);
-            if (kFoldProj) {
+            if (kKvEpi) {
+                // nothing to do: the projection epilogues wrote h->Ks / h->Vs, the K pooling kernel the score bias
+            } else if (kFoldProj) {
                 const float *mb = WF(bk + "attn.fold_k.mb"), *cb = WF(bk + "attn.fold_k.cb");
                 b.add([=](cudaStream_t s) { return kv_pack_launch(Kp, Vp, k_ln, mb, cb, F, C, 64, kT, tmax, K1, sb, V2, s); }, "kv_pack");
             } else {
@@ -593,7 +642,8 @@ int build_program(dsb_handle* h) {
             mo.mode = 1;
             mo.C = C; mo.HW = HW; mo.F = remap ? Fu : F;
             mo.f_group = remap ? kT : 0; mo.f_used = remap ? tmax : 0;
-            mo.A = q_ln; mo.W1 = h->K1; mo.W2 = h->V2; mo.b1 = h->sbias; mo.b2 = W(h, bk + "attn.proj.bias");
+            mo.A = q_ln; mo.W1 = kKvEpi ? h->Ks[i] : h->K1; mo.W2 = kKvEpi ? h->Vs[i] : h->V2;
+            mo.b1 = kKvEpi ? h->sbs[i] : h->sbias; mo.b2 = W(h, bk + "attn.proj.bias");
             mo.residual = Xi; mo.out = h->X1[i];
             MlpLaunch ml;
             if (int r = mlp_fused_lower(mo, &ml)) return fail(h, DSB_ERR_CUDA, "attention chain lower failed (%d)", r);
@@ -606,7 +656,7 @@ int build_program(dsb_handle* h) {
             b.depend(2, 1, 0);                                  // join V
             b.depend(3, 2, 0);                                  // join K
             b.set_zone(4);
-            {
+            if (!kKvEpi) {
                 const float *Kp = h->Kp, *Vp = h->Vp;
                 const float *mb = WF(bk + "attn.fold_k.mb"), *cb = WF(bk + "attn.fold_k.cb");
                 bf16 *KB = h->KB, *VB = h->VB;
@@ -614,13 +664,13 @@ int build_program(dsb_handle* h) {
                 b.add([=](cudaStream_t s) { return kv_pack_launch(Kp, Vp, k_ln, mb, cb, F, C, 48, kT, tmax, KB, sb, VB, s); }, "kv_pack");
             }
             {   // scores (query projection inside the keys) + per-head softmax over the 18 keys
-                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, C, 48, q_ln, h->KB);
-                op.b_rows_per_frame = 48; op.rowbias = h->sbias; op.out_softmax = h->P;
+                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, C, 48, q_ln, kKvEpi ? h->Ks[i] : h->KB);
+                op.b_rows_per_frame = 48; op.rowbias = kKvEpi ? h->sbs[i] : h->sbias; op.out_softmax = h->P;
                 if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
                 b.conv(op, "attn.qk_softmax", 2.0 * (double)tokens * C * C + 2.0 * (double)tokens * 18 * C);   // proj_q + bmm
             }
             {   // P . V'' (output projection inside the values) + bias + residual
-                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, 64, C, h->P, h->VB);
+                ConvOp op = make_op(CONV_1X1, remap ? Fu : F, 1, HW, 64, C, h->P, kKvEpi ? h->Vs[i] : h->VB);
                 op.b_rows_per_frame = C; op.shift = W(h, bk + "attn.proj.bias"); op.residual = Xi; op.out_f32 = h->X1[i];
                 if (remap) { op.f_group = kT; op.f_used = tmax; op.out_remap = 1; }
                 b.conv(op, "attn.pv_proj", 2.0 * (double)tokens * 18 * C + 2.0 * (double)tokens * C * C);      // bmm + proj
@@ -690,18 +740,13 @@ int build_program(dsb_handle* h) {
                 b.conv(op, "mlp.fc2", 4.0 * (double)tokens * C * C);
             }
         }
-        {   // norm_mts on frames 0..4 only (the only ones ReduceTemp reads), then the (5,1,1) reduction + ReLU
-            const std::string nk = "invpt_decoder.norm_mts." + std::to_string(i) + ".";
-            const float *gm = W(h, nk + "weight"), *bm = W(h, nk + "bias");
-            const float* x2 = h->X2[i];
-            bf16* lnm = h->lnm;
-            b.add([=](cudaStream_t s) { return ln_apply_launch(x2, tokens, C, gm, bm, lnm, HW, kT, kReduce, s, 1); }, "ln_apply_mts", (double)tokens * C * 6.0 * 5.0 / 9.0);
-            ConvOp op = make_op(CONV_TEMPORAL, B, H, Wd, C, 768, h->lnm,
-                                WP("invpt_decoder.redu_chan_up." + std::to_string(i) + ".proj.0.weight"));
-            op.T = kT; op.kt = kReduce; op.act = ACT_RELU; op.out_f32 = h->r[i]; op.ab_f16 = 1;
-            op.split_ws = h->splitws; op.split_ws_elems = kSplitWsPerClip * h->cfg.max_batch; op.split_frames_nominal = 8;
-                b.conv(op, "reduce_temp");
+        if (head_mode == 0) emit_head(i);                       // in line on the caller's stream
+        else if (head_mode == 1 || i == 3) {                    // forked as soon as X2_i exists (stage 3: nothing to hide under)
+            if (i < 3) { b.depend(4, 0, 3); b.cur = 3; }
+            emit_head(i);
+            b.cur = 0;
         }
+        if (head_mode && i == 3) b.depend(5, 3, 0);             // r_0..r_2 complete before the multi-scale sum
     }
 
     // ------------------------------------------------------------ multi-scale head (sal_unet.py:482-489,320-327)
@@ -730,7 +775,7 @@ int build_program(dsb_handle* h) {
 int run_program(dsb_handle* h, cudaStream_t s, bool serial = false) {
     // programmatic dependent launch (common.cuh): a launch that directly follows a cross-stream wait keeps a full
     // dependency (no PDL attribute); every other launch may be scheduled under the tail of its stream predecessor
-    bool after_wait[3] = {false, false, false};
+    bool after_wait[4] = {false, false, false, false};
     for (size_t i = 0; i < h->prog.size(); ++i) {
         const int kind = h->prog_kind[i], si = h->prog_stream[i];
         cudaStream_t st = (serial || si == 0) ? s : h->side[si - 1];
@@ -773,7 +818,7 @@ extern "C" int dsb_create(const dsb_config* cfg, dsb_handle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (gemm_init()) { delete h; return DSB_ERR_CUDA; }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
         if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
@@ -787,7 +832,7 @@ extern "C" void dsb_destroy(dsb_handle* h) {
         if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (void* p : h->allocs) cudaFree(p);
     if (h->noise_stage) cudaFree(h->noise_stage);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
     for (int i = 0; i < 8; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);

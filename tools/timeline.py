@@ -13,11 +13,11 @@ for _ in range(3):
     tl = e.profile_timeline(xg, t)
 end = max(b for _, _, b, _ in tl)
 print("# B=%d one evaluation: %d launches, makespan %.3f ms" % (B, len(tl), end))
-busy = {0: 0.0, 1: 0.0, 2: 0.0}
+busy = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
 for name, a, b, s in tl:
     busy[s] += b - a
 print("# busy per stream (ms):", {k: round(v, 3) for k, v in busy.items()})
-prev_end = {0: 0.0, 1: 0.0, 2: 0.0}
+prev_end = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
 print("%-22s %2s %9s %9s %8s %8s" % ("launch", "st", "start_us", "end_us", "dur_us", "gap_us"))
 for name, a, b, s in tl:
     print("%-22s %2d %9.1f %9.1f %8.1f %8.1f" % (name[:22], s, 1e3 * a, 1e3 * b, 1e3 * (b - a), 1e3 * (a - prev_end[s])))
