@@ -283,6 +283,28 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float hx = 0.5f * x;
     return fmaf(copysignf(erf_abs, x), hx, hx);             // 0.5 x (1 + erf(z))
 }
+// the same on a pair with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot per two values);
+// identical operation order per element, so the result is bit-identical to gelu_erf on each half
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+    const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), az, make_float2(1.0f, 1.0f));
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+    float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+    p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+    p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+    const float2 a2 = __fmul2_rn(__fmul2_rn(make_float2(-1.4426950408889634f, -1.4426950408889634f), az), az);
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a2.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a2.y));
+    const float2 pt = __fmul2_rn(p, t);
+    const float2 erf_abs = __ffma2_rn(make_float2(-pt.x, -pt.y), e, make_float2(1.0f, 1.0f));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y)), hx, hx);
+}
 // two fp16 values (saturated to the finite range) in one 32-bit word: operands of the GEMMs that run in kind::f16 with
 // fp16 inputs (GemmParams::ab_f16) -- same tensor-core rate as bf16, three more mantissa bits
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {

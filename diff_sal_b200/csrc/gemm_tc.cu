@@ -388,7 +388,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
                         } else if (p.act == ACT_GELU) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 g = gelu_erf2(make_float2(v[2 * j], v[2 * j + 1]));
+                                v[2 * j] = g.x; v[2 * j + 1] = g.y;
+                            }
                         }
                         if (p.residual) {
 #pragma unroll

@@ -24,6 +24,9 @@
 namespace dsb {
 
 static constexpr int kMlpThreads = 480;           // warps: 0 A+W1 producer, 1 MMA, 2..9 GELU stage, 10..13 output stage, 14 W2 producer
+// (Measured and rejected: a second group of eight GELU-stage warps taking every other hidden chunk.  736 threads cap the
+// kernel at 80 registers, the output stage spills its residual prefetch, and the chain kernels ran 1.6x SLOWER: 126 / 123 us
+// against 77 / 62 us for the MLP / attention chain of stage 2.)
 static constexpr int kHC = 64;                    // hidden columns per chunk
 static constexpr uint32_t kAcc2Col = 128;         // TMEM column of the second accumulator (acc1 buffers at 0 and 64)
 
@@ -217,9 +220,9 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                     const float* b1 = p.b1 + h * kHC + half * 32;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float v0 = gelu_erf(__uint_as_float(raw[2 * j]) + __ldg(b1 + 2 * j));
-                        const float v1 = gelu_erf(__uint_as_float(raw[2 * j + 1]) + __ldg(b1 + 2 * j + 1));
-                        packed[j] = pack_bf16x2(v0, v1);
+                        const float2 bb = __ldg(reinterpret_cast<const float2*>(b1) + j);
+                        const float2 v = gelu_erf2(__fadd2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), bb));
+                        packed[j] = pack_bf16x2(v.x, v.y);
                     }
                 } else {
                     // scores of head 0 live in columns 0..17, head 1 in 18..35: the warp with half == 0 holds columns

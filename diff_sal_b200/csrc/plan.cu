@@ -818,8 +818,20 @@ extern "C" int dsb_create(const dsb_config* cfg, dsb_handle** out) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (gemm_init()) { delete h; return DSB_ERR_CUDA; }
-    for (int i = 0; i < 3; ++i)
-        if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
+    {
+        // Block-scheduling priorities (DSB_PRIO=1, an experiment kept for the record): with the K branch -- the longest of the
+        // three Q / K / V producers -- at the highest priority it finishes in half the time, the Q producers on the caller's
+        // stream take correspondingly longer and the step time does not move (24.5 / 24.5 / 24.7 / 24.8 ms, on / off / on /
+        // off): the phase is bound by the SM time of its kernels, not by their order.  Default: one priority for all.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);         // lo = least (numerically greatest), hi = greatest priority
+        const char* e = getenv("DSB_PRIO");
+        const bool on = e && e[0] == '1';
+        const int mid = (lo + hi) / 2;
+        const int prio[3] = {on ? mid : lo, on ? hi : lo, lo};
+        for (int i = 0; i < 3; ++i)
+            if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio[i]) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
+    }
     for (int i = 0; i < 8; ++i)
         if (cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return DSB_ERR_CUDA; }
     *out = h;
