@@ -220,6 +220,7 @@ int conv_lower(const ConvOp& op, ConvLaunch* out) {
     p.epi_transposed = (op.out_f32 && !op.out_bf16 && !op.head_w && !op.out_softmax && bn % 32 == 0) ? 1 : 0;
     p.f_group = op.f_group; p.f_used = op.f_used; p.out_remap = op.out_remap;
     p.kv_mode = op.kv_mode; p.kv_R = op.kv_R; p.kv_C = op.kv_C;
+    p.trace = op.trace;
     if (op.kv_mode && (!op.out_bf16 || op.out_f32 || S_plan > 1 || op.kind != CONV_1X1 || op.kv_C % 16 || op.N != 2 * op.kv_C ||
                        op.kv_R < 36 || op.H != 1 || op.F != 1 || op.W % 18))
         return -26;

@@ -41,6 +41,7 @@ struct ConvOp {
     int out2_fmul, out2_fadd;
     int ab_f16;             // A and Wt hold fp16 values (GemmParams::ab_f16)
     int out_f16;            // out_bf16 receives fp16 values (GemmParams::out_f16); not with split-K
+    unsigned long long* trace; // GemmParams::trace (tools only)
     int kv_mode, kv_R, kv_C;   // attention-operand output layouts (GemmParams::kv_mode); needs out_bf16, CONV_1X1, no split-K
     int two_cta;            // -1: never, 0: automatic (pairs when there are enough tiles), 1: force
     int halo;               // 1: request the halo-tile path (CONV_3X3, Cin % 64 == 0, N <= 128, enough 8x16 tiles for CTA

@@ -5,6 +5,7 @@
 #include "gemm_tc.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dsb {
@@ -25,7 +26,17 @@ struct __align__(16) GemmBarriers {
     uint32_t pad;
 };
 
-template <bool TWO>
+// Compile-time epilogue flavours.  The generic kernel (EPI = 0) tests every epilogue option at run time inside its
+// innermost loops: the row-coalesced store loop came to ~135 SASS instructions per (4 rows x 128 B) store and the twelve
+// epilogue warps saturated the issue slots -- a per-role clock trace (tools/gemm_trace.py) showed 3.4 k cycles per
+// 32-column chunk, 2-5x the MMA time of the mid-size GEMMs.  A specialised instantiation has bit 0 set and states the
+// options in the other bits, so its loops hold only the work of that flavour.
+enum : int {
+    kEpiSpecial = 1, kEpiTransposed = 2, kEpiScale = 4, kEpiShift = 8, kEpiRowbias = 16, kEpiResidual = 32,
+    kEpiRelu = 64, kEpiGelu = 128, kEpiOut32 = 256, kEpiOut16 = 512, kEpiOut2 = 1024, kEpiKvK = 2048, kEpiKvV = 4096
+};
+
+template <bool TWO, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const int num_stages) {
@@ -35,6 +46,16 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     // two_cta: the CTA pair of a cluster shares one M = 256 tcgen05.mma (cta_group::2); each CTA stages its own 128
     // A rows and HALF of the B rows, which halves the shared-memory operand traffic per MMA
     constexpr bool two = TWO;            // separate instantiations: the 1-CTA kernel holds no cta_group::2 code
+    constexpr bool SP = (EPI & kEpiSpecial) != 0;
+#define F_SCALE (SP ? (EPI & kEpiScale) != 0 : p.scale != nullptr)
+#define F_SHIFT (SP ? (EPI & kEpiShift) != 0 : p.shift != nullptr)
+#define F_ROWBIAS (SP ? (EPI & kEpiRowbias) != 0 : p.rowbias != nullptr)
+#define F_RES (SP ? (EPI & kEpiResidual) != 0 : p.residual != nullptr)
+#define F_ACT (SP ? ((EPI & kEpiRelu) ? (int)ACT_RELU : (EPI & kEpiGelu) ? (int)ACT_GELU : (int)ACT_NONE) : p.act)
+#define F_OUT32 (SP ? (EPI & kEpiOut32) != 0 : p.out_f32 != nullptr)
+#define F_OUT16 (SP ? (EPI & kEpiOut16) != 0 : p.out_bf16 != nullptr)
+#define F_OUT2 (SP ? (EPI & kEpiOut2) != 0 : p.out2_f32 != nullptr)
+#define F_KV (SP ? ((EPI & kEpiKvK) ? 1 : (EPI & kEpiKvV) ? 2 : 0) : p.kv_mode)
     uint32_t rank = 0u;
     if constexpr (two) rank = cluster_ctarank();
     // a pipeline stage holds `ksub` K sub-blocks of bk channels: [ksub][128][bk] of A then [ksub][bn_local][bk] of B
@@ -81,6 +102,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     // nothing above touched global memory written by the previous kernel, everything below may
     pdl_trigger();
     pdl_wait();
+    const bool tracing = p.trace != nullptr && blockIdx.x < 4;
+    unsigned long long* const trc = tracing ? p.trace + (size_t)blockIdx.x * 3 * 16 * 4 : nullptr;
+    if (tracing && threadIdx.x == 0) p.trace[768 + blockIdx.x * 2] = clock64();
 
     const int n_tiles = p.N / p.bn;
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
@@ -98,7 +122,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         // (whole warp convergent, one elected lane issues: keeps coordinates in uniform registers)
         int s = 0;
         uint32_t phase = 0;
-        for (int unit = unit0; unit < total_units; unit += unit_step) {
+        int ucount = 0;
+        for (int unit = unit0; unit < total_units; unit += unit_step, ++ucount) {
+            if (tracing && ucount < 16 && lane == 0) trc[(0 * 16 + ucount) * 4 + 0] = clock64();
             const int tile = unit / ksplit, ks = unit - tile * ksplit;
             const int nt = tile % n_tiles;
             const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;   // may be one past the end
@@ -161,6 +187,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 while (tap >= p.taps) { tap -= p.taps; ++cb; }
                 if (++s == num_stages) { s = 0; phase ^= 1u; }
             }
+            if (tracing && ucount < 16 && lane == 0) trc[(0 * 16 + ucount) * 4 + 1] = clock64();
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -184,13 +211,16 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int unit = unit0; unit < total_units; unit += unit_step) {
+            int ucount = 0;
+            for (int unit = unit0; unit < total_units; unit += unit_step, ++ucount) {
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
+                if (tracing && ucount < 16 && lane == 0) trc[(1 * 16 + ucount) * 4 + 0] = clock64();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
                 for (int kb = 0; kb < nk; ++kb) {
                     mbar_wait(&bars->full[s], phase);
                     tc_fence_after();
+                    if (tracing && kb == 0 && ucount < 16 && lane == 0) trc[(1 * 16 + ucount) * 4 + 1] = clock64();
                     if (elect_one()) {
                         uint64_t da = da0 + (uint64_t)((uint32_t)s * stage_step);
                         uint64_t db = db0 + (uint64_t)((uint32_t)s * stage_step);
@@ -252,6 +282,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     if constexpr (two) umma_commit_2sm(&bars->tmem_full[acc]); else umma_commit(&bars->tmem_full[acc]);
                 }
                 __syncwarp();
+                if (tracing && ucount < 16 && lane == 0) trc[(1 * 16 + ucount) * 4 + 2] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -265,7 +296,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         const int rf = r >> (bw_log2 + bh_log2);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int unit = unit0; unit < total_units; unit += unit_step) {
+        int ucount = 0;
+        const bool tr_e = tracing && warp == 2 && lane == 0;
+        for (int unit = unit0; unit < total_units; unit += unit_step, ++ucount) {
+            if (tr_e && ucount < 16) trc[(2 * 16 + ucount) * 4 + 0] = clock64();
             const int tile = unit / ksplit, ks = unit - tile * ksplit;
             const int nt = tile % n_tiles;
             const int mt = two ? 2 * (tile / n_tiles) + (int)rank : tile / n_tiles;
@@ -285,9 +319,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
 
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (tr_e && ucount < 16) trc[(2 * 16 + ucount) * 4 + 1] = clock64();
             const uint32_t t_addr = tmem_base + (uint32_t)acc * kAccStride + ((uint32_t)(q * 32) << 16);
             float head = 0.0f;
-            if (p.out_softmax) {
+            if (!SP && p.out_softmax) {
                 // 2 heads x 18 keys: the whole score row lives in this thread (one warp per quadrant does it)
                 if (half == 0) {
                 uint32_t raw[48];
@@ -325,7 +360,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     op[7] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 }
-            } else if (p.head_w) {
+            } else if (!SP && p.head_w) {
                 // fused 96 -> 1 head: each of the quadrant's two warps reduces its chunks, partials meet in smem
                 for (int c = half * 16; c < p.bn; c += 16 * kPerQuad) {
                     uint32_t raw[16];
@@ -343,13 +378,13 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         }
                     }
                 }
-            } else if (!p.epi_transposed) {
+            } else if (SP ? !(EPI & kEpiTransposed) : !p.epi_transposed) {
                 // direct epilogue: thread = one output row, 16-column chunks; the residual of a chunk is requested
                 // before the TMEM load so that its DRAM latency overlaps the tcgen05.ld round trip
                 for (int c = half * 16; c < p.bn; c += 16 * kPerQuad) {
                     const int n = n0 + c;
                     float4 res[4];
-                    if (p.residual && valid) {
+                    if (F_RES && valid) {
                         const float4* rp = reinterpret_cast<const float4*>(p.residual + pix_in * p.N + n);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) res[j] = rp[j];
@@ -361,21 +396,21 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-                        if (p.scale) {
+                        if (F_SCALE) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 t = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
                                 v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                             }
                         }
-                        if (p.shift) {
+                        if (F_SHIFT) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
                                 v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                             }
                         }
-                        if (p.rowbias) {
+                        if (F_ROWBIAS) {
                             const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (size_t)fs * p.N + n);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -383,37 +418,37 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                                 v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                             }
                         }
-                        if (p.act == ACT_RELU) {
+                        if (F_ACT == ACT_RELU) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-                        } else if (p.act == ACT_GELU) {
+                        } else if (F_ACT == ACT_GELU) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float2 g = gelu_erf2(make_float2(v[2 * j], v[2 * j + 1]));
                                 v[2 * j] = g.x; v[2 * j + 1] = g.y;
                             }
                         }
-                        if (p.residual) {
+                        if (F_RES) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
                             }
                         }
-                        if (p.out_f32) {
+                        if (F_OUT32) {
                             float4* op = reinterpret_cast<float4*>(p.out_f32 + (size_t)ks * p.split_stride + pix_out * p.ldo + n);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-                        if (p.out2_f32) {
+                        if (F_OUT2) {
                             float4* op = reinterpret_cast<float4*>(p.out2_f32 + pix_out2 * p.ldo + n);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-                        if (p.kv_mode) {
+                        if (F_KV) {
                             // attention operands: row = frame * 18 + key, 16 columns of one head (kv_C % 16 == 0)
                             const int fr = (int)pix_out / 18, j = (int)pix_out - fr * 18;
                             const int hh = n / p.kv_C, cc = n - hh * p.kv_C;
-                            if (p.kv_mode == 1) {
+                            if (F_KV == 1) {
                                 uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + ((size_t)fr * p.kv_R + hh * 18 + j) * p.kv_C + cc);
                                 op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                                    pack_bf16x2(v[6], v[7]));
@@ -425,9 +460,9 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) op[k * 64] = __float2bfloat16(v[k]);
                             }
-                        } else if (p.out_bf16) {
+                        } else if (F_OUT16) {
                             uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix_out * p.ldo + n);
-                            if (p.out_f16) {
+                            if (!SP && p.out_f16) {
                                 op[0] = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
                                                    pack_f16x2(v[6], v[7]));
                                 op[1] = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
@@ -458,7 +493,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     // the chunk's residual rows (coalesced: 4 rows x 128 B per instruction) are requested before the
                     // TMEM load so that their DRAM latency overlaps the tcgen05.ld + smem transpose
                     float4 resv[8];
-                    if (p.residual) {
+                    if (F_RES) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int row = it * 4 + rq;
@@ -478,39 +513,43 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                     __syncwarp();
                     const int n = n0 + c + cq;
                     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-                    if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+                    if (F_SCALE) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+                    if (F_SHIFT) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int row = it * 4 + rq;
                         const int po = rowtab[row * 3 + 0];
                         if (po < 0) continue;
                         float4 v = *reinterpret_cast<const float4*>(tile + row * 36 + cq);
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                        if (p.rowbias) {
+                        if (F_SCALE) {
+                            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                            v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        } else if (F_SHIFT) {
+                            v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
+                        }
+                        if (F_ROWBIAS) {
                             const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)rowtab[row * 3 + 2] * p.N + n));
                             v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
                         }
-                        if (p.act == ACT_RELU) {
+                        if (F_ACT == ACT_RELU) {
                             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                        } else if (p.act == ACT_GELU) {
+                        } else if (F_ACT == ACT_GELU) {
                             v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
                         }
-                        if (p.residual) {
+                        if (F_RES) {
                             const float4 t = resv[it];
                             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                         }
-                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
-                        if (p.out2_f32) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)rowtab[96 + row] * p.ldo + n) = v;
-                        if (p.out_bf16)
+                        if (F_OUT32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
+                        if (F_OUT2) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)rowtab[96 + row] * p.ldo + n) = v;
+                        if (F_OUT16)
                             *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po * p.ldo + n) =
-                                p.out_f16 ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w))
-                                          : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                                (!SP && p.out_f16) ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w))
+                                                   : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                     }
                 }
             }
-            if (p.head_w) {
+            if (!SP && p.head_w) {
                 float* hp = epi_base + q * 32 + lane;                           // [4 quadrants][32 rows]
                 if (half > 0) hp[(half - 1) * 128] = head;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // the epilogue warps only
@@ -522,6 +561,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             }
             tc_fence_before();
+            if (tr_e && ucount < 16) trc[(2 * 16 + ucount) * 4 + 2] = clock64();
             if constexpr (two) mbar_arrive_leader(&bars->tmem_empty[acc]); else mbar_arrive(&bars->tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
@@ -529,10 +569,71 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
 
     tc_fence_before();
     if constexpr (two) cluster_sync_all(); else __syncthreads();
+    if (tracing && threadIdx.x == 0) p.trace[768 + blockIdx.x * 2 + 1] = clock64();
     if (warp == 1) {
         tc_fence_after();
         if constexpr (two) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
+}
+
+#undef F_SCALE
+#undef F_SHIFT
+#undef F_ROWBIAS
+#undef F_RES
+#undef F_ACT
+#undef F_OUT32
+#undef F_OUT16
+#undef F_OUT2
+#undef F_KV
+
+// the flavours the denoiser's program uses (anything else runs the generic kernel)
+constexpr int kET = kEpiSpecial | kEpiTransposed | kEpiOut32;      // fp32 output, row-coalesced epilogue
+constexpr int kED = kEpiSpecial | kEpiOut16;                       // bf16 output, direct epilogue
+#define DSB_EPI_LIST(X)                                                                                             \
+    X(0)                                                                       /* generic                         */ \
+    X(kET | kEpiShift)                                                         /* 1x1 shortcut, plain linears     */ \
+    X(kET | kEpiShift | kEpiResidual)                                          /* P.V + proj bias, fc2            */ \
+    X(kET | kEpiScale | kEpiShift | kEpiRelu)                                  /* upembed.conv2 (last stage)      */ \
+    X(kET | kEpiScale | kEpiShift | kEpiRelu | kEpiResidual)                   /* upembed.conv2 + skip            */ \
+    X(kET | kEpiRelu)                                                          /* ReduceTemp                      */ \
+    X(kET | kEpiShift | kEpiRowbias)                                           /* res.conv1 + temb                */ \
+    X(kET | kEpiShift | kEpiOut2)                                              /* Downsample, two destinations    */ \
+    X(kEpiSpecial | kEpiOut32)                                                 /* split-K partial sums            */ \
+    X(kED | kEpiShift | kEpiGelu)                                              /* fc1                             */ \
+    X(kED | kEpiScale | kEpiShift | kEpiRelu)                                  /* upembed.conv1                   */ \
+    X(kED | kEpiShift | kEpiResidual)                                          /* res.conv2 + shortcut            */ \
+    X(kED | kEpiShift | kEpiKvK)                                               /* folded K projection             */ \
+    X(kED | kEpiShift | kEpiKvV)                                               /* folded V projection             */
+
+struct GemmVariant {
+    int epi;
+    const void* fn[2];      // [two_cta]
+};
+#define DSB_EPI_ROW(E) {(E), {(const void*)gemm_tc_kernel<false, (E)>, (const void*)gemm_tc_kernel<true, (E)>}},
+static const GemmVariant kVariants[] = {DSB_EPI_LIST(DSB_EPI_ROW)};
+static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+// epilogue flavour of a launch (0: generic)
+static int epi_of(const GemmParams& p) {
+    if (p.out_softmax || p.head_w || p.out_f16) return 0;
+    int e = kEpiSpecial;
+    if (p.epi_transposed) e |= kEpiTransposed;
+    if (p.scale) e |= kEpiScale;
+    if (p.shift) e |= kEpiShift;
+    if (p.rowbias) e |= kEpiRowbias;
+    if (p.residual) e |= kEpiResidual;
+    if (p.act == ACT_RELU) e |= kEpiRelu;
+    if (p.act == ACT_GELU) e |= kEpiGelu;
+    if (p.out_f32) e |= kEpiOut32;
+    if (p.out_bf16) e |= kEpiOut16;
+    if (p.out2_f32) e |= kEpiOut2;
+    if (p.kv_mode == 1) e |= kEpiKvK;
+    if (p.kv_mode == 2) e |= kEpiKvV;
+    static const bool off = [] { const char* v = getenv("DSB_EPI_GENERIC"); return v && v[0] == '1'; }();
+    if (off) return 0;
+    for (int i = 1; i < kNumVariants; ++i)
+        if (kVariants[i].epi == e) return i;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -579,10 +680,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 int gemm_init() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
+        for (int i = 0; i < kNumVariants; ++i)
+            for (int t = 0; t < 2; ++t) {
+                cudaError_t e = cudaFuncSetAttribute(kVariants[i].fn[t], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) return (int)e;
+            }
         attr_set = true;
     }
     return 0;
@@ -623,12 +725,25 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     if (stages < 2) return -15;
     const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBarriers) + epi_bytes + 1024;
     if (int e = gemm_init()) return e;
+    const int vi = epi_of(p);
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_f;
     if (!p.two_cta) {
         const int total = m_tiles * (p.N / p.bn) * (p.ksplit > 1 ? p.ksplit : 1);
         int grid = total < num_sms ? total : num_sms;
         if (grid < 1) return -16;
-        return (int)launch_pdl_ex(true, gemm_tc_kernel<false>, dim3(grid), dim3(kGemmThreads), smem, stream, p, tmA, tmB, stages);
+        void* args[4] = {(void*)&p, (void*)&tmA, (void*)&tmB, (void*)&stages};
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_use(true) ? 1 : 0;
+        return (int)cudaLaunchKernelExC(&cfg, kVariants[vi].fn[0], args);
     }
     const int pairs = ((m_tiles + 1) / 2) * (p.N / p.bn);
     int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
@@ -648,7 +763,8 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_use(true) ? 2 : 1;
-    return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, p, tmA, tmB, stages);
+    void* args[4] = {(void*)&p, (void*)&tmA, (void*)&tmB, (void*)&stages};
+    return (int)cudaLaunchKernelExC(&cfg, kVariants[vi].fn[1], args);
 }
 
 }  // namespace dsb

@@ -66,6 +66,11 @@ struct GemmParams {
     // n = head*kv_C + c.  kv_mode 1 writes out_bf16 as the score operand [frame][kv_R][kv_C] (row head*18 + j), kv_mode 2
     // as the transposed P.V operand [frame][kv_C][64] (column head*18 + j); padding rows / columns are never written.
     int kv_mode, kv_R, kv_C;
+    // per-role clock trace (tools/gemm_trace.py; null in the product path): CTAs 0..3 write, per work unit u < 16,
+    // trace[((cta * 3 + role) * 16 + u) * 4 + k] = clock64 at: role 0 (TMA producer) k0 first slot wait, k1 last load issued;
+    // role 1 (MMA issuer) k0 accumulator free, k1 first stage landed, k2 last MMA issued; role 2 (epilogue warp 2) k0 start of
+    // the wait for the accumulator, k1 accumulator complete, k2 epilogue done.  trace[768 + cta*2 + {0,1}] = kernel start / end.
+    unsigned long long* trace;
 };
 
 // One-time per-process kernel attribute setup (safe to call repeatedly; called outside stream capture).

@@ -26,6 +26,10 @@ static int g_test_ab_f16 = 0;
 // 1: A / Wt of dsb_test_conv hold fp16 values (GemmParams::ab_f16)
 extern "C" void dsb_test_set_ab_f16(int on) { g_test_ab_f16 = on; }
 
+static unsigned long long* g_test_trace = nullptr;
+// per-role clock trace buffer (GemmParams::trace; 784 x u64) for the next dsb_test_conv calls; NULL: off
+extern "C" void dsb_test_set_gemm_trace(void* buf) { g_test_trace = (unsigned long long*)buf; }
+
 static float* g_test_split_ws = nullptr;
 static long g_test_split_elems = 0;
 // split-K scratch for dsb_test_conv (NULL: never split); returns the slice count the LAST lowered op used
@@ -49,6 +53,7 @@ extern "C" int dsb_test_conv(int kind, int F, int H, int W, int Cin, int N, int 
     op.split_ws = g_test_split_ws; op.split_ws_elems = g_test_split_elems;
     op.halo = g_test_halo;
     op.ab_f16 = g_test_ab_f16;
+    op.trace = g_test_trace;
     ConvLaunch l;
     int r = conv_lower(op, &l);
     if (r) return r;

@@ -55,6 +55,9 @@ void dsb_test_set_split_ws(float* ws, long elems);
 int dsb_test_last_ksplit(void);
 /* 1: the A / Wt buffers of dsb_test_conv hold fp16 (not bf16) values -- the operand type of the output-head GEMMs */
 void dsb_test_set_ab_f16(int on);
+/* per-role clock64 trace of the GEMM kernel for the next dsb_test_conv calls (device buffer of 784 uint64; layout in
+ * csrc/gemm_tc.cuh GemmParams::trace; tools/gemm_trace.py); NULL switches it off */
+void dsb_test_set_gemm_trace(void* buf);
 /* request the halo-tile 3x3 path in dsb_test_conv, and whether its last call took it */
 void dsb_test_set_halo(int on);
 int dsb_test_last_halo(void);
