@@ -252,6 +252,35 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // ----------------------------------------------------------------------------------------------
+// explicit shared-memory accesses
+// ----------------------------------------------------------------------------------------------
+// The kernels carve their dynamic shared memory out of a pointer that was rounded up to 1024 bytes through an integer:
+// after that round trip the compiler no longer knows the address space and emits GENERIC loads / stores (LD.E / ST.E in
+// SASS) for ordinary dereferences.  Those take the global-memory path of the LSU and queue with the kernel's real global
+// stores -- the epilogues' shared-memory transposes cost ~1 k cycles per 32-column chunk that way.  These helpers take a
+// shared-window address (smem_u32) and always produce LDS / STS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    const uint4 v = lds128(addr);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return __uint_as_float(v);
+}
+
+// ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

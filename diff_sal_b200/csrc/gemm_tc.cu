@@ -73,6 +73,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + (size_t)num_stages * stage_bytes);
     // per-epilogue-warp transpose tile [32 rows][36 words] + row table, behind the barriers
     float* epi_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + sizeof(GemmBarriers));
+    float* epi_cst = epi_base + 128 * kPerQuad;            // [2 units in flight][scale 256 | shift 256] of the unit's N tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -298,6 +299,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
         uint32_t acc_phase = 0;
         int ucount = 0;
         const bool tr_e = tracing && warp == 2 && lane == 0;
+        const int dbg = p.trace ? (int)p.trace[780] : 0;      // tools/gemm_trace.py experiments: 1 = no stores, 2 = no TMEM loads
         for (int unit = unit0; unit < total_units; unit += unit_step, ++ucount) {
             if (tr_e && ucount < 16) trc[(2 * 16 + ucount) * 4 + 0] = clock64();
             const int tile = unit / ksplit, ks = unit - tile * ksplit;
@@ -317,6 +319,19 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             const size_t pix_out2 = ((size_t)(fo * p.out2_fmul + p.out2_fadd) * p.H + y) * p.W + x;
             const int n0 = nt * p.bn;
 
+            // The unit's per-column constants go to shared memory while the MMAs of the unit are still running: read from
+            // global inside the chunk loops, every chunk paid an exposed L2 round trip for a new cache line of them
+            // (the dominant stall of the bf16 epilogues in the ncu source view).  Two buffers: a warp that runs ahead
+            // into the next unit must not overwrite what a slower warp still reads.
+            const uint32_t cs = smem_u32(epi_cst + (ucount & 1) * 512);   // shared-window byte address
+            if (F_SCALE || F_SHIFT) {
+                const int et = (int)threadIdx.x - 64;
+                if (et < p.bn) {
+                    sts32(cs + 4u * et, F_SCALE ? __ldg(p.scale + n0 + et) : 1.0f);
+                    sts32(cs + 4u * (256 + et), F_SHIFT ? __ldg(p.shift + n0 + et) : 0.0f);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // the epilogue warps only
+            }
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
             if (tr_e && ucount < 16) trc[(2 * 16 + ucount) * 4 + 1] = clock64();
@@ -399,14 +414,14 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                         if (F_SCALE) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.scale + n) + j);
+                                const float4 t = lds128f(cs + 4u * (c + 4 * j));
                                 v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                             }
                         }
                         if (F_SHIFT) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + n) + j);
+                                const float4 t = lds128f(cs + 4u * (256 + c + 4 * j));
                                 v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                             }
                         }
@@ -479,48 +494,50 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
             } else {
                 // general epilogue: 32-column chunks are transposed through shared memory so that one warp
                 // instruction touches whole 128-byte rows (coalesced residual loads and output stores)
-                float* tile = epi_base + 128 * kPerQuad + (warp - 2) * (32 * 36 + 128);
-                int* rowtab = reinterpret_cast<int*>(tile + 32 * 36);      // [32]: pix_out | pix_in | frame | pix_out2
-                __syncwarp();
-                rowtab[lane * 3 + 0] = valid ? (int)pix_out : -1;
-                rowtab[lane * 3 + 1] = (int)pix_in;
-                rowtab[lane * 3 + 2] = fs;
-                rowtab[96 + lane] = (int)pix_out2;
-                __syncwarp();
+                const uint32_t tile = smem_u32(epi_base + 128 * kPerQuad + 1024 + (warp - 2) * (32 * 36 + 128));   // [32][36] floats
                 const int cq = (lane & 7) * 4;                             // this lane's 4 columns inside the chunk
                 const int rq = lane >> 3;                                  // row offset inside a group of 4 rows
+                // where the 8 rows this lane stores (row = it * 4 + rq) go: fetched once per unit from the lanes that own
+                // those rows (shuffles; the store loop below has no load-dependent branch or address)
+                int po[8];
+                {
+                    const int my_po = valid ? (int)pix_out : -1;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) po[it] = __shfl_sync(0xffffffffu, my_po, it * 4 + rq);
+                }
                 for (int c = half * 32; c < p.bn; c += 32 * kPerQuad) {
-                    // the chunk's residual rows (coalesced: 4 rows x 128 B per instruction) are requested before the
-                    // TMEM load so that their DRAM latency overlaps the tcgen05.ld + smem transpose
+                    // the chunk's residual rows (coalesced: 4 rows x 128 B per instruction) and per-column constants are
+                    // requested before the TMEM load so that their latency overlaps the tcgen05.ld + smem transpose
+                    const int n = n0 + c + cq;
                     float4 resv[8];
                     if (F_RES) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
-                            const int row = it * 4 + rq;
                             resv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rowtab[row * 3 + 0] >= 0)
-                                resv[it] = *reinterpret_cast<const float4*>(p.residual + (size_t)rowtab[row * 3 + 1] * p.N + n0 + c + cq);
+                            const int pin = __shfl_sync(0xffffffffu, (int)pix_in, it * 4 + rq);
+                            if (po[it] >= 0) resv[it] = *reinterpret_cast<const float4*>(p.residual + (size_t)pin * p.N + n);
                         }
                     }
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (F_SCALE) sc = lds128f(cs + 4u * (c + cq));
+                    if (F_SHIFT) sh = lds128f(cs + 4u * (256 + c + cq));
                     uint32_t raw[32];
-                    tmem_ld32(t_addr + c, raw);
-                    tmem_ld_wait();
+                    if (dbg != 2) {
+                        tmem_ld32(t_addr + c, raw);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) raw[j] = 0u;
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(tile + lane * 36 + 4 * j) =
-                            make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+                        sts128(tile + 4u * (lane * 36 + 4 * j), make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]));
                     __syncwarp();
-                    const int n = n0 + c + cq;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (F_SCALE) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-                    if (F_SHIFT) sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int row = it * 4 + rq;
-                        const int po = rowtab[row * 3 + 0];
-                        if (po < 0) continue;
-                        float4 v = *reinterpret_cast<const float4*>(tile + row * 36 + cq);
+                        float4 v = lds128f(tile + 4u * (row * 36 + cq));
                         if (F_SCALE) {
                             v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
                             v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
@@ -528,8 +545,11 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
                         }
                         if (F_ROWBIAS) {
-                            const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)rowtab[row * 3 + 2] * p.N + n));
-                            v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
+                            const int fr = __shfl_sync(0xffffffffu, fs, row);
+                            if (po[it] >= 0) {
+                                const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)fr * p.N + n));
+                                v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
+                            }
                         }
                         if (F_ACT == ACT_RELU) {
                             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
@@ -540,12 +560,17 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, cons
                             const float4 t = resv[it];
                             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                         }
-                        if (F_OUT32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po * p.ldo + n) = v;
-                        if (F_OUT2) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)rowtab[96 + row] * p.ldo + n) = v;
-                        if (F_OUT16)
-                            *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po * p.ldo + n) =
-                                (!SP && p.out_f16) ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w))
-                                                   : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                        if (F_OUT2) {
+                            const int po2 = __shfl_sync(0xffffffffu, (int)pix_out2, row);
+                            if (po[it] >= 0) *reinterpret_cast<float4*>(p.out2_f32 + (size_t)po2 * p.ldo + n) = v;
+                        }
+                        if (po[it] >= 0 && dbg != 1) {
+                            if (F_OUT32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)po[it] * p.ldo + n) = v;
+                            if (F_OUT16)
+                                *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)po[it] * p.ldo + n) =
+                                    (!SP && p.out_f16) ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w))
+                                                       : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                        }
                     }
                 }
             }
@@ -718,7 +743,7 @@ int gemm_launch(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& 
         stage_bytes = (((uint32_t)(p.halo_pw * p.halo_ph) * (uint32_t)p.bk * 2u + 1023u) & ~1023u) +
                       9u * (uint32_t)(p.two_cta ? p.bn / 2 : p.bn) * (uint32_t)p.bk * 2u;
     }
-    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad) * sizeof(float);
+    const uint32_t epi_bytes = (uint32_t)((p.epi_transposed ? kEpiWarps * (32 * 36 + 128) : 0) + 128 * kPerQuad + 1024) * sizeof(float);
     const uint32_t budget = 225u * 1024u - 1024u - (uint32_t)sizeof(GemmBarriers) - epi_bytes;
     int stages = (int)(budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;

@@ -8,6 +8,7 @@ from diff_sal_b200 import _lib as L
 M, Cin, N = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 act = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 want_bf16 = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+dbg = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 lib = L.test_lib()
 g = torch.Generator().manual_seed(0)
 a = (torch.randn(M, Cin, generator=g)).to(torch.bfloat16).cuda()
@@ -29,6 +30,7 @@ e0.record()
 for _ in range(20): run()
 e1.record(); torch.cuda.synchronize()
 print("M=%d K=%d N=%d act=%d: %.2f us per launch, %.1f TF/s" % (M, Cin, N, act, 1e3 * e0.elapsed_time(e1) / 20, 2.0 * M * Cin * N / (e0.elapsed_time(e1) / 20 * 1e-3) / 1e12))
+trace[780] = dbg
 lib.dsb_test_set_gemm_trace(ctypes.c_void_p(trace.data_ptr()))
 run(); torch.cuda.synchronize()
 lib.dsb_test_set_gemm_trace(None)
