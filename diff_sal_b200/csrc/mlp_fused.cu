@@ -41,14 +41,17 @@ struct __align__(16) MlpBarriers {
     uint32_t pad[3];
 };
 
+// MODE and C are compile-time (four instantiations): every loop bound, operand size and descriptor step below is then a
+// constant, as in the specialised epilogues of gemm_tc.cu
+template <int MODE, int C>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const int NS) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int C = p.C, bk = p.bk;
-    const int ksub = C / bk;                       // K sub-blocks of GEMM1
-    const int NC = p.mode ? 1 : 2 * C / kHC;       // hidden chunks per tile (attention: one chunk of 2 x 18 (+28) keys)
+    constexpr int bk = (C % 64 == 0) ? 64 : 32;
+    constexpr int ksub = C / bk;                   // K sub-blocks of GEMM1
+    constexpr int NC = MODE ? 1 : 2 * C / kHC;     // hidden chunks per tile (attention: one chunk of 2 x 18 (+28) keys)
     const uint32_t a_sub = 128u * bk * 2u;
     const uint32_t a_bytes = a_sub * ksub;
     const uint32_t w1_sub = (uint32_t)kHC * bk * 2u;
@@ -115,7 +118,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                     uint8_t* w = sW1 + s * w1_bytes;
                     mbar_expect_tx(&bars->w1_full[s], w1_bytes);
                     for (int j = 0; j < ksub; ++j)
-                        tma_load_2d(w + j * w1_sub, &tmW1, &bars->w1_full[s], j * bk, h * kHC + (p.mode ? fs * kHC : 0));
+                        tma_load_2d(w + j * w1_sub, &tmW1, &bars->w1_full[s], j * bk, h * kHC + (MODE ? fs * kHC : 0));
                 }
                 __syncwarp();
             }
@@ -131,7 +134,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                 mbar_wait(&bars->w2_empty[s], ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&bars->w2_full[s], w2_bytes);
-                    tma_load_2d(sW2 + s * w2_bytes, &tmW2, &bars->w2_full[s], h * kHC, p.mode ? fs * C : 0);
+                    tma_load_2d(sW2 + s * w2_bytes, &tmW2, &bars->w2_full[s], h * kHC, MODE ? fs * C : 0);
                 }
                 __syncwarp();
             }
@@ -145,7 +148,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
         const uint64_t dW1 = umma_smem_desc(smem_u32(sW1), rb1);
         const uint64_t dW2 = umma_smem_desc(smem_u32(sW2), 128u);
         const uint64_t dA2 = umma_smem_desc(smem_u32(sA2), 128u);
-        const int k1 = bk / 16;
+        constexpr int k1 = bk / 16;
         uint32_t gbase = 0, it = 0;
 
         auto issue_g1 = [&](int h) {
@@ -216,7 +219,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->acc1_empty[s]);
                 uint32_t packed[16];
-                if (p.mode == 0) {
+                if (MODE == 0) {
                     const float* b1 = p.b1 + h * kHC + half * 32;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -298,7 +301,7 @@ mlp_fused_kernel(const MlpParams p, const __grid_constant__ CUtensorMap tmA, con
         // residual of chunk c + 1 is requested before chunk c is processed.
         const int q = warp & 3;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int nch = C / 32;
+        constexpr int nch = C / 32;
         float* tile = reinterpret_cast<float*>(bars + 1) + 1024 + (warp - 10) * (32 * 36);   // behind the 4 KB softmax exchange
         const int cq = (lane & 7) * 4;                      // this lane's 4 columns inside a chunk
         const int rq = lane >> 3;                           // row offset inside a group of 4 rows
@@ -416,14 +419,22 @@ int mlp_fused_run(const MlpLaunch& l, int num_sms, cudaStream_t stream) {
     const size_t smem = fixed + (size_t)NS * w_stage;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
+        const void* fns[4] = {(const void*)mlp_fused_kernel<0, 96>, (const void*)mlp_fused_kernel<0, 192>,
+                              (const void*)mlp_fused_kernel<1, 96>, (const void*)mlp_fused_kernel<1, 192>};
+        for (const void* f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+        }
         attr = true;
     }
     const int tiles = ((p.HW + 127) / 128) * p.F;
     int grid = tiles < num_sms ? tiles : num_sms;
     if (grid < 1) return -41;
-    return (int)launch_pdl_ex(true, mlp_fused_kernel, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
+    if (p.mode == 0 && p.C == 96) return (int)launch_pdl_ex(true, mlp_fused_kernel<0, 96>, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
+    if (p.mode == 0 && p.C == 192) return (int)launch_pdl_ex(true, mlp_fused_kernel<0, 192>, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
+    if (p.mode == 1 && p.C == 96) return (int)launch_pdl_ex(true, mlp_fused_kernel<1, 96>, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
+    if (p.mode == 1 && p.C == 192) return (int)launch_pdl_ex(true, mlp_fused_kernel<1, 192>, dim3(grid), dim3(kMlpThreads), smem, stream, p, l.tmA, l.tmW1, l.tmW2, NS);
+    return -40;
 }
 
 }  // namespace dsb
