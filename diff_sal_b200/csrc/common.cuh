@@ -251,6 +251,14 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return launch_pdl_ex(false, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
+// 1-D bulk copy global -> shared (TMA without a tensor map): `bytes` (multiple of 16, both addresses 16-byte aligned)
+// land at `dst` and are credited to `bar` like a tensor load
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // explicit shared-memory accesses
 // ----------------------------------------------------------------------------------------------

@@ -273,30 +273,62 @@ int gn_apply_launch(const float* x, int F, int HW, int C, const double* acc, con
 // all CL partial sets in rank order -> the same bits in every CTA, run to run); pass 2 re-reads the slice (L2-resident:
 // the encoder tensors are 2 - 33 MB) and writes bf16(swish(GN(x))) and, optionally, bf16(x).  Replaces the
 // gn_stats_kernel / gn_apply_kernel pair (two launches and a last-block fold per GroupNorm, six GroupNorms per evaluation).
+// Round 2b: the CTA's slice of the frame (HW / CL pixels x C channels, 32 - 258 KB) is fetched ONCE by 1-D TMA bulk
+// copies into shared memory, all requested up front by one thread; both passes then read shared memory.  The first
+// version streamed the slice twice through ordinary loads: with one 512-thread CTA per SM only ~12 KB were in flight per
+// SM and the six GroupNorms of the (strictly serial) noise encoder ran at 0.4 - 1.2 TB/s.  What does not fit in the
+// kGnSmemCap bytes (only the C = 192 map of the first block: 258 KB per CTA) is streamed as before.
+constexpr uint32_t kGnSmemCap = 192u * 1024u;
+constexpr uint32_t kGnChunk = 32u * 1024u;
+
 template <int CL>
 __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__ x, int HW, int C,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       bf16* __restrict__ out_act, bf16* __restrict__ out_raw) {
     pdl_trigger();
     pdl_wait();
+    extern __shared__ __align__(128) float4 gsl[];         // resident part of the slice
     __shared__ float ssum[4][768];
     __shared__ float ssq[4][768];
     __shared__ double part[32][2];
     __shared__ float mean[32], rstd[32];
+    __shared__ __align__(8) uint64_t bar;
     const unsigned rank = cluster_ctarank();
     const int f = blockIdx.x / CL, tid = threadIdx.x;
     const int cv_n = C >> 2, cg = C >> 5;
     const int per = (HW + CL - 1) / CL;
     const int p0 = (int)rank * per, p1 = min(HW, p0 + per);
     const float4* base = reinterpret_cast<const float4*>(x + (size_t)f * HW * C);
+    const int res_px = max(0, min(p1 - p0, (int)(kGnSmemCap / ((uint32_t)C * 4u))));   // pixels kept in shared memory
+    const int pr = p0 + res_px;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)res_px * (uint32_t)C * 4u;
+        mbar_expect_tx(&bar, bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(base + (size_t)p0 * cv_n);
+        const uint32_t dst = smem_u32(gsl);
+        for (uint32_t o = 0; o < bytes; o += kGnChunk) tma_bulk_load(dst + o, src + o, min(kGnChunk, bytes - o), &bar);
+    }
     // ---- pass 1: thread = (4-channel vector, pixel lane); 512 threads = P pixel lanes x cv_n vectors (P = 21 .. 2)
     const int P = min(4, 512 / cv_n);                     // smem holds 4 lanes; more lanes fold into them below
     const int PL = 512 / cv_n;                            // pixel lanes actually running
     const int cv = tid % cv_n, pl = tid / cv_n;
     float4 s4 = make_float4(0, 0, 0, 0), q4 = make_float4(0, 0, 0, 0);
+    mbar_wait(&bar, 0u);
     if (pl < PL) {
+        int px = p0 + pl;
 #pragma unroll 8
-        for (int px = p0 + pl; px < p1; px += PL) {
+        for (; px < pr; px += PL) {
+            const float4 v = gsl[(size_t)(px - p0) * cv_n + cv];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
+        }
+#pragma unroll 8
+        for (; px < p1; px += PL) {
             const float4 v = base[(size_t)px * cv_n + cv];
             s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
             q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
@@ -318,24 +350,33 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
         __syncthreads();
     }
     if (tid < 32) {
-        double sm = 0.0, sq = 0.0;
+        // fp64 is slow on this part (a dependent DADD chain of 4 x cg = 12 .. 96 links cost microseconds): one chain per
+        // smem lane, joined in lane order
+        double sml[4] = {0.0, 0.0, 0.0, 0.0}, sql[4] = {0.0, 0.0, 0.0, 0.0};
         const int lanes = min(P, PL);
-        for (int l = 0; l < lanes; ++l)
-            for (int k = 0; k < cg; ++k) { sm += (double)ssum[l][tid * cg + k]; sq += (double)ssq[l][tid * cg + k]; }
-        part[tid][0] = sm;
-        part[tid][1] = sq;
+        for (int k = 0; k < cg; ++k) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+                if (l < lanes) { sml[l] += (double)ssum[l][tid * cg + k]; sql[l] += (double)ssq[l][tid * cg + k]; }
+        }
+        part[tid][0] = (sml[0] + sml[1]) + (sml[2] + sml[3]);
+        part[tid][1] = (sql[0] + sql[1]) + (sql[2] + sql[3]);
     }
     cluster_sync_all();                                    // partials of all CL CTAs are visible cluster-wide
     if (tid < 32) {
         double sm = 0.0, sq = 0.0;
         const uint32_t local = smem_u32(&part[tid][0]);
-        for (unsigned r = 0; r < CL; ++r) {                // rank order: identical bits in every CTA
+        double pa[CL], pb[CL];
+#pragma unroll
+        for (unsigned r = 0; r < CL; ++r) {                // all remote reads in flight together (they were serialised)
             uint32_t remote;
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-            double a, b;
-            asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(remote));
-            sm += a;
-            sq += b;
+            asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(pa[r]), "=d"(pb[r]) : "r"(remote));
+        }
+#pragma unroll
+        for (unsigned r = 0; r < CL; ++r) {                // rank order: identical bits in every CTA
+            sm += pa[r];
+            sq += pb[r];
         }
         const double n = (double)HW * cg;
         const double m = sm / n;
@@ -345,10 +386,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
         rstd[tid] = (float)(1.0 / sqrt(v + 1e-6));
     }
     cluster_sync_all();                                    // nobody leaves (or overwrites part) while peers still read it
-    // ---- pass 2: apply + swish over the same slice
-    const int total = (p1 - p0) * cv_n;
-    // 512 is not always a multiple of cv_n (C = 96: 24 | 512 ? no) -> recompute the vector index per element
-    const uint2* dummy = nullptr; (void)dummy;
+    // ---- pass 2: apply + swish over the same slice (resident part from shared memory)
+    const int total = (p1 - p0) * cv_n, total_res = res_px * cv_n;
     const float4* xin = base + (size_t)p0 * cv_n;
     uint2* oa = reinterpret_cast<uint2*>(out_act + (size_t)f * HW * C) + (size_t)p0 * cv_n;
     uint2* orw = out_raw ? reinterpret_cast<uint2*>(out_raw + (size_t)f * HW * C) + (size_t)p0 * cv_n : nullptr;
@@ -363,7 +402,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
                     bw = fmaf(-mean[g3], aw, bt.w);
 #pragma unroll 8
         for (int i = tid; i < total; i += stride) {
-            const float4 v = xin[i];
+            const float4 v = i < total_res ? gsl[i] : xin[i];
             oa[i] = make_uint2(pack_bf16x2(swishf(fmaf(v.x, ax, bx)), swishf(fmaf(v.y, ay, by))),
                                pack_bf16x2(swishf(fmaf(v.z, az, bz)), swishf(fmaf(v.w, aw, bw))));
             if (orw) orw[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -381,12 +420,19 @@ static int gn_fused_launch_cl(const float* x, int F, int HW, int C, const float*
             (void)cudaGetLastError();
             ok = 0;
         }
+        if (ok && cudaFuncSetAttribute(gn_fused_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSmemCap) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ok = 0;
+        }
     }
     if (!ok) return -1000;
+    const int per = (HW + CL - 1) / CL;
+    const size_t slice = (size_t)per * C * 4;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(F * CL);
     cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = slice < kGnSmemCap ? slice : kGnSmemCap;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
