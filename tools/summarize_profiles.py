@@ -37,7 +37,7 @@ with open(os.path.join(P, R + "_launches_summary.txt"), "w") as f:
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%-60s n=%4d %11.1f us %6.1f%%\n" % (k[:60], n, us, 100 * us / tot))
 gemm_us = sum(us for k, (n, us) in agg.items() if "gemm_tc" in k or "mlp_fused" in k or "splitk" in k)
-prep_us = sum(us for k, (n, us) in agg.items() if any(t in k for t in ("pack_", "bn_fold", "stem_compose", "transpose", "nct_to_frames", "audio_tokens")))
+prep_us = sum(us for k, (n, us) in agg.items() if any(t in k for t in ("pack_", "bn_fold", "stem_compose", "transpose", "nct_to_frames", "audio_tokens", "fold_weights", "fold_bias", "q_dw_prep", "dw_affine_prep", "audio_cmajor")))
 print("launch list: %d launches, GEMM-class share of the two evaluations %.1f%%" % (len(rows), 100 * gemm_us / (tot - prep_us)))
 
 # ---------------------------------------------------------------- (2) GEMM traffic (second evaluation)
@@ -81,7 +81,7 @@ want = [("gpu__time_duration.sum", "us"), ("sm__throughput.avg.pct_of_peak_susta
         ("sm__inst_executed_pipe_tensor.sum", "tc_inst")]
 with open(os.path.join(P, R + "_gemm_sol.txt"), "w") as f:
     f.write("# ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy "
-            "--clock-control none -k regex:'gemm_tc|mlp_fused' --launch-skip 51 --launch-count 47 python tools/ncu_one_eval.py\n")
+            "--clock-control none -k regex:'gemm_tc|mlp_fused' --launch-skip 47 --launch-count 43 python tools/ncu_one_eval.py\n")
     f.write("# every tensor-core launch of the second (warm) B=8 evaluation, in program order\n")
     f.write("%3s %-22s %9s %6s %6s %9s %9s %5s %3s\n" % ("#", "kernel", "us", "sm%", "dram%", "dram GB/s", "warps%", "grid", "clu"))
     ki = h.index("Kernel Name")
@@ -100,8 +100,8 @@ keys = ["Kernel Name", "Grid Size", "Block Size", "launch__cluster_size", "gpu__
         "sm__inst_executed_pipe_tensor.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-for rep, outn, what in [(R + "_gemm_mtproj", R + "_gemm_mtproj_ncu.txt", "mt_proj 3x3 768->96 + BN + ReLU + fused 96->1 head, 112x192, B=8 (--launch-skip 89)"),
-                        (R + "_gemm_upconv1", R + "_gemm_upconv1_ncu.txt", "upembed.conv1 of stage 1: dilated 3x3 768->384 + BN + ReLU on 72 frames of 14x24 (--launch-skip 68)"),
+for rep, outn, what in [(R + "_gemm_mtproj", R + "_gemm_mtproj_ncu.txt", "mt_proj 3x3 768->96 + BN + ReLU + fused 96->1 head, 112x192, B=8 (--launch-skip 81)"),
+                        (R + "_gemm_upconv1", R + "_gemm_upconv1_ncu.txt", "upembed.conv1 of stage 1: dilated 3x3 768->384 + BN + ReLU on 72 frames of 14x24 (--launch-skip 62)"),
                         (R + "_mlp_fused", R + "_mlp_fused_ncu.txt", "mlp_fused_kernel, MLP chain of the last stage: fc1 -> GELU -> fc2 -> +residual, C = 96, 215 040 live tokens (-k regex:mlp_fused --launch-skip 7)")]:
     if not os.path.exists(os.path.join(G, rep + ".ncu-rep")):
         continue
