@@ -182,3 +182,47 @@ extern "C" int dsb_test_mlp_fused(int C, int HW, int F, int f_group, int f_used,
     if (int r = mlp_fused_lower(op, &l)) return r;
     return mlp_fused_run(l, num_sms_cached(), (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// query / output projections folded into the K / V projection weights (kernels.cu, plan.cu): weight folding, the two
+// projection GEMMs with the operand-layout epilogues, and the score bias produced by the K pooling kernel.
+// k_ln / v_ln: bf16 [F*18][C]; K1: bf16 [F][R][C], V2: bf16 [F][C][64] (caller zero-fills both); mb fp32 [2][C], cb fp32 [2]
+extern "C" int dsb_test_fold_kv(const float* wq, const float* bq, const float* wk, const float* bk, const float* wp,
+                                const float* wv, const float* bv, int C, int F, int R, const void* k_ln, const void* v_ln,
+                                void* K1, void* V2, float* mb, float* cb, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    float *MK = nullptr, *MV = nullptr, *cK = nullptr, *cV = nullptr;
+    bf16 *pk = nullptr, *pv = nullptr;
+    const size_t cc = (size_t)2 * C * C;
+    if (cudaMalloc(&MK, cc * 4) || cudaMalloc(&MV, cc * 4) || cudaMalloc(&cK, 2 * C * 4) || cudaMalloc(&cV, 2 * C * 4) ||
+        cudaMalloc(&pk, cc * 2) || cudaMalloc(&pv, cc * 2))
+        return -1;
+    int r = fold_weights_launch(wq, bq, wk, bk, wp, wv, bv, C, 1.0f / sqrtf((float)C), MK, MV, cK, cV, mb, cb, s);
+    if (!r) r = pack_weight_launch(MK, 2 * C, C, 1, pk, s);
+    if (!r) r = pack_weight_launch(MV, 2 * C, C, 1, pv, s);
+    for (int which = 0; which < 2 && !r; ++which) {
+        ConvOp op;
+        memset(&op, 0, sizeof(op));
+        op.kind = CONV_1X1; op.F = 1; op.H = 1; op.W = F * 18; op.Cin = C; op.N = 2 * C; op.dilation = 1; op.T = 1; op.kt = 1;
+        op.A = (const bf16*)(which ? v_ln : k_ln); op.Wt = which ? pv : pk;
+        op.shift = which ? cV : cK;
+        op.out_bf16 = (bf16*)(which ? V2 : K1);
+        op.kv_mode = which ? 2 : 1; op.kv_R = R; op.kv_C = C;
+        ConvLaunch l;
+        r = conv_lower(op, &l);
+        if (!r) r = conv_run(l, num_sms_cached(), s);
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(MK); cudaFree(MV); cudaFree(cK); cudaFree(cV); cudaFree(pk); cudaFree(pv);
+    return r;
+}
+
+// dsb_test_pool_ln with the folded score bias as a by-product: sb fp32 [F][R] rows head*18 + key (caller zero-fills)
+extern "C" int dsb_test_pool_ln_sb(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb,
+                                   const float* w, const float* g, const float* b, void* stats_scratch, void* out, int T,
+                                   int tmax, const float* mb, const float* cb, float* sb, int R, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int r = ln_stats_launch(x, (long)F * H * W, C, (float2*)stats_scratch, H * W, T, tmax, s)) return r;
+    return pool_ln_launch(x, (const float2*)stats_scratch, F, H, W, C, sk, ng, nb, w, g, b, (bf16*)out, T, tmax, s,
+                          ScoreBias{mb, cb, sb, R});
+}

@@ -67,6 +67,17 @@ int dsb_test_last_halo(void);
 int dsb_test_umma_shift(const void* A, const void* B, float* out, int shift_rows, int sbo_bytes, int base_offset_mode,
                         void* stream);
 
+/* Projections folded into the K / V projection weights (csrc/kernels.cu "projections folded into K / V"): folds the fp32
+ * weights, runs the two projection GEMMs with the attention-operand epilogues.  k_ln / v_ln bf16 [F*18][C]; K1 bf16
+ * [F][R][C], V2 bf16 [F][C][64] (zero-filled by the caller: padding is never written); mb fp32 [2][C], cb fp32 [2] out. */
+int dsb_test_fold_kv(const float* wq, const float* bq, const float* wk, const float* bk, const float* wp, const float* wv,
+                     const float* bv, int C, int F, int R, const void* k_ln, const void* v_ln, void* K1, void* V2,
+                     float* mb, float* cb, void* stream);
+/* dsb_test_pool_ln + the folded score bias sb fp32 [F][R] (row head*18 + key) = pooled_token . mb[head] + cb[head] */
+int dsb_test_pool_ln_sb(const float* x, int F, int H, int W, int C, int sk, const float* ng, const float* nb, const float* w,
+                        const float* g, const float* b, void* stats_scratch, void* out, int T, int tmax, const float* mb,
+                        const float* cb, float* sb, int R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

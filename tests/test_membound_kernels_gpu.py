@@ -239,3 +239,64 @@ def test_timestep_embedding_mlp(L, tvals):
     for o, wp, bp in zip(outs, wps, bps):
         ref = F.linear(h, wp, bp)
         assert (o - ref).abs().max().item() <= 3e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("C,Fr,R", [(96, 3, 64), (192, 2, 64), (384, 2, 48), (768, 1, 48)])
+def test_projections_folded_into_kv(L, C, Fr, R):
+    """attention.py:97-113 with proj_q folded into proj_k and proj into proj_v at the WEIGHT level (plan.cu kFoldProj):
+    the K / V projection GEMMs emit the score operand K'[f][h*18+j][c], the P.V operand V''[f][c][h*18+j] and the K pooling
+    kernel the folded score bias; all three against the unfused fp32 formulas."""
+    wq, wk_, wv, wp = (rnd(C, C, seed=70 + i, scale=C ** -0.5) for i in range(4))
+    bq, bk, bv = (rnd(C, seed=80 + i, scale=0.2) for i in range(3))
+    k_ln = rnd(Fr * 18, C, seed=90).to(torch.bfloat16)
+    v_ln = rnd(Fr * 18, C, seed=91).to(torch.bfloat16)
+    K1 = torch.zeros(Fr, R, C, device="cuda", dtype=torch.bfloat16)
+    V2 = torch.zeros(Fr, C, 64, device="cuda", dtype=torch.bfloat16)
+    mb = torch.zeros(2, C, device="cuda")
+    cb = torch.zeros(2, device="cuda")
+    check(L.test_lib().dsb_test_fold_kv(L.ptr(wq), L.ptr(bq), L.ptr(wk_), L.ptr(bk), L.ptr(wp), L.ptr(wv), L.ptr(bv), C, Fr, R,
+                                        L.ptr(k_ln), L.ptr(v_ln), L.ptr(K1), L.ptr(V2), L.ptr(mb), L.ptr(cb), L.stream_ptr()))
+    torch.cuda.synchronize()
+    scale, d = C ** -0.5, C // 2
+    K = (k_ln.float() @ wk_.t() + bk).reshape(Fr, 18, C)
+    V = (v_ln.float() @ wv.t() + bv).reshape(Fr, 18, C)
+    K1_ref = torch.zeros(Fr, R, C, device="cuda")
+    V2_ref = torch.zeros(Fr, C, 64, device="cuda")
+    sb_ref = torch.zeros(Fr, R, device="cuda")
+    for h in range(2):
+        sl = slice(h * d, (h + 1) * d)
+        K1_ref[:, h * 18:(h + 1) * 18] = scale * K[:, :, sl] @ wq[sl, :]
+        sb_ref[:, h * 18:(h + 1) * 18] = scale * K[:, :, sl] @ bq[sl]
+        V2_ref[:, :, h * 18:(h + 1) * 18] = (V[:, :, sl] @ wp[:, sl].t()).transpose(1, 2)
+    tol = 3 * BF
+    assert (K1.float() - K1_ref).abs().max().item() <= tol * max(1.0, K1_ref.abs().max().item())
+    assert (V2.float() - V2_ref).abs().max().item() <= tol * max(1.0, V2_ref.abs().max().item())
+    assert K1[:, 36:].abs().max().item() == 0 and V2[:, :, 36:].abs().max().item() == 0      # padding untouched
+    # folded score bias: sb[f][h*18+j] = k_ln[j] . mb[h] + cb[h] must equal scale * K_h[j] . bq_h
+    sb_from_tables = torch.zeros(Fr, R, device="cuda")
+    kl = k_ln.float().reshape(Fr, 18, C)
+    for h in range(2):
+        sb_from_tables[:, h * 18:(h + 1) * 18] = kl @ mb[h] + cb[h]
+    assert (sb_from_tables - sb_ref).abs().max().item() <= 1e-4 * max(1.0, sb_ref.abs().max().item())
+
+
+def test_score_bias_from_pooling_kernel(L):
+    """the K pooling kernels write sb[f][h*18+j] = k_ln[f,j] . mb[h] + cb[h] beside the pooled tokens (kernels.cu ScoreBias)"""
+    Fr, H, W, C, s, R = 2, 28, 48, 192, 8, 64
+    x = rnd(Fr, C, H, W, seed=13, scale=1.3)
+    ng, nb = rnd(C, seed=14, scale=0.2, shift=1.0), rnd(C, seed=15, scale=0.1)
+    wv = rnd(C, 1, 1, s, s, seed=16, scale=1.0 / s)
+    vg, vb = rnd(C, seed=17, scale=0.2, shift=1.0), rnd(C, seed=18, scale=0.1)
+    mb, cb = rnd(2, C, seed=19, scale=0.1), rnd(2, seed=20)
+    wt = wv.reshape(C, s * s).t().contiguous()
+    out = torch.empty(Fr * 18, C, device="cuda", dtype=torch.bfloat16)
+    sb = torch.zeros(Fr, R, device="cuda")
+    stats = torch.empty(Fr * H * W, 2, device="cuda")
+    check(L.test_lib().dsb_test_pool_ln_sb(L.ptr(nhwc(x)), Fr, H, W, C, s, L.ptr(ng), L.ptr(nb), L.ptr(wt), L.ptr(vg), L.ptr(vb),
+                                           L.ptr(stats), L.ptr(out), 1, 1, L.ptr(mb), L.ptr(cb), L.ptr(sb), R, L.stream_ptr()))
+    torch.cuda.synchronize()
+    tok = out.float().reshape(Fr, 18, C)
+    for h in range(2):
+        ref = tok @ mb[h] + cb[h]
+        assert (sb[:, h * 18:(h + 1) * 18] - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert sb[:, 36:].abs().max().item() == 0
