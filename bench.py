@@ -255,21 +255,18 @@ def run_b200(args):
         sets.append((x.to(dev), [f.to(dev) for f in feats[:3]], aud.to(dev)))
     n_clips_total = B * world
     gatherer = MapGatherer(n_clips_total, (1, 224, 384), torch.float32, dev)     # preallocated gather buffers
-    xbufs = [torch.empty_like(sets[0][0]) for _ in range(2)]
+    xbuf = torch.empty_like(sets[0][0])
 
-    # N > 1: the all-gather of step k's maps runs on a side stream (MapGatherer.start) beside the loop of step k + 1; two
-    # state buffers / gather slots alternate, and the timed region ends only after the last gathers have completed
+    # The gather stays in line: MapGatherer.start / finish can put it on a side stream beside the next step's loop, which
+    # measured +1.7 % at N = 2 but -1.1 % at N = 8 (the NCCL kernel's CTAs take SMs from the persistent one-CTA-per-SM
+    # tensor-core kernels and break up their CTA pairs) -- DESIGN.md section 7.
     def step(k, wait=True):
         x, feats, aud = sets[k & 1]
-        b = k & 1
-        if world > 1:
-            gatherer.release(b)                     # step k - 2's gather read xbufs[b]
         eng.set_condition(feats, aud)
-        xbufs[b].copy_(x)
-        y = eng.sample(ops, xbufs[b], use_graph=True)
+        xbuf.copy_(x)
+        y = eng.sample(ops, xbuf, use_graph=True)
         if world > 1:
-            gatherer.start(y, b)
-            return gatherer.finish(b) if wait else None
+            y = gatherer(y)
         return y
 
     def barrier():
@@ -298,10 +295,7 @@ def run_b200(args):
     barrier()
     e0.record()
     for k in range(args.steps):
-        step(k, wait=False)
-    if world > 1:
-        gatherer.release(0)
-        gatherer.release(1)
+        step(k)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
