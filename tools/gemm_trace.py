@@ -1,6 +1,6 @@
 # per-role clock trace of one GEMM-class launch (GemmParams::trace): where a tile's time goes -- operand arrival, MMA issue,
 # accumulator completion, epilogue -- for the producer / MMA / epilogue roles of CTAs 0..3.
-# usage: python tools/gemm_trace.py M Cin N [act] [bf16_out] [dbg]                       (token linear)
+# usage: python tools/gemm_trace.py M Cin N [act] [bf16_out]                             (token linear)
 #        python tools/gemm_trace.py conv F H W Cin N dilation [act] [bf16_out] [residual] [scale] [halo]   (3x3 conv)
 import sys, ctypes, torch
 sys.path.insert(0, '.')
