@@ -260,7 +260,7 @@ def run_b200(args):
     # The gather stays in line: MapGatherer.start / finish can put it on a side stream beside the next step's loop, which
     # measured +1.7 % at N = 2 but -1.1 % at N = 8 (the NCCL kernel's CTAs take SMs from the persistent one-CTA-per-SM
     # tensor-core kernels and break up their CTA pairs) -- DESIGN.md section 7.
-    def step(k, wait=True):
+    def step(k):
         x, feats, aud = sets[k & 1]
         eng.set_condition(feats, aud)
         xbuf.copy_(x)
